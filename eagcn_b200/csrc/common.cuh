@@ -1,0 +1,124 @@
+// Shared device/host helpers for the eagcn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/eagcn_b200.h"
+
+#define EAGCN_LAUNCH_CHECK()                                  \
+  do {                                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                  \
+    if (e__ != cudaSuccess) return (int)e__;                  \
+  } while (0)
+
+#define EAGCN_TINY 1e-9f            // reference layers.py:294
+#define EAGCN_SIG_STRIDE 257        // sigma table row: [0..255] codes, [256] = sigmoid(self_r)
+#define EAGCN_NO_EDGE 255
+
+namespace eagcn {
+
+constexpr int kWarp = 32;
+constexpr int kStatRows = 64;       // rows per statistics tile (agg / bn kernels)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: the dropout keep mask is a pure function of
+// (seed, offset, element index) so backward regenerates it instead of storing it.
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// keep decision for element idx (one philox call serves 4 consecutive elements)
+__device__ __forceinline__ bool dropout_keep(const Philox& ph, uint64_t offset, uint64_t stream, uint64_t idx, float p) {
+  uint4 r = ph((idx >> 2) + offset, stream);
+  uint32_t x = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  // uniform in [0,1): keep iff u >= p
+  return (float)(x >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+struct LayerDev {                 // by-value kernel argument: per-view parameter pointers
+  int V, fin, fo_tot;
+  int fo[EAGCN_MAX_VIEWS];
+  int off[EAGCN_MAX_VIEWS + 1];
+  int chan[EAGCN_MAX_VIEWS];
+  const float* att_w[EAGCN_MAX_VIEWS];
+  const float* self_r[EAGCN_MAX_VIEWS];
+  const float* W[EAGCN_MAX_VIEWS];
+  const float* bias[EAGCN_MAX_VIEWS];
+  const float* gamma[EAGCN_MAX_VIEWS];
+  const float* beta[EAGCN_MAX_VIEWS];
+  float* run_mean[EAGCN_MAX_VIEWS];
+  float* run_var[EAGCN_MAX_VIEWS];
+  long long* nbt[EAGCN_MAX_VIEWS];
+};
+
+struct PlanDev {
+  int B, N, V, t_cap, e_cap;
+  int chan[EAGCN_MAX_VIEWS];
+  int* counts; int* deg; int* blk; int* pos_row; int* row_pos; int* row_ptr; int* mol_ptr;
+  int* col; int* colpos; int* rev;
+  uint8_t* code; uint8_t* rcode;
+};
+
+inline PlanDev to_dev(const eagcn_plan_t* p) {
+  PlanDev d;
+  d.B = (int)p->B; d.N = (int)p->N; d.V = (int)p->V; d.t_cap = (int)p->t_cap; d.e_cap = (int)p->e_cap;
+  for (int v = 0; v < EAGCN_MAX_VIEWS; ++v) d.chan[v] = (int)p->chan[v];
+  d.counts = (int*)p->counts; d.deg = (int*)p->deg; d.blk = (int*)p->blk; d.pos_row = (int*)p->pos_row;
+  d.row_pos = (int*)p->row_pos; d.row_ptr = (int*)p->row_ptr; d.mol_ptr = (int*)p->mol_ptr;
+  d.col = (int*)p->col; d.colpos = (int*)p->colpos; d.rev = (int*)p->rev;
+  d.code = (uint8_t*)p->code; d.rcode = (uint8_t*)p->rcode;
+  return d;
+}
+
+inline LayerDev to_dev(const eagcn_layer_t* l, const eagcn_plan_t* p) {
+  LayerDev d;
+  d.V = (int)l->V; d.fin = (int)l->fin; d.fo_tot = (int)l->fo_tot;
+  for (int v = 0; v < EAGCN_MAX_VIEWS; ++v) {
+    d.fo[v] = (int)l->fo[v]; d.off[v] = (int)l->off[v]; d.chan[v] = p ? (int)p->chan[v] : 0;
+    d.att_w[v] = (const float*)l->att_w[v]; d.self_r[v] = (const float*)l->self_r[v];
+    d.W[v] = (const float*)l->W[v]; d.bias[v] = (const float*)l->bias[v];
+    d.gamma[v] = (const float*)l->gamma[v]; d.beta[v] = (const float*)l->beta[v];
+    d.run_mean[v] = (float*)l->run_mean[v]; d.run_var[v] = (float*)l->run_var[v];
+    d.nbt[v] = (long long*)l->nbt[v];
+  }
+  d.off[EAGCN_MAX_VIEWS] = (int)l->off[EAGCN_MAX_VIEWS];
+  return d;
+}
+
+inline bool plan_ok(const eagcn_plan_t* p) {
+  return p && p->B > 0 && p->N > 0 && p->V > 0 && p->V <= EAGCN_MAX_VIEWS && p->t_cap > 0 &&
+         (p->t_cap % EAGCN_ROW_TILE) == 0 && p->e_cap > 0 && p->counts && p->deg && p->blk && p->pos_row &&
+         p->row_pos && p->row_ptr && p->mol_ptr && p->col && p->colpos && p->rev && p->code && p->rcode &&
+         p->B * p->N < (int64_t)2147483000;
+}
+
+inline bool plan_ok_count(const eagcn_plan_t* p) {
+  return p && p->B > 0 && p->N > 0 && p->V > 0 && p->V <= EAGCN_MAX_VIEWS && p->counts && p->deg && p->blk &&
+         p->B * p->N < (int64_t)2147483000;
+}
+
+}  // namespace eagcn

@@ -1,0 +1,336 @@
+// Backward of one GraphConv_Layer on packed rows (replaces the autograd replay of reference
+// layers.py:293-325 driven by train.py:333).  Nothing big is stored by forward except Z = H.W_all and the
+// pre-BatchNorm Y; attention weights are recomputed from the uint8 edge codes and 1/R.
+//
+//   bnbwd-partial : g = dX * dropout * relu'  ;  per-channel  S1 = sum g,  S2 = sum g*xhat   (xhat = BN-normalised Y)
+//   bnbwd-apply   : dY = gamma*invstd * (g - S1/M - xhat*S2/M)     (training; M = B*N padded positions)
+//                   dY = gamma*invstd * g                           (eval: running statistics)
+//                   Padded rows receive the constant dY_pad = -gamma*invstd*(S1/M + xhat_pad*S2/M); they only
+//                   feed d(bias), and sum over ALL positions of dY is identically 0 in training, so
+//                   d(bias) = 0 there (the reference's autograd returns rounding noise around 0).
+//   agg-bwd       : with Y_v[i] = sum_j A_v[i,j] Z_v[j] + b,  A = U/R:
+//                     dU[i,j]  = dY_v[i].(Z_v[j] - (Y_v[i]-b)) / R_i       (quotient rule; sum_j A[i,j] Z[j] = Y-b)
+//                     d a_v[c] = sum_{edges of type c} dU * s(1-s),   d r_v = sum_i dU[i,i] * s_r(1-s_r)
+//                     Q_v[j]   = sum_i A_v[i,j] dY_v[i]   (transposed aggregation through the reverse-edge codes)
+//   gemm          : dH = Q . W_all^T ,  dW_all = H^T . Q   (split-K, fixed-order reduction)
+#include "common.cuh"
+
+namespace eagcn {
+
+int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
+            const int* Mdev, cudaStream_t st);
+int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, int N, int Kcap, const int* Kdev,
+            float* ws, long long ws_floats, cudaStream_t st);
+long long gemm_tn_workspace_floats(int M, int N, int Kcap);
+bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l);
+__global__ void stat_reduce_kernel(PlanDev p, const float* __restrict__ partial, double* __restrict__ sums, int C);
+
+template <int VEC>
+__device__ __forceinline__ void ld4(const float* __restrict__ row, int q, int lane, int lim, float (&o)[4]) {
+  if (VEC == 4) {
+    const int c = q * 128 + lane * 4;
+    if (c < lim) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(row + c));
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else { o[0] = o[1] = o[2] = o[3] = 0.0f; }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = q * 128 + u * 32 + lane; o[u] = c < lim ? __ldg(row + c) : 0.0f; }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void st4(float* __restrict__ row, int q, int lane, int lim, const float (&o)[4]) {
+  if (VEC == 4) {
+    const int c = q * 128 + lane * 4;
+    if (c < lim) *reinterpret_cast<float4*>(row + c) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = q * 128 + u * 32 + lane; if (c < lim) row[c] = o[u]; }
+  }
+}
+
+// g for one element (shared by partial / apply): dX * keep/(1-p) * [BN output > 0]
+__device__ __forceinline__ float grad_through_act(float dx, float y, float mean, float invstd, float gamma, float beta,
+                                                  int training, float p_drop, const unsigned long long* rng,
+                                                  unsigned long long stream, unsigned long long idx, float& xhat) {
+  xhat = (y - mean) * invstd;
+  const float z = xhat * gamma + beta;
+  float g = z > 0.0f ? dx : 0.0f;
+  if (training && p_drop > 0.0f) {
+    const Philox ph(rng[0]);
+    g = dropout_keep(ph, rng[1], stream, idx, p_drop) ? g * (1.0f / (1.0f - p_drop)) : 0.0f;
+  }
+  return g;
+}
+
+// grid (row tiles, ceil(C/128)); thread -> channel, 64 rows serial per 2 half-tiles
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(PlanDev p, const float* __restrict__ dX,
+                                                             const float* __restrict__ Y, const float* __restrict__ ball,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             float* __restrict__ partial, int C, int training, float p_drop,
+                                                             const unsigned long long* rng, unsigned long long stream) {
+  __shared__ float s[2][2][128];
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int tile = blockIdx.x;
+  if (tile * kStatRows >= T) return;
+  const int cl = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + cl;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    const float mu = mean[c], is = invstd[c], g_ = ball[C + c], b_ = ball[2 * C + c];
+    const int r0 = tile * kStatRows + half * (kStatRows / 2);
+    const int r1 = min(T, r0 + kStatRows / 2);
+    for (int t = r0; t < r1; ++t) {
+      const long long idx = (long long)t * C + c;
+      float xh;
+      const float g = grad_through_act(dX[idx], Y[idx], mu, is, g_, b_, training, p_drop, rng, stream,
+                                       (unsigned long long)idx, xh);
+      s1 += g; s2 = fmaf(g, xh, s2);
+    }
+  }
+  s[half][0][cl] = s1; s[half][1][cl] = s2;
+  __syncthreads();
+  if (half == 0 && c < C) {
+    partial[((size_t)tile * 2 + 0) * C + c] = s[0][0][cl] + s[1][0][cl];
+    partial[((size_t)tile * 2 + 1) * C + c] = s[0][1][cl] + s[1][1][cl];
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(PlanDev p, const float* __restrict__ dX,
+                                                           const float* __restrict__ Y, const float* __restrict__ ball,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const double* __restrict__ bsums, float* __restrict__ dY, int C,
+                                                           int training, float p_drop, const unsigned long long* rng,
+                                                           unsigned long long stream, double M) {
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)p.t_cap * C) return;
+  const int t = (int)(idx / C), c = (int)(idx - (long long)t * C);
+  if (t >= T) { dY[idx] = 0.0f; return; }
+  float xh;
+  const float gam = ball[C + c];
+  const float g = grad_through_act(dX[idx], Y[idx], mean[c], invstd[c], gam, ball[2 * C + c], training, p_drop, rng,
+                                   stream, (unsigned long long)idx, xh);
+  float r = g;
+  if (training) r = g - (float)(bsums[c] / M) - xh * (float)(bsums[C + c] / M);
+  dY[idx] = gam * invstd[c] * r;
+}
+
+// dvec = [dbias | dgamma | dbeta]
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ ball, const float* __restrict__ invstd,
+                                                              const double* __restrict__ bsums, float* __restrict__ dvec,
+                                                              int C, int training) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = bsums[c], s2 = bsums[C + c];
+  dvec[c] = training ? 0.0f : (float)((double)ball[C + c] * (double)invstd[c] * s1);
+  dvec[C + c] = (float)s2;
+  dvec[2 * C + c] = (float)s1;
+}
+
+// grid (row tiles, V); 8 warps x 8 rows.  Fo_v handled in super-chunks of 512 channels (4 x 128).
+template <int VEC>
+__global__ void __launch_bounds__(256) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+                                                      const float* __restrict__ Y, const float* __restrict__ dY,
+                                                      const float* __restrict__ ball, const float* __restrict__ sig,
+                                                      const float* __restrict__ invR, float* __restrict__ Q,
+                                                      float* __restrict__ dpart) {
+  __shared__ float s_hist[8][EAGCN_SIG_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.y, tile = blockIdx.x;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  if (tile * kStatRows >= T) return;
+  for (int i = threadIdx.x; i < 8 * EAGCN_SIG_STRIDE; i += 256) (&s_hist[0][0])[i] = 0.0f;
+  __syncthreads();
+  const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot;
+  const float* sg = sig + v * EAGCN_SIG_STRIDE;
+  const float sig_r = sg[256];
+  const uint8_t* code = p.code + (size_t)v * p.e_cap;
+  const uint8_t* rcode = p.rcode + (size_t)v * p.e_cap;
+  const float* iR = invR + (size_t)v * p.t_cap;
+  const int nsc = (fo + 511) / 512;
+  for (int r = 0; r < 8; ++r) {
+    const int t = tile * kStatRows + warp * 8 + r;
+    if (t >= T) break;
+    const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
+    const float invR_t = iR[t];
+    const float* dYt = dY + (size_t)t * ld + off;
+    // ---- c_t = dY_t . (Y_t - b),  d_self = dY_t . Z_t   (full Fo_v dots) ----
+    float ct = 0.f, dself = 0.f;
+    for (int q = 0; q < (fo + 127) / 128; ++q) {
+      float a[4], y[4], b[4], z[4];
+      ld4<VEC>(dYt, q, lane, fo, a);
+      ld4<VEC>(Y + (size_t)t * ld + off, q, lane, fo, y);
+      ld4<VEC>(ball + off, q, lane, fo, b);
+      ld4<VEC>(Z + (size_t)t * ld + off, q, lane, fo, z);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { ct = fmaf(a[u], y[u] - b[u], ct); dself = fmaf(a[u], z[u], dself); }
+    }
+    ct = warp_sum(ct); dself = warp_sum(dself);
+    if (lane == 0) s_hist[warp][256] += (dself - ct) * invR_t * sig_r * (1.0f - sig_r);
+    const float a_self = sig_r * invR_t;
+    // ---- edges, 32 at a time ----
+    for (int eb = e0; eb < e1; eb += 32) {   // active rows have deg >= 1
+      const int e = eb + lane;
+      int j_e = 0, c_e = 0; float aq_e = 0.f, s_e = 0.f, d_e = 0.f;
+      if (e < e1) {
+        j_e = p.col[e]; c_e = code[e];
+        s_e = sg[c_e];
+        aq_e = sg[rcode[e]] * iR[j_e];               // A_v[j -> t]: edge (j,t) has type rcode, row sum R_j
+      }
+      const int cnt = min(32, e1 - eb);
+      for (int sc = 0; sc < nsc; ++sc) {
+        float dyt[4][4], qacc[4][4];
+        const int nq = min(4, (fo - sc * 512 + 127) / 128);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          if (qq < nq) {
+            ld4<VEC>(dYt, sc * 4 + qq, lane, fo, dyt[qq]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qacc[qq][u] = 0.0f;
+          }
+        }
+        for (int k = 0; k < cnt; ++k) {
+          const int j = __shfl_sync(0xffffffffu, j_e, k);
+          const float aq = __shfl_sync(0xffffffffu, aq_e, k);
+          float dot = 0.0f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            if (qq < nq) {
+              float zj[4], gj[4];
+              ld4<VEC>(Z + (size_t)j * ld + off, sc * 4 + qq, lane, fo, zj);
+              ld4<VEC>(dY + (size_t)j * ld + off, sc * 4 + qq, lane, fo, gj);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { dot = fmaf(dyt[qq][u], zj[u], dot); qacc[qq][u] = fmaf(aq, gj[u], qacc[qq][u]); }
+            }
+          }
+          dot = warp_sum(dot);
+          if (lane == k) d_e += dot;
+        }
+        // Q rows: first edge chunk initialises with the self term, later chunks accumulate
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          if (qq < nq) {
+            float* qrow = Q + (size_t)t * ld + off;
+            float base[4];
+            if (eb == e0) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) base[u] = a_self * dyt[qq][u];
+            } else {
+              ld4<VEC>(qrow, sc * 4 + qq, lane, fo, base);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) base[u] += qacc[qq][u];
+            st4<VEC>(qrow, sc * 4 + qq, lane, fo, base);
+          }
+        }
+      }
+      // attention-logit gradients of this chunk's edges, serialised -> deterministic
+      const float ds_e = (d_e - ct) * invR_t * s_e * (1.0f - s_e);
+      for (int k = 0; k < cnt; ++k) {
+        const float dsk = __shfl_sync(0xffffffffu, ds_e, k);
+        const int ck = __shfl_sync(0xffffffffu, c_e, k);
+        if (lane == 0) s_hist[warp][ck] += dsk;
+      }
+    }
+  }
+  __syncthreads();
+  float* out = dpart + ((size_t)tile * L.V + v) * EAGCN_SIG_STRIDE;
+  for (int i = threadIdx.x; i < EAGCN_SIG_STRIDE; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += s_hist[w][i];
+    out[i] = a;
+  }
+}
+
+// datt[v][i] = sum over live tiles (fixed order)
+__global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float* __restrict__ dpart,
+                                                          float* __restrict__ datt, int V) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= V * EAGCN_SIG_STRIDE) return;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int ntile = (T + kStatRows - 1) / kStatRows;
+  double a = 0.0;
+  for (int t = 0; t < ntile; ++t) a += (double)dpart[(size_t)t * V * EAGCN_SIG_STRIDE + i];
+  datt[i] = (float)a;
+}
+
+static bool vec4_ok_b(const eagcn_layer_t* l) {
+  if (l->fo_tot % 4) return false;
+  for (int v = 0; v < l->V; ++v) if ((l->fo[v] % 4) || (l->off[v] % 4)) return false;
+  return true;
+}
+
+}  // namespace eagcn
+using namespace eagcn;
+
+extern "C" int64_t eagcn_gemm_workspace_bytes(int64_t fin, int64_t fo_tot, int64_t t_cap) {
+  return gemm_tn_workspace_floats((int)fin, (int)fo_tot, (int)t_cap) * (int64_t)sizeof(float);
+}
+extern "C" int64_t eagcn_partial_floats(int64_t t_cap, int64_t fo_tot, int64_t V) {
+  const int64_t tiles = eagcn_stat_tiles(t_cap);
+  const int64_t a = tiles * 2 * fo_tot, b = tiles * V * EAGCN_SIG_STRIDE;
+  return a > b ? a : b;
+}
+
+extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w,
+                                      void* stream) {
+  if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
+  if (!w->dX || !w->Y || !w->ball || !w->mean || !w->invstd || !w->partial || !w->bsums) return EAGCN_E_ARG;
+  if (w->training && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanDev p = to_dev(plan);
+  const int C = (int)layer->fo_tot;
+  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
+  bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+                                              (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
+                                              w->training ? 1 : 0, (float)w->p_drop,
+                                              (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
+  EAGCN_LAUNCH_CHECK();
+  stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->bsums, C);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w,
+                                      void* stream) {
+  if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
+  if (!w->dX || !w->Y || !w->Z || !w->H || !w->ball || !w->mean || !w->invstd || !w->partial || !w->bsums || !w->dY ||
+      !w->Q || !w->dH || !w->dwall || !w->dvec || !w->datt || !w->wall || !w->sig || !w->invR || !w->gemm_ws)
+    return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanDev p = to_dev(plan);
+  LayerDev L = to_dev(layer, plan);
+  const int C = L.fo_tot;
+  const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
+  const long long total = (long long)p.t_cap * C;
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
+      (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
+      (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
+  EAGCN_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
+                                                          (const double*)w->bsums, (float*)w->dvec, C,
+                                                          w->training ? 1 : 0);
+  EAGCN_LAUNCH_CHECK();
+  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
+  if (vec4_ok_b(layer))
+    agg_bwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+                                            (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
+                                            (float*)w->Q, (float*)w->partial);
+  else
+    agg_bwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+                                            (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
+                                            (float*)w->Q, (float*)w->partial);
+  EAGCN_LAUNCH_CHECK();
+  datt_reduce_kernel<<<(L.V * EAGCN_SIG_STRIDE + 255) / 256, 256, 0, st>>>(p, (const float*)w->partial, (float*)w->datt,
+                                                                           L.V);
+  EAGCN_LAUNCH_CHECK();
+  int rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
+                   p.counts + EAGCN_CNT_T, st);
+  if (rc) return rc;
+  rc = gemm_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->dwall, L.fin, C, p.t_cap,
+               p.counts + EAGCN_CNT_T, (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st);
+  return rc;
+}

@@ -1,0 +1,338 @@
+// Forward of one GraphConv_Layer (reference layers.py:293-325, structure 'Concate') on packed rows.
+//
+//   prep   : W_all = [W_1 | ... | W_V] (fin x fo_tot), bias/gamma/beta vectors, sigmoid(att) tables
+//   gemm   : Z = H . W_all                       (layers.py:40; reassociated: A_v (H W_v) == (A_v H) W_v)
+//   agg    : per row i, view v -- one warp per row:
+//              w_e  = sigmoid(a_v[code_v(e)])                         layers.py:82-83 (1x1 conv == lookup)
+//              R    = sum_e w_e + sigmoid(r_v) + (N - deg_i) * 1e-9   layers.py:84,87  (self loop + tiny)
+//              Y_v  = sum_e (w_e/R) Z_v[j_e] + (sigmoid(r_v)/R) Z_v[i] + b_v      layers.py:90,39,43
+//            + per-channel sum / sum-of-squares of (Y - b) for BatchNorm (warp-shuffle row reductions,
+//              fixed-order cross-warp / cross-tile reduction -> deterministic)
+//   bn     : statistics over ALL B*N padded positions (layers.py:408-412): the (B*N - T) rows that are
+//            padding / bond-less hold exactly Y = b, so they add 0 to both centred sums and only enter
+//            through the population size M.  Running stats updated like nn.BatchNorm1d.
+//   apply  : X = dropout(relu(BN(Y)))            (layers.py:93-94), rows ordered as the concat of
+//            layers.py:313; padded rows are never materialised here (rows_scatter writes their zeros).
+//
+// The 1e-9 "mask_tiny" weights stay in the normaliser R; their contribution to the aggregate
+// (<= N*1e-9*|H|, measured <= 1.2e-7 absolute) is below fp32 resolution of the
+// reference's own summation and is not materialised.
+#include "common.cuh"
+
+namespace eagcn {
+
+int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
+            const int* Mdev, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __restrict__ wall,
+                                                          float* __restrict__ ball, float* __restrict__ sig) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long nW = (long long)L.fin * L.fo_tot;
+  if (idx < nW) {
+    const int k = (int)(idx / L.fo_tot), c = (int)(idx - (long long)k * L.fo_tot);
+    int v = 0;
+    while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+    wall[idx] = __ldg(L.W[v] + (long long)k * L.fo[v] + (c - L.off[v]));
+  }
+  if (idx < L.fo_tot) {
+    const int c = (int)idx;
+    int v = 0;
+    while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+    const int cc = c - L.off[v];
+    ball[c] = L.bias[v][cc];
+    ball[L.fo_tot + c] = L.gamma[v][cc];
+    ball[2 * L.fo_tot + c] = L.beta[v][cc];
+    ball[3 * L.fo_tot + c] = 0.0f;
+  }
+  if (idx < (long long)L.V * EAGCN_SIG_STRIDE) {
+    const int v = (int)(idx / EAGCN_SIG_STRIDE), c = (int)(idx - (long long)v * EAGCN_SIG_STRIDE);
+    float s = 0.5f;                                   // code == C_v (all-zero relation vector): sigmoid(0)
+    if (c < L.chan[v]) s = sigmoidf_(L.att_w[v][c]);
+    if (c == 256) s = sigmoidf_(L.self_r[v][0]);
+    sig[idx] = s;
+  }
+}
+
+// lane <-> channel mapping of one 128-channel chunk q: VEC=4 -> lane*4+u (float4), VEC=1 -> u*32+lane
+template <int VEC>
+__device__ __forceinline__ int chan_of(int q, int lane, int u) {
+  return VEC == 4 ? q * 128 + lane * 4 + u : q * 128 + u * 32 + lane;
+}
+template <int VEC>
+__device__ __forceinline__ void load4(const float* __restrict__ row, int q, int lane, int lim, float (&o)[4]) {
+  if (VEC == 4) {
+    const int c = q * 128 + lane * 4;
+    if (c < lim) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(row + c));
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else { o[0] = o[1] = o[2] = o[3] = 0.0f; }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = q * 128 + u * 32 + lane; o[u] = c < lim ? __ldg(row + c) : 0.0f; }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store4(float* __restrict__ row, int q, int lane, int lim, const float (&o)[4]) {
+  if (VEC == 4) {
+    const int c = q * 128 + lane * 4;
+    if (c < lim) *reinterpret_cast<float4*>(row + c) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = q * 128 + u * 32 + lane; if (c < lim) row[c] = o[u]; }
+  }
+}
+
+// grid (row tiles of kStatRows, V).  8 warps x 8 rows.
+template <int VEC>
+__global__ void __launch_bounds__(256) agg_fwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+                                                      const float* __restrict__ ball, const float* __restrict__ sig,
+                                                      float* __restrict__ Y, float* __restrict__ invR,
+                                                      float* __restrict__ partial, int n_pad, int want_stats) {
+  __shared__ float s_red[8][2][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.y;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int tile = blockIdx.x;
+  if (tile * kStatRows >= T) return;
+  const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot;
+  const float* sg = sig + v * EAGCN_SIG_STRIDE;
+  const float sig_r = sg[256];
+  const uint8_t* code = p.code + (size_t)v * p.e_cap;
+  const int nq = (fo + 127) / 128;
+  for (int q = 0; q < nq; ++q) {
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float bias4[4];
+    load4<VEC>(ball + off, q, lane, fo, bias4);
+    for (int r = 0; r < 8; ++r) {
+      const int t = tile * kStatRows + warp * 8 + r;
+      if (t >= T) break;
+      const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
+      const int deg = e1 - e0;
+      // ---- attention row sum (layers.py:84,87) ----
+      float sw = 0.0f;
+      for (int e = e0 + lane; e < e1; e += 32) sw += sg[code[e]];
+      sw = warp_sum(sw);
+      const float R = sw + sig_r + (float)(n_pad - deg) * EAGCN_TINY;
+      if (q == 0 && lane == 0) invR[(size_t)v * p.t_cap + t] = 1.0f / R;
+      // ---- aggregate (layers.py:90,39) ----
+      float acc[4], zi[4];
+      load4<VEC>(Z + (size_t)t * ld + off, q, lane, fo, zi);
+      const float a_self = sig_r / R;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = a_self * zi[u];
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        float a_e = 0.0f; int j_e = 0;
+        if (e < e1) { a_e = sg[code[e]] / R; j_e = p.col[e]; }
+        const int cnt = min(32, e1 - eb);
+        for (int k = 0; k < cnt; ++k) {
+          const float a = __shfl_sync(0xffffffffu, a_e, k);
+          const int j = __shfl_sync(0xffffffffu, j_e, k);
+          float zj[4];
+          load4<VEC>(Z + (size_t)j * ld + off, q, lane, fo, zj);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fmaf(a, zj[u], acc[u]);
+        }
+      }
+      float y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { y[u] = acc[u] + bias4[u]; s1[u] += acc[u]; s2[u] = fmaf(acc[u], acc[u], s2[u]); }
+      store4<VEC>(Y + (size_t)t * ld + off, q, lane, fo, y);
+    }
+    if (want_stats) {
+      // cross-warp reduction in fixed order
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cl = VEC == 4 ? lane * 4 + u : u * 32 + lane;
+        s_red[warp][0][cl] = s1[u]; s_red[warp][1][cl] = s2[u];
+      }
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        const int c = q * 128 + threadIdx.x;
+        if (c < fo) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { a += s_red[w][0][threadIdx.x]; b += s_red[w][1][threadIdx.x]; }
+          partial[((size_t)tile * 2 + 0) * ld + off + c] = a;
+          partial[((size_t)tile * 2 + 1) * ld + off + c] = b;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// sums[k][c] = sum over live tiles of partial[tile][k][c]   (double, fixed order)
+__global__ void __launch_bounds__(256) stat_reduce_kernel(PlanDev p, const float* __restrict__ partial,
+                                                          double* __restrict__ sums, int C) {
+  __shared__ double s[8][2][32];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int ntile = (T + kStatRows - 1) / kStatRows;
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int t = ty; t < ntile; t += 8) {
+      a += (double)partial[((size_t)t * 2 + 0) * C + c];
+      b += (double)partial[((size_t)t * 2 + 1) * C + c];
+    }
+  s[ty][0][cx] = a; s[ty][1][cx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double aa = 0.0, bb = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { aa += s[w][0][cx]; bb += s[w][1][cx]; }
+    sums[c] = aa; sums[C + c] = bb;
+  }
+}
+
+// BatchNorm finalize: batch statistics over M = B*N padded positions (training) or running stats.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(LayerDev L, const float* __restrict__ ball,
+                                                          const double* __restrict__ sums, float* __restrict__ mean,
+                                                          float* __restrict__ invstd, int training, double M,
+                                                          double eps, double momentum) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= L.fo_tot) return;
+  int v = 0;
+  while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+  const int cc = c - L.off[v];
+  if (training) {
+    const double b = (double)ball[c];
+    const double m1 = sums[c] / M;                       // mean of (Y - b) over all positions
+    double var = sums[L.fo_tot + c] / M - m1 * m1;       // biased variance (shift-invariant)
+    if (var < 0.0) var = 0.0;
+    const double mu = b + m1;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + eps));
+    const double unb = M > 1.0 ? var * (M / (M - 1.0)) : var;
+    L.run_mean[v][cc] = (float)((1.0 - momentum) * (double)L.run_mean[v][cc] + momentum * mu);
+    L.run_var[v][cc] = (float)((1.0 - momentum) * (double)L.run_var[v][cc] + momentum * unb);
+    if (cc == 0 && L.nbt[v]) L.nbt[v][0] += 1;
+  } else {
+    mean[c] = L.run_mean[v][cc];
+    invstd[c] = 1.0f / sqrtf(L.run_var[v][cc] + (float)eps);
+  }
+}
+
+// X = dropout(relu((Y - mean) * invstd * gamma + beta)); one thread per 4 channels (scalar tail-safe)
+__global__ void __launch_bounds__(256) bn_apply_kernel(PlanDev p, const float* __restrict__ Y,
+                                                       const float* __restrict__ ball, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, float* __restrict__ X, int C,
+                                                       int training, float p_drop, const unsigned long long* rng,
+                                                       unsigned long long rng_stream) {
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // one element per thread
+  const long long total = (long long)p.t_cap * C;
+  if (idx >= total) return;
+  const int t = (int)(idx / C), c = (int)(idx - (long long)t * C);
+  if (t >= T) { X[idx] = 0.0f; return; }
+  const float g = ball[C + c], b = ball[2 * C + c];
+  float x = (Y[idx] - mean[c]) * invstd[c] * g + b;
+  x = fmaxf(x, 0.0f);
+  if (training && p_drop > 0.0f) {
+    const Philox ph(rng[0]);
+    x = dropout_keep(ph, rng[1], rng_stream, (unsigned long long)idx, p_drop) ? x * (1.0f / (1.0f - p_drop)) : 0.0f;
+  }
+  X[idx] = x;
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(long long total, float p_drop,
+                                                           const unsigned long long* rng, unsigned long long rng_stream,
+                                                           uint8_t* __restrict__ keep) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const Philox ph(rng[0]);
+  keep[idx] = dropout_keep(ph, rng[1], rng_stream, (unsigned long long)idx, p_drop) ? 1 : 0;
+}
+
+static bool vec4_ok(const eagcn_layer_t* l) {
+  if (l->fo_tot % 4) return false;
+  for (int v = 0; v < l->V; ++v) if ((l->fo[v] % 4) || (l->off[v] % 4)) return false;
+  return true;
+}
+
+bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l) {
+  if (!l || l->V != plan->V || l->fin <= 0 || l->fo_tot <= 0) return false;
+  long long s = 0;
+  for (int v = 0; v < l->V; ++v) {
+    if (l->fo[v] <= 0 || l->off[v] != s) return false;
+    s += l->fo[v];
+    if (!l->att_w[v] || !l->self_r[v] || !l->W[v] || !l->bias[v] || !l->gamma[v] || !l->beta[v] || !l->run_mean[v] ||
+        !l->run_var[v])
+      return false;
+    if (plan->chan[v] > 254) return false;
+  }
+  return s == l->fo_tot;
+}
+
+}  // namespace eagcn
+using namespace eagcn;
+
+extern "C" int64_t eagcn_stat_tiles(int64_t t_cap) { return (t_cap + kStatRows - 1) / kStatRows; }
+
+extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w,
+                                     void* stream) {
+  if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
+  if (!w->H || !w->Z || !w->Y || !w->invR || !w->wall || !w->ball || !w->sig || !w->partial || !w->sums)
+    return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanDev p = to_dev(plan);
+  LayerDev L = to_dev(layer, plan);
+  const int C = L.fo_tot;
+  long long n = (long long)L.fin * C;
+  if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
+  if (n < C) n = C;
+  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->ball, (float*)w->sig);
+  EAGCN_LAUNCH_CHECK();
+  int rc = gemm_nn((const float*)w->H, L.fin, (const float*)w->wall, C, (float*)w->Z, C, p.t_cap, C, L.fin,
+                   p.counts + EAGCN_CNT_T, st);
+  if (rc) return rc;
+  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
+  const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);
+  const int want = w->training ? 1 : 0;
+  if (vec4_ok(layer))
+    agg_fwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+                                            (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
+  else
+    agg_fwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+                                            (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
+  EAGCN_LAUNCH_CHECK();
+  if (want) {
+    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->sums, C);
+    EAGCN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w,
+                                     void* stream) {
+  if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
+  if (!w->Y || !w->X || !w->ball || !w->sums || !w->mean || !w->invstd) return EAGCN_E_ARG;
+  if (w->training && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
+  if (w->p_drop < 0.0 || w->p_drop >= 1.0) return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanDev p = to_dev(plan);
+  LayerDev L = to_dev(layer, plan);
+  const int C = L.fo_tot;
+  const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
+                                                      (float*)w->invstd, w->training ? 1 : 0, M, w->eps, w->momentum);
+  EAGCN_LAUNCH_CHECK();
+  const long long total = (long long)p.t_cap * C;
+  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
+      w->training ? 1 : 0, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out,
+                                  void* stream) {
+  if (!plan_ok(plan) || !w || !w->rng || !keep_out || fo_tot <= 0) return EAGCN_E_ARG;
+  const long long total = (long long)plan->t_cap * fo_tot;
+  dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      total, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, (uint8_t*)keep_out);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}

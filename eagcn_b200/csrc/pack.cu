@@ -1,0 +1,305 @@
+// Graph-plan construction: padded dense batch -> packed active rows + CSR edges + uint8 edge codes.
+//
+// Replaces, once per batch and for all layers (forward and backward), what the reference rebuilds
+// inside every GraphConv_Layer.forward call: mask_blank / identity (layers.py:294-304) and the
+// 1x1-conv attention-score input (layers.py:82), whose one-hot planes [B,C_v,N,N] collapse to one
+// uint8 code per directed edge and view (the conv over a one-hot vector is a table lookup).
+// The one-hot planes are only *gathered at bonded pairs* (adj != 0); the off-graph zeros of the
+// 4*(Kb+10)*N^2 bytes per molecule are never read -- they are multiplied by adj == 0 in the
+// reference (layers.py:83) and cannot influence the result.
+//
+// Four small kernels, no host synchronisation, deterministic output order (rows ascending by
+// flat position, neighbours ascending by column):
+//   count : one warp per padded row -> degree; per-CTA (active rows, edges) totals
+//   scan  : single CTA exclusive scan of the per-CTA totals -> T, E
+//   fill  : row numbering, CSR offsets, neighbour positions, per-view codes (validated one-hot)
+//   link  : neighbour row ids, reverse-edge index (validates symmetry), reverse codes
+#include "common.cuh"
+
+namespace eagcn {
+
+constexpr int kPackRows = 64;      // padded rows per CTA
+constexpr int kPackThreads = 256;  // 8 warps x 8 rows
+
+struct RelPtrs { const float* p[EAGCN_MAX_VIEWS]; };
+
+template <bool kCodes>
+__device__ __forceinline__ bool edge_at(const float* adj, const uint8_t* codes, const PlanDev& p, int b, int i, int j,
+                                         bool& bad) {
+  if (kCodes) {
+    return codes[(((size_t)b * p.V + 0) * p.N + i) * p.N + j] != EAGCN_NO_EDGE;
+  } else {
+    float a = adj[((size_t)b * p.N + i) * p.N + j];
+    if (a != 0.0f && a != 1.0f) bad = true;
+    return a != 0.0f;
+  }
+}
+
+template <bool kCodes>
+__global__ void __launch_bounds__(kPackThreads) pack_count_kernel(PlanDev p, const float* __restrict__ adj,
+                                                                  const uint8_t* __restrict__ codes) {
+  __shared__ int s_deg[kPackRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.B * p.N;
+  bool bad = false;
+  for (int r = 0; r < 8; ++r) {
+    const int lr = warp * 8 + r;
+    const int row = blockIdx.x * kPackRows + lr;
+    int cnt = 0;
+    if (row < P) {
+      const int b = row / p.N, i = row - b * p.N;
+      for (int j0 = 0; j0 < p.N; j0 += 32) {
+        const int j = j0 + lane;
+        bool nz = (j < p.N) && edge_at<kCodes>(adj, codes, p, b, i, j, bad);
+        cnt += __popc(__ballot_sync(0xffffffffu, nz));
+      }
+      if (lane == 0) p.deg[row] = cnt;
+    }
+    if (lane == 0) s_deg[lr] = cnt;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_ADJ_NOT_01);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int na = 0, ne = 0;
+    for (int r = 0; r < kPackRows; ++r) { na += s_deg[r] > 0; ne += s_deg[r]; }
+    p.blk[2 * blockIdx.x] = na;
+    p.blk[2 * blockIdx.x + 1] = ne;
+  }
+}
+
+// single CTA: exclusive scan (in place) of blk[2*i], blk[2*i+1]; totals -> counts
+__global__ void __launch_bounds__(1024) pack_scan_kernel(PlanDev p, int nblk) {
+  __shared__ int s_a[1024], s_e[1024];
+  const int tid = threadIdx.x;
+  const int per = (nblk + 1023) / 1024;
+  const int lo = tid * per, hi = min(nblk, lo + per);
+  int sa = 0, se = 0;
+  for (int i = lo; i < hi; ++i) { sa += p.blk[2 * i]; se += p.blk[2 * i + 1]; }
+  s_a[tid] = sa; s_e[tid] = se;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {           // Hillis-Steele inclusive scan
+    int va = 0, ve = 0;
+    if (tid >= o) { va = s_a[tid - o]; ve = s_e[tid - o]; }
+    __syncthreads();
+    s_a[tid] += va; s_e[tid] += ve;
+    __syncthreads();
+  }
+  int ra = s_a[tid] - sa, re = s_e[tid] - se;     // exclusive prefix of this thread's chunk
+  for (int i = lo; i < hi; ++i) {
+    int a = p.blk[2 * i], e = p.blk[2 * i + 1];
+    p.blk[2 * i] = ra; p.blk[2 * i + 1] = re;
+    ra += a; re += e;
+  }
+  if (tid == 1023) {
+    const int T = s_a[1023], E = s_e[1023];
+    p.counts[EAGCN_CNT_T] = T;
+    p.counts[EAGCN_CNT_E] = E;
+    int st = 0;
+    if (T > p.t_cap) st |= EAGCN_ST_ROW_CAP;
+    if (E > p.e_cap) st |= EAGCN_ST_EDGE_CAP;
+    if (st) atomicOr(&p.counts[EAGCN_CNT_STATUS], st);
+  }
+}
+
+template <bool kCodes>
+__global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, const float* __restrict__ adj,
+                                                                 const uint8_t* __restrict__ codes, RelPtrs rel) {
+  __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.B * p.N;
+  const int row0 = blockIdx.x * kPackRows;
+  if (threadIdx.x < kPackRows) {
+    const int row = row0 + threadIdx.x;
+    s_deg[threadIdx.x] = row < P ? p.deg[row] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = p.blk[2 * blockIdx.x], e = p.blk[2 * blockIdx.x + 1];
+    for (int r = 0; r < kPackRows; ++r) {
+      s_t[r] = t; s_e[r] = e;
+      t += s_deg[r] > 0; e += s_deg[r];
+    }
+  }
+  __syncthreads();
+  const int T = p.counts[EAGCN_CNT_T], E = p.counts[EAGCN_CNT_E];
+  if (threadIdx.x < kPackRows) {
+    const int row = row0 + threadIdx.x;
+    if (row < P) {
+      const bool act = s_deg[threadIdx.x] > 0;
+      const int t = s_t[threadIdx.x];
+      p.pos_row[row] = (act && t < p.t_cap) ? t : -1;
+      if (act && t < p.t_cap) { p.row_pos[t] = row; p.row_ptr[t] = s_e[threadIdx.x]; }
+      if (row % p.N == 0) p.mol_ptr[row / p.N] = min(t, p.t_cap);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.mol_ptr[p.B] = min(T, p.t_cap);
+    if (T <= p.t_cap) p.row_ptr[T] = E;
+  }
+  bool bad = false;
+  for (int r = 0; r < 8; ++r) {
+    const int lr = warp * 8 + r;
+    const int row = row0 + lr;
+    if (row >= P) break;
+    const int deg = s_deg[lr];
+    if (deg == 0 || s_t[lr] >= p.t_cap) continue;
+    const int e0 = s_e[lr];
+    if (e0 + deg > p.e_cap) continue;            // status already flagged by the scan
+    const int b = row / p.N, i = row - b * p.N;
+    int run = 0;
+    for (int j0 = 0; j0 < p.N; j0 += 32) {
+      const int j = j0 + lane;
+      bool dummy = false;
+      const bool nz = (j < p.N) && edge_at<kCodes>(adj, codes, p, b, i, j, dummy);
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (m == 0) continue;
+      const int e = e0 + run + __popc(m & ((1u << lane) - 1u));
+      if (nz) p.colpos[e] = b * p.N + j;
+      for (int v = 0; v < p.V; ++v) {
+        const int C = p.chan[v];
+        int found = C;
+        if (nz) {
+          if (kCodes) {
+            const int c = codes[(((size_t)b * p.V + v) * p.N + i) * p.N + j];
+            if (c > C) bad = true; else found = c;
+          } else {
+            const float* base = rel.p[v] + (((size_t)b * C) * p.N + i) * p.N + j;
+            int cnt = 0;
+            for (int c = 0; c < C; ++c) {
+              const float x = __ldg(base + (size_t)c * p.N * p.N);
+              if (x != 0.0f) { ++cnt; found = c; if (x != 1.0f) bad = true; }
+            }
+            if (cnt > 1) bad = true;
+          }
+          p.code[(size_t)v * p.e_cap + e] = (uint8_t)found;
+        }
+      }
+      run += __popc(m);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_NOT_ONEHOT);
+}
+
+// one warp per active row: neighbour row ids, reverse edge (binary search), reverse codes
+__global__ void __launch_bounds__(256) pack_link_kernel(PlanDev p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  if (t >= T) return;
+  const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
+  if (e1 > p.e_cap) return;
+  const int mypos = p.row_pos[t];
+  bool asym = false;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int jpos = p.colpos[e];
+    const int jr = p.pos_row[jpos];
+    int re = e, jcol = t;
+    if (jr < 0) {
+      asym = true;
+    } else {
+      jcol = jr;
+      int lo = p.row_ptr[jr], hi = p.row_ptr[jr + 1];
+      if (hi > p.e_cap) { asym = true; hi = lo; }
+      int found = -1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int c = p.colpos[mid];
+        if (c == mypos) { found = mid; break; }
+        if (c < mypos) lo = mid + 1; else hi = mid;
+      }
+      if (found < 0) asym = true; else re = found;
+    }
+    p.col[e] = jcol;
+    p.rev[e] = re;
+    for (int v = 0; v < p.V; ++v) p.rcode[(size_t)v * p.e_cap + e] = p.code[(size_t)v * p.e_cap + re];
+  }
+  if (__any_sync(0xffffffffu, asym) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_ASYMMETRIC);
+}
+
+// inverse of the packing for one view (parity check: indexing must round-trip bit-exactly)
+__global__ void __launch_bounds__(256) unpack_view_kernel(PlanDev p, int v, float* __restrict__ rel_out,
+                                                          float* __restrict__ adj_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  if (t >= T) return;
+  const int e0 = p.row_ptr[t], e1 = min(p.row_ptr[t + 1], p.e_cap);
+  const int pos = p.row_pos[t];
+  const int b = pos / p.N, i = pos - b * p.N;
+  const int C = p.chan[v];
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int j = p.colpos[e] - b * p.N;
+    const int c = p.code[(size_t)v * p.e_cap + e];
+    if (adj_out) adj_out[((size_t)b * p.N + i) * p.N + j] = 1.0f;
+    if (rel_out && c < C) rel_out[(((size_t)b * C + c) * p.N + i) * p.N + j] = 1.0f;
+  }
+}
+
+template <bool kCodes>
+static int pack_count_impl(const eagcn_plan_t* plan, const void* src, cudaStream_t st) {
+  if (!plan_ok_count(plan) || !src) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  const int P = p.B * p.N;
+  const int nblk = (P + kPackRows - 1) / kPackRows;
+  cudaError_t e = cudaMemsetAsync(p.counts, 0, 8 * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  pack_count_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
+                                                           kCodes ? (const uint8_t*)src : nullptr);
+  EAGCN_LAUNCH_CHECK();
+  pack_scan_kernel<<<1, 1024, 0, st>>>(p, nblk);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool kCodes>
+static int pack_fill_impl(const eagcn_plan_t* plan, const void* src, const void* const* rel, cudaStream_t st) {
+  if (!plan_ok(plan) || !src) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  RelPtrs rp;
+  for (int v = 0; v < EAGCN_MAX_VIEWS; ++v) rp.p[v] = nullptr;
+  if (!kCodes) {
+    if (!rel) return EAGCN_E_ARG;
+    for (int v = 0; v < p.V; ++v) {
+      if (!rel[v] || p.chan[v] <= 0 || p.chan[v] > 254) return EAGCN_E_ARG;
+      rp.p[v] = (const float*)rel[v];
+    }
+  }
+  const int P = p.B * p.N;
+  const int nblk = (P + kPackRows - 1) / kPackRows;
+  pack_fill_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
+                                                          kCodes ? (const uint8_t*)src : nullptr, rp);
+  EAGCN_LAUNCH_CHECK();
+  pack_link_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace eagcn
+
+using namespace eagcn;
+
+extern "C" int eagcn_pack_count(const eagcn_plan_t* plan, const void* adj, void* stream) {
+  return pack_count_impl<false>(plan, adj, (cudaStream_t)stream);
+}
+extern "C" int eagcn_pack_fill(const eagcn_plan_t* plan, const void* adj, const void* const* rel, void* stream) {
+  return pack_fill_impl<false>(plan, adj, rel, (cudaStream_t)stream);
+}
+extern "C" int eagcn_pack_count_codes(const eagcn_plan_t* plan, const void* codes, void* stream) {
+  return pack_count_impl<true>(plan, codes, (cudaStream_t)stream);
+}
+extern "C" int eagcn_pack_fill_codes(const eagcn_plan_t* plan, const void* codes, void* stream) {
+  return pack_fill_impl<true>(plan, codes, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int eagcn_unpack_view(const eagcn_plan_t* plan, int64_t v, void* rel_out, void* adj_out, void* stream) {
+  if (!plan_ok(plan) || v < 0 || v >= plan->V) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nn = (size_t)p.B * p.N * p.N;
+  cudaError_t e;
+  if (rel_out) { e = cudaMemsetAsync(rel_out, 0, nn * p.chan[v] * sizeof(float), st); if (e) return (int)e; }
+  if (adj_out) { e = cudaMemsetAsync(adj_out, 0, nn * sizeof(float), st); if (e) return (int)e; }
+  unpack_view_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p, (int)v, (float*)rel_out, (float*)adj_out);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,104 @@
+// Dense [B,N,F] <-> packed active rows [T,F], and the sum read-out over atoms.
+//
+// rows_scatter is the reference's "cat(...) * mask3" (layers.py:313): padded rows and atoms without
+// bonds are written as exact zeros.  rows_gather is the inverse at the layer input.  The read-out
+// is models.py:108 (torch.sum(x2, 1)) evaluated on packed rows: rows of molecule b are contiguous
+// [mol_ptr[b], mol_ptr[b+1]) and are summed in ascending order (deterministic).
+#include "common.cuh"
+
+namespace eagcn {
+
+// one warp per row, lanes stride the feature dimension (float4 when F % 4 == 0)
+__global__ void __launch_bounds__(256) rows_gather_kernel(PlanDev p, const float* __restrict__ dense,
+                                                          float* __restrict__ packed, int F) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= p.t_cap) return;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  float* dst = packed + (size_t)t * F;
+  if (t >= T) {                                   // keep the slack rows of the last tile defined
+    for (int c = lane; c < F; c += 32) dst[c] = 0.0f;
+    return;
+  }
+  const float* src = dense + (size_t)p.row_pos[t] * F;
+  if ((F & 3) == 0) {
+    for (int c = lane; c < F / 4; c += 32) reinterpret_cast<float4*>(dst)[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
+  } else {
+    for (int c = lane; c < F; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) rows_scatter_kernel(PlanDev p, const float* __restrict__ packed,
+                                                           float* __restrict__ dense, int F) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * 8 + warp;
+  if (pos >= p.B * p.N) return;
+  const int t = p.pos_row[pos];
+  float* dst = dense + (size_t)pos * F;
+  if ((F & 3) == 0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(packed + (size_t)max(t, 0) * F);
+    for (int c = lane; c < F / 4; c += 32) reinterpret_cast<float4*>(dst)[c] = t >= 0 ? __ldg(src + c) : z;
+  } else {
+    const float* src = packed + (size_t)max(t, 0) * F;
+    for (int c = lane; c < F; c += 32) dst[c] = t >= 0 ? __ldg(src + c) : 0.0f;
+  }
+}
+
+// grid (B, ceil(F/128)); 128 threads, one channel each; rows summed in order
+__global__ void __launch_bounds__(128) readout_sum_kernel(PlanDev p, const float* __restrict__ packed,
+                                                          float* __restrict__ out, int F) {
+  const int b = blockIdx.x;
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= F) return;
+  const int t0 = p.mol_ptr[b], t1 = p.mol_ptr[b + 1];
+  float s = 0.0f;
+  for (int t = t0; t < t1; ++t) s += __ldg(packed + (size_t)t * F + c);
+  out[(size_t)b * F + c] = s;
+}
+
+__global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const float* __restrict__ dout,
+                                                              float* __restrict__ dpacked, int F) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= p.t_cap) return;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  float* dst = dpacked + (size_t)t * F;
+  if (t >= T) { for (int c = lane; c < F; c += 32) dst[c] = 0.0f; return; }
+  const int b = p.row_pos[t] / p.N;
+  const float* src = dout + (size_t)b * F;
+  for (int c = lane; c < F; c += 32) dst[c] = __ldg(src + c);
+}
+
+}  // namespace eagcn
+using namespace eagcn;
+
+extern "C" int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, void* packed, int64_t F, void* stream) {
+  if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  rows_gather_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dense, (float*)packed, (int)F);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, void* dense, int64_t F, void* stream) {
+  if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  rows_scatter_kernel<<<(p.B * p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)dense, (int)F);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, void* out, int64_t F, void* stream) {
+  if (!plan_ok(plan) || !out || !packed || F <= 0) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  dim3 grid(p.B, (unsigned)((F + 127) / 128));
+  readout_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)out, (int)F);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout, void* dpacked, int64_t F, void* stream) {
+  if (!plan_ok(plan) || !dout || !dpacked || F <= 0) return EAGCN_E_ARG;
+  PlanDev p = to_dev(plan);
+  readout_sum_bwd_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dout, (float*)dpacked, (int)F);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}

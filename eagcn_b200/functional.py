@@ -1,0 +1,302 @@
+"""torch.autograd bindings of the CUDA layer path (the only callers of the C ABI's compute entry points).
+
+``graph_conv_layer`` is the packed-row core of GraphConv_Layer.forward (reference layers.py:293-325):
+H [t_cap, fin] -> X [t_cap, sum_v fo_v].  Everything runs on torch's current CUDA stream, allocates
+through torch's caching allocator and never synchronises, so a whole training step can be captured in
+one CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from ._lib import LayerStruct, WorkStruct, check, lib, ptr
+from .plan import GraphPlan, _stream
+
+_F32 = torch.float32
+
+
+@dataclass
+class LayerConfig:
+    """Static description of one GraphConv_Layer call."""
+    fin: int
+    fo: tuple
+    training: bool
+    p_drop: float = 0.0
+    eps: float = 1e-5            # layers.py:399
+    momentum: float = 0.1        # layers.py:399
+    rng_stream: int = 0
+    # BatchNorm statistics across data-parallel ranks: callable(tensor) -> None that
+    # all-reduces (sum) an fp64 [2, fo_tot] tensor in place, or None for per-replica statistics
+    stat_allreduce: object = None
+
+
+class RngState:
+    """Device-resident philox (seed, offset); advancing it is a captured device op (graph-replay safe)."""
+    _states = {}
+
+    def __init__(self, device, seed=0):
+        self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self._inc = torch.tensor([0, 1 << 20], dtype=torch.int64, device=device)
+
+    @classmethod
+    def get(cls, device):
+        key = torch.device(device).index or 0
+        if key not in cls._states:
+            cls._states[key] = cls(device, seed=torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        return cls._states[key]
+
+    def seed(self, seed):
+        self.state.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+    def advance(self):
+        self.state.add_(self._inc)
+
+
+def manual_seed(seed, device=None):
+    """Seed the dropout generator of the CUDA path (independent of torch's generator, layers.py:94)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    RngState.get(dev).seed(seed)
+
+
+def _layer_struct(plan: GraphPlan, cfg: LayerConfig, params, buffers):
+    """params: per view (att_w, self_r, W, bias, gamma, beta); buffers: per view (run_mean, run_var, nbt)."""
+    s = LayerStruct()
+    s.fin, s.V = cfg.fin, plan.V
+    off = 0
+    for v in range(plan.V):
+        s.fo[v] = cfg.fo[v]
+        s.off[v] = off
+        off += cfg.fo[v]
+        a, r, W, b, g, be = params[6 * v: 6 * v + 6]
+        rm, rv, nbt = buffers[3 * v: 3 * v + 3]
+        s.att_w[v], s.self_r[v], s.W[v], s.bias[v] = a.data_ptr(), r.data_ptr(), W.data_ptr(), b.data_ptr()
+        s.gamma[v], s.beta[v] = g.data_ptr(), be.data_ptr()
+        s.run_mean[v], s.run_var[v] = rm.data_ptr(), rv.data_ptr()
+        s.nbt[v] = nbt.data_ptr() if nbt is not None else None
+    for v in range(plan.V, _lib.MAX_VIEWS + 1):
+        s.off[v] = off
+    s.fo_tot = off
+    return s
+
+
+def _check_params(plan, cfg, params, buffers):
+    dev = plan.device
+    for v in range(plan.V):
+        a, r, W, b, g, be = params[6 * v: 6 * v + 6]
+        fo = cfg.fo[v]
+        exp = [(a, plan.channels[v]), (r, 1), (W, cfg.fin * fo), (b, fo), (g, fo), (be, fo),
+               (buffers[3 * v], fo), (buffers[3 * v + 1], fo)]
+        for t, n in exp:
+            if t.device != dev or t.dtype != _F32 or t.numel() != n or not t.is_contiguous():
+                raise ValueError("GraphConv_Layer parameter with unexpected device/dtype/shape "
+                                 f"(view {v + 1}: expected {n} contiguous float32 on {dev}, got {tuple(t.shape)} "
+                                 f"{t.dtype} on {t.device})")
+
+
+class _GraphConvLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, cfg, buffers, H, *params):
+        L = lib()
+        dev = plan.device
+        if H.device != dev or H.dtype != _F32 or H.dim() != 2 or H.shape[0] != plan.t_cap or H.shape[1] != cfg.fin:
+            raise ValueError(f"packed input must be float32 [{plan.t_cap}, {cfg.fin}] on {dev}, "
+                             f"got {tuple(H.shape)} {H.dtype} on {H.device}")
+        H = H.contiguous()
+        params = tuple(p.detach() for p in params)
+        _check_params(plan, cfg, params, buffers)
+        ls = _layer_struct(plan, cfg, params, buffers)
+        C = int(ls.fo_tot)
+        T = plan.t_cap
+        f32 = dict(dtype=_F32, device=dev)
+        w = WorkStruct()
+        Z = torch.empty(T, C, **f32)
+        Y = torch.empty(T, C, **f32)
+        X = torch.empty(T, C, **f32)
+        invR = torch.empty(plan.V, T, **f32)
+        wall = torch.empty(cfg.fin, C, **f32)
+        ball = torch.empty(4, C, **f32)
+        sig = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
+        partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
+        sums = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        mean = torch.empty(C, **f32)
+        invstd = torch.empty(C, **f32)
+        rng = RngState.get(dev)
+        rng_snapshot = None
+        if cfg.training and cfg.p_drop > 0.0:
+            rng_snapshot = rng.state.clone()        # backward regenerates the same keep mask from it
+        w.H, w.Z, w.Y, w.X, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(X), ptr(invR)
+        w.wall, w.ball, w.sig, w.partial, w.sums = ptr(wall), ptr(ball), ptr(sig), ptr(partial), ptr(sums)
+        w.mean, w.invstd = ptr(mean), ptr(invstd)
+        w.rng = ptr(rng_snapshot)
+        w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
+        w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
+        w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
+        st = _stream()
+        check(L.eagcn_layer_forward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_forward_a")
+        if cfg.training and cfg.stat_allreduce is not None:
+            cfg.stat_allreduce(sums)
+        check(L.eagcn_layer_forward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_forward_b")
+        if rng_snapshot is not None:
+            rng.advance()
+        ctx.plan, ctx.cfg, ctx.buffers, ctx.params = plan, cfg, buffers, params
+        ctx.saved = (H, Z, Y, invR, wall, ball, sig, mean, invstd, rng_snapshot)
+        ctx.mark_non_differentiable()
+        return X
+
+    @staticmethod
+    def backward(ctx, dX):
+        L = lib()
+        plan, cfg, buffers, params = ctx.plan, ctx.cfg, ctx.buffers, ctx.params
+        H, Z, Y, invR, wall, ball, sig, mean, invstd, rng_snapshot = ctx.saved
+        dev = plan.device
+        ls = _layer_struct(plan, cfg, params, buffers)
+        C = int(ls.fo_tot)
+        T = plan.t_cap
+        f32 = dict(dtype=_F32, device=dev)
+        dX = dX.contiguous()
+        w = WorkStruct()
+        dY = torch.empty(T, C, **f32)
+        Q = torch.empty(T, C, **f32)
+        dH = torch.empty(T, cfg.fin, **f32)
+        dwall = torch.empty(cfg.fin, C, **f32)
+        dvec = torch.empty(3, C, **f32)
+        datt = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
+        bsums = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
+        ws_bytes = int(L.eagcn_gemm_workspace_bytes(cfg.fin, C, T))
+        gemm_ws = torch.empty(max(ws_bytes // 4, 1), **f32)
+        w.H, w.Z, w.Y, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(invR)
+        w.wall, w.ball, w.sig, w.partial = ptr(wall), ptr(ball), ptr(sig), ptr(partial)
+        w.mean, w.invstd, w.rng = ptr(mean), ptr(invstd), ptr(rng_snapshot)
+        w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
+        w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
+        w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
+        w.dX, w.dY, w.Q, w.dH, w.dwall, w.dvec, w.datt = ptr(dX), ptr(dY), ptr(Q), ptr(dH), ptr(dwall), ptr(dvec), ptr(datt)
+        w.bsums, w.gemm_ws, w.gemm_ws_bytes = ptr(bsums), ptr(gemm_ws), ws_bytes
+        st = _stream()
+        check(L.eagcn_layer_backward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_a")
+        if cfg.training and cfg.stat_allreduce is not None:
+            cfg.stat_allreduce(bsums)
+        check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+        grads = []
+        off = 0
+        for v in range(plan.V):
+            fo = cfg.fo[v]
+            a, r, W, b, g, be = params[6 * v: 6 * v + 6]
+            grads += [datt[v, :plan.channels[v]].reshape(a.shape), datt[v, 256:257].reshape(r.shape),
+                      dwall[:, off:off + fo], dvec[0, off:off + fo], dvec[1, off:off + fo], dvec[2, off:off + fo]]
+            off += fo
+        return (None, None, None, dH, *grads)
+
+
+def graph_conv_layer(plan: GraphPlan, cfg: LayerConfig, H, params, buffers):
+    """X = GraphConv_Layer(H) on packed rows.  params: flat per-view (att_w, self_r, W, bias, gamma, beta);
+    buffers: flat per-view (running_mean, running_var, num_batches_tracked)."""
+    return _GraphConvLayerFn.apply(plan, cfg, tuple(buffers), H, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+class _GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, dense):
+        if dense.device != plan.device:
+            raise _lib.EagcnError(f"eagcn_b200 is CUDA-only (no CPU fallback): features are on {dense.device}")
+        if dense.dim() != 3 or dense.shape[0] != plan.B or dense.shape[1] != plan.N:
+            raise ValueError(f"afms must be [B={plan.B}, N={plan.N}, F], got {tuple(dense.shape)}")
+        ctx.plan = plan
+        return plan.gather(dense.float())
+
+    @staticmethod
+    def backward(ctx, g):
+        # d(dense): gradient of the gathered rows; padded / bond-less rows get exact zeros (their features
+        # reach the output only through the dropped 1e-9 mask_tiny terms)
+        return None, ctx.plan.scatter(g)
+
+
+class _ScatterRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, packed):
+        ctx.plan = plan
+        return plan.scatter(packed)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, ctx.plan.gather(g)
+
+
+def gather_rows(plan, dense):
+    return _GatherRowsFn.apply(plan, dense)
+
+
+def scatter_rows(plan, packed):
+    return _ScatterRowsFn.apply(plan, packed)
+
+
+class _ReadoutSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, packed):
+        ctx.plan = plan
+        F = packed.shape[1]
+        out = torch.empty(plan.B, F, dtype=_F32, device=plan.device)
+        check(lib().eagcn_readout_sum(plan.ref, ptr(packed.contiguous()), ptr(out), F, _stream()), "eagcn_readout_sum")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan = ctx.plan
+        F = g.shape[1]
+        out = torch.empty(plan.t_cap, F, dtype=_F32, device=plan.device)
+        check(lib().eagcn_readout_sum_bwd(plan.ref, ptr(g.contiguous()), ptr(out), F, _stream()),
+              "eagcn_readout_sum_bwd")
+        return None, out
+
+
+def readout_sum(plan, packed):
+    """torch.sum(x, 1) of models.py:108 on packed rows -> [B, F]."""
+    return _ReadoutSumFn.apply(plan, packed)
+
+
+# ------------------------------------------------------------------------------------------------
+class _AttentionDenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *att_ws):
+        s = LayerStruct()
+        s.V = plan.V
+        att = tuple(a.detach().contiguous() for a in att_ws)
+        for v in range(plan.V):
+            s.att_w[v] = att[v].data_ptr()
+        A = torch.empty(plan.V, plan.B, plan.N, plan.N, dtype=_F32, device=plan.device)
+        check(lib().eagcn_attention_dense(plan.ref, ctypes.byref(s), ptr(A), _stream()), "eagcn_attention_dense")
+        ctx.plan, ctx.att = plan, att
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        plan, att = ctx.plan, ctx.att
+        s = LayerStruct()
+        s.V = plan.V
+        for v in range(plan.V):
+            s.att_w[v] = att[v].data_ptr()
+        datt = torch.empty(plan.V, _lib.SIG_STRIDE, dtype=_F32, device=plan.device)
+        check(lib().eagcn_attention_dense_bwd(plan.ref, ctypes.byref(s), ptr(dA.contiguous()), ptr(datt), _stream()),
+              "eagcn_attention_dense_bwd")
+        return (None, *[datt[v, :plan.channels[v]].reshape(att[v].shape) for v in range(plan.V)])
+
+
+def attention_dense(plan, att_ws):
+    """A_weight = stack_v(sigmoid(att_v(rel_v)) * adj)  [V,B,N,N]  (layers.py:83,318)."""
+    return _AttentionDenseFn.apply(plan, *att_ws)
+
+
+def dropout_keep_mask(plan, cfg: LayerConfig, fo_tot, rng_state):
+    """Test hook: the keep mask eagcn_layer_forward_b draws for (rng_state, cfg.rng_stream): u8 [t_cap, fo_tot]."""
+    w = WorkStruct()
+    w.rng = ptr(rng_state)
+    w.p_drop, w.rng_stream = float(cfg.p_drop), int(cfg.rng_stream)
+    keep = torch.empty(plan.t_cap, fo_tot, dtype=torch.uint8, device=plan.device)
+    check(lib().eagcn_dropout_mask(plan.ref, ctypes.byref(w), fo_tot, ptr(keep), _stream()), "eagcn_dropout_mask")
+    return keep

@@ -1,0 +1,146 @@
+"""Mirror of the reference's ``models.py`` (EAGCN, models.py:14-121) on the CUDA layer path.
+
+``EAGCN`` keeps the constructor arguments, sub-module names (layer1..layer4, den1..den3, Graph_BN,
+bn_den1, bn_den2), state_dict keys and the 3-tuple return of the reference.  Differences, all about
+not doing dead work (results are unchanged):
+  * one GraphPlan is built per batch and the atom features stay in packed-row form between layers
+    (the reference re-reads the dense padded tensors and all one-hot planes in each layer, models.py:97-100);
+  * the dense attention stack is not materialised for the 'sum' / 'ave' read-outs (only 'pool' uses it);
+  * ``atom_representations`` (models.py:102 does a blocking ``x2.data.cpu()`` every forward) is returned
+    as a lazy handle that performs the scatter + D2H copy only when something actually reads it.
+
+``EAGCNStack`` is the same model with a configurable number of GraphConv_Layers (BASELINE.json's
+"2-layer" / "3-layer" configurations; the reference hard-codes 4, models.py:50-61).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter
+
+from . import functional as EF
+from ._lib import EagcnError
+from .layers import GraphConv_Layer, PackedRows, _param_device
+from .plan import GraphPlan
+
+
+class Dense(nn.Module):
+    """layers.py:360-392: bias-free fully connected layer (weight [in,out])."""
+
+    def __init__(self, in_features, out_features, bias=False):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        dev = _param_device()
+        self.weight = Parameter(torch.empty(in_features, out_features, device=dev))
+        if bias:
+            self.bias = Parameter(torch.empty(out_features, device=dev))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, input):
+        out = torch.mm(input, self.weight)
+        return out + self.bias if self.bias is not None else out
+
+
+class LazyAtomRep:
+    """Stand-in for ``x2.data.cpu()`` (models.py:102): materialises on first use."""
+
+    def __init__(self, packed: PackedRows):
+        self._packed = PackedRows(packed.rows.detach(), packed.plan)
+        self._value = None
+
+    def materialize(self):
+        if self._value is None:
+            self._value = self._packed.dense().cpu()
+            self._packed = None
+        return self._value
+
+    def __getattr__(self, name):
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, i):
+        return self.materialize()[i]
+
+
+class EAGCNStack(nn.Module):
+    """``n_layers`` GraphConv_Layers + sum/ave read-out + the reference's dense head.
+
+    widths: per layer the 5 per-view output widths, e.g. [(80,)*5, (140,)*5] for the Tox21 2-layer config.
+    """
+
+    def __init__(self, n_bfeat, n_afeat, widths, n_den1, n_den2, nclass, dropout, molfp_mode="sum",
+                 last_flags=None):
+        super().__init__()
+        if molfp_mode not in ("sum", "ave"):
+            raise EagcnError("CUDA read-out implements molfp_mode 'sum' / 'ave' (models.py:104-111)")
+        self.molfp_mode, self.dropout = molfp_mode, dropout
+        fin = n_afeat
+        self.n_layers = len(widths)
+        for l, w in enumerate(widths):
+            last = bool(last_flags[l]) if last_flags is not None else False
+            layer = GraphConv_Layer(fin, n_bfeat, *w, dropout=dropout, structure="Concate", last=last)
+            layer.materialize_A = False
+            layer.rng_stream = l
+            setattr(self, f"layer{l + 1}", layer)
+            fin = sum(w)
+        self.out_width = fin
+        self.den1 = Dense(fin, n_den1)
+        self.den2 = Dense(n_den1, n_den2)
+        self.den3 = Dense(n_den2, nclass)
+        dev = _param_device()
+        self.Graph_BN = nn.BatchNorm1d(fin).to(dev)
+        self.bn_den1 = nn.BatchNorm1d(n_den1).to(dev)
+        self.bn_den2 = nn.BatchNorm1d(n_den2).to(dev)
+
+    @property
+    def conv_layers(self):
+        return [getattr(self, f"layer{l + 1}") for l in range(self.n_layers)]
+
+    def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None, size=None):
+        if isinstance(adjs, GraphPlan):
+            plan = adjs
+        else:
+            plan = GraphConv_Layer._plan_for(adjs, (TypeAtt, OrderAtt, AromAtt, ConjAtt, RingAtt))
+        h = afms if isinstance(afms, PackedRows) else PackedRows(EF.gather_rows(plan, afms), plan)
+        for layer in self.conv_layers:                                              # models.py:97-100
+            h, _ = layer(plan, h)
+        atom_representations = LazyAtomRep(h)                                       # models.py:102
+        x = EF.readout_sum(plan, h.rows)                                            # models.py:108
+        if self.molfp_mode == "ave":                                                # models.py:109-111
+            x = x / size.view(-1, 1).to(x.dtype)
+        x = self.Graph_BN(x)                                                        # models.py:112
+        x = self.den1(x)
+        x = F.relu(self.bn_den1(x))
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        x = self.den2(x)
+        graph_representation = x
+        x = F.relu(self.bn_den2(x))
+        x = self.den3(x)
+        return x, atom_representations, graph_representation
+
+
+class EAGCN(EAGCNStack):
+    """Reference constructor signature (models.py:22-25); structure 'Concate', molfp 'sum' | 'ave'."""
+
+    def __init__(self, n_bfeat, n_afeat, n_sgc1_1, n_sgc1_2, n_sgc1_3, n_sgc1_4, n_sgc1_5,
+                 n_sgc2_1, n_sgc2_2, n_sgc2_3, n_sgc2_4, n_sgc2_5, n_den1, n_den2, nclass, dropout,
+                 structure="Concate", molfp_mode="sum", pool_num=5):
+        if structure != "Concate":
+            raise EagcnError("the CUDA path implements structure='Concate'; GCN/GAT/Weighted_sum are the "
+                             "reference's comparison baselines and stay on stock PyTorch")
+        l1 = (n_sgc1_1, n_sgc1_2, n_sgc1_3, n_sgc1_4, n_sgc1_5)
+        l2 = (n_sgc2_1, n_sgc2_2, n_sgc2_3, n_sgc2_4, n_sgc2_5)
+        l3 = tuple(2 * w for w in l2)                                               # models.py:56-61
+        super().__init__(n_bfeat, n_afeat, [l1, l2, l3, l3], n_den1, n_den2, nclass, dropout, molfp_mode,
+                         last_flags=[False, False, False, True])
+        self.ngc1, self.ngc2 = sum(l1), sum(l2)

@@ -1,0 +1,181 @@
+/*
+ * eagcn_b200 -- C ABI of the B200-native EAGCN multi-view edge-attention graph-convolution path.
+ *
+ * Drop-in boundary.  The reference (Luckick/EAGCN) has no FFI of its own: its
+ * "plugin surface" is the nn.Module forward of eagcn_pytorch/layers.py.  Each entry point below
+ * replaces a span of that Python/ATen code; the host side (eagcn_b200/layers.py, a mirror of the
+ * reference's layers.py classes) calls these through ctypes with raw device pointers taken from
+ * torch tensors (tensor.data_ptr()) and torch's current CUDA stream.
+ *
+ * Conventions: every pointer is a DEVICE pointer to contiguous row-major memory unless it says
+ * "host"; sizes are int64_t; functions are asynchronous with respect to the host, re-entrant,
+ * keep no global mutable state, never synchronise the device, never throw and never exit.
+ * Return value: 0 = ok, negative = invalid argument (EAGCN_E_*), positive = cudaError_t of the
+ * failing runtime call / launch.
+ *
+ * All structs are made of 8-byte fields only (void*, int64_t, double) so that the ctypes mirror in
+ * eagcn_b200/_lib.py cannot disagree about padding.
+ */
+#ifndef EAGCN_B200_H_
+#define EAGCN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAGCN_ABI_VERSION 3
+#define EAGCN_MAX_VIEWS 16
+#define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
+
+#define EAGCN_E_ARG (-1)            /* null pointer / bad size */
+#define EAGCN_E_UNSUPPORTED (-2)    /* shape outside what the kernels cover */
+
+/* bits of plan.counts[2] (device-side status word, read lazily by the host) */
+#define EAGCN_ST_ADJ_NOT_01 1       /* adjacency value other than 0.0 / 1.0             */
+#define EAGCN_ST_NOT_ONEHOT 2       /* relation tensor not one-hot 0/1 on a bonded pair */
+#define EAGCN_ST_ASYMMETRIC 4       /* adj[b,i,j] != adj[b,j,i]                         */
+#define EAGCN_ST_EDGE_CAP   8       /* more directed edges than e_cap                    */
+#define EAGCN_ST_ROW_CAP   16       /* more active rows than t_cap                       */
+
+/* indices into plan.counts (int32 device array of 8) */
+#define EAGCN_CNT_T 0               /* number of active atom rows (rows with >=1 bond)  */
+#define EAGCN_CNT_E 1               /* number of directed edges (nnz of adj)            */
+#define EAGCN_CNT_STATUS 2
+
+/*
+ * Graph plan: the packed form of one padded batch (adj [B,N,N] + V one-hot relation tensors).
+ * Replaces, for every layer and for forward AND backward, the reference's per-layer mask /
+ * identity construction (layers.py:294-304) and the 1x1-conv attention-score input
+ * (layers.py:82: the one-hot planes become one uint8 code per edge and view).
+ * Active rows (m[b,i] = max_j adj[b,i,j] = 1, layers.py:295) are numbered 0..T-1 in ascending
+ * flat position b*N+i; edges are CSR over those rows, neighbours ascending.
+ */
+typedef struct eagcn_plan {
+  int64_t B, N, V;                  /* batch, padded atoms, views                          */
+  int64_t t_cap, e_cap;             /* row capacity (multiple of EAGCN_ROW_TILE), edge cap  */
+  int64_t chan[EAGCN_MAX_VIEWS];    /* C_v: channels of relation tensor v                  */
+  void* counts;                     /* int32 [8]                                           */
+  void* deg;                        /* int32 [B*N]        scratch (degree per flat row)    */
+  void* blk;                        /* int32 [2*nblk+2]   scratch, nblk = ceil(B*N/256)    */
+  void* pos_row;                    /* int32 [B*N]        flat position -> row or -1       */
+  void* row_pos;                    /* int32 [t_cap]      row -> flat position             */
+  void* row_ptr;                    /* int32 [t_cap+1]    CSR offsets                      */
+  void* mol_ptr;                    /* int32 [B+1]        first row of each molecule       */
+  void* col;                        /* int32 [e_cap]      neighbour row                    */
+  void* colpos;                     /* int32 [e_cap]      neighbour flat position          */
+  void* rev;                        /* int32 [e_cap]      index of the reverse edge        */
+  void* code;                       /* uint8 [V][e_cap]   type_v(i,j); C_v = all-zero vec  */
+  void* rcode;                      /* uint8 [V][e_cap]   type_v(j,i)                      */
+} eagcn_plan_t;
+
+/*
+ * Parameters of one GraphConv_Layer (layers.py:266-288): V GraphConv_blocks, each
+ * att.weight [1,C_v,1,1], self_r [1], graph_conv.weight [fin,fo_v] / .bias [fo_v],
+ * batch_norm.bn.{weight,bias,running_mean,running_var,num_batches_tracked}.
+ */
+typedef struct eagcn_layer {
+  int64_t fin, fo_tot, V;
+  int64_t fo[EAGCN_MAX_VIEWS];
+  int64_t off[EAGCN_MAX_VIEWS + 1]; /* prefix sums of fo                                   */
+  void* att_w[EAGCN_MAX_VIEWS];     /* f32 [C_v]                                           */
+  void* self_r[EAGCN_MAX_VIEWS];    /* f32 [1]                                             */
+  void* W[EAGCN_MAX_VIEWS];         /* f32 [fin, fo_v]                                     */
+  void* bias[EAGCN_MAX_VIEWS];      /* f32 [fo_v]                                          */
+  void* gamma[EAGCN_MAX_VIEWS];     /* f32 [fo_v]  bn.weight                               */
+  void* beta[EAGCN_MAX_VIEWS];      /* f32 [fo_v]  bn.bias                                 */
+  void* run_mean[EAGCN_MAX_VIEWS];  /* f32 [fo_v]  updated in training                     */
+  void* run_var[EAGCN_MAX_VIEWS];   /* f32 [fo_v]                                          */
+  void* nbt[EAGCN_MAX_VIEWS];       /* i64 [1]     num_batches_tracked                     */
+} eagcn_layer_t;
+
+/* Per-call buffers of one layer invocation; everything is caller-allocated (torch caching
+ * allocator).  Saved-for-backward: Z, Y, invR, mean, invstd, sums, sig, wall (+ H). */
+typedef struct eagcn_work {
+  void* H;        /* f32 [t_cap, fin]      packed input rows                               */
+  void* Z;        /* f32 [t_cap, fo_tot]   H @ W_all                                       */
+  void* Y;        /* f32 [t_cap, fo_tot]   pre-BatchNorm output                            */
+  void* X;        /* f32 [t_cap, fo_tot]   layer output, packed rows                       */
+  void* invR;     /* f32 [V, t_cap]        1 / attention row sum                           */
+  void* wall;     /* f32 [fin, fo_tot]     concatenated projection weights                 */
+  void* ball;     /* f32 [4, fo_tot]       bias, gamma, beta, (spare)                      */
+  void* sig;      /* f32 [V, 257]          sigmoid(att_w) table, [256] = sigmoid(self_r)   */
+  void* partial;  /* f32 [n_tiles, 2, fo_tot]  per-tile statistics partials                */
+  void* sums;     /* f64 [2, fo_tot]       batch sums (all-reduced by the host for global BN) */
+  void* mean;     /* f32 [fo_tot]                                                         */
+  void* invstd;   /* f32 [fo_tot]                                                         */
+  void* rng;      /* u64 [2]               philox seed, offset (device; graph-replay safe) */
+  int64_t training;
+  int64_t rng_stream;   /* distinguishes layers sharing one rng state                      */
+  int64_t m_total;      /* BatchNorm population: B*N of the (global) padded batch           */
+  int64_t n_pad;        /* padded width N used for the (N - deg)*1e-9 normaliser term       */
+  double p_drop;
+  double eps;
+  double momentum;
+  /* backward only */
+  void* dX;       /* f32 [t_cap, fo_tot]   gradient wrt X (packed)                         */
+  void* dY;       /* f32 [t_cap, fo_tot]   workspace                                       */
+  void* Q;        /* f32 [t_cap, fo_tot]   workspace: sum_v A_v^T dY_v                     */
+  void* dH;       /* f32 [t_cap, fin]      out                                             */
+  void* dwall;    /* f32 [fin, fo_tot]     out: gradient of the concatenated weights       */
+  void* dvec;     /* f32 [3, fo_tot]       out: dbias, dgamma, dbeta                       */
+  void* datt;     /* f32 [V, 257]          out: d att_w (first C_v), [256] = d self_r      */
+  void* bsums;    /* f64 [2, fo_tot]       backward batch sums (sum g, sum g*xhat)         */
+  void* gemm_ws;  /* f32 split-K workspace, gemm_ws_bytes bytes                            */
+  int64_t gemm_ws_bytes;
+} eagcn_work_t;
+
+int eagcn_version(void);
+/* number of CTAs/tiles the statistics partial buffer must hold for a given t_cap */
+int64_t eagcn_stat_tiles(int64_t t_cap);
+/* floats the `partial` buffer must hold (BatchNorm partials, then attention-gradient partials) */
+int64_t eagcn_partial_floats(int64_t t_cap, int64_t fo_tot, int64_t V);
+/* bytes of split-K workspace eagcn_layer_backward_b wants for dW_all = H^T Q */
+int64_t eagcn_gemm_workspace_bytes(int64_t fin, int64_t fo_tot, int64_t t_cap);
+
+/* --- graph plan (replaces layers.py:294-304 + the one-hot inputs of layers.py:82) -------- */
+/* phase 1: degrees, active-row / edge counts -> counts[0..1] (host may read them to size the
+ * plan exactly; not needed when capacities are known)                                        */
+int eagcn_pack_count(const eagcn_plan_t* plan, const void* adj, void* stream);
+/* phase 2: fill CSR + codes.  rel[v]: f32 [B, C_v, N, N] device pointers (host array of V)   */
+int eagcn_pack_fill(const eagcn_plan_t* plan, const void* adj, const void* const* rel, void* stream);
+/* packed uint8 data boundary: same plan from codes u8 [B,V,N,N]
+ * (255 = no bond) instead of adj + one-hot planes                                            */
+int eagcn_pack_count_codes(const eagcn_plan_t* plan, const void* codes, void* stream);
+int eagcn_pack_fill_codes(const eagcn_plan_t* plan, const void* codes, void* stream);
+/* inverse of packing, for the bit-exactness check: one-hot f32 [B,C_v,N,N] of view v and adj  */
+int eagcn_unpack_view(const eagcn_plan_t* plan, int64_t v, void* rel_out, void* adj_out, void* stream);
+
+/* --- dense <-> packed rows --------------------------------------------------------------- */
+int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, void* packed, int64_t F, void* stream);
+/* dense[b,i,:] = packed[row] for active rows, 0 elsewhere (the "* mask3" of layers.py:313)   */
+int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, void* dense, int64_t F, void* stream);
+/* sum read-out over atoms (models.py:108): out[b,:] = sum_rows packed; and its backward      */
+int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, void* out, int64_t F, void* stream);
+int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout, void* dpacked, int64_t F, void* stream);
+
+/* --- one GraphConv_Layer (layers.py:293-325, structure == 'Concate') ---------------------- */
+/* part A: weights concat + sigmoid tables, Z = H @ W_all (layers.py:40), attention score /
+ * row-normalise / aggregate / +bias (layers.py:82-92,39,43) -> Y, BatchNorm batch sums -> sums */
+int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
+/* part B: BatchNorm finalize (+ running stats, layers.py:408-412), ReLU, dropout
+ * (layers.py:93-94), concat (layers.py:313) -> X                                              */
+int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
+/* backward part A: dX -> BatchNorm backward batch sums (bsums)                                */
+int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
+/* backward part B: dY, attention gradients, Q = sum_v A_v^T dY_v, dH = Q @ W_all^T,
+ * dW_all = H^T @ Q, dbias / dgamma / dbeta / d att / d self_r                                 */
+int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
+
+/* --- returned attention A1 (layers.py:83,318): dense [V,B,N,N] and its backward ------------ */
+int eagcn_attention_dense(const eagcn_plan_t* plan, const eagcn_layer_t* layer, void* A_out, void* stream);
+int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const void* dA, void* datt, void* stream);
+
+/* --- test hook: the keep mask eagcn_layer_forward_b draws (u8 [t_cap, fo_tot]) ------------- */
+int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAGCN_B200_H_ */

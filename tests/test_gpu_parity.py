@@ -1,0 +1,304 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libeagcn_sm100.so) via eagcn_b200; the checker is the oracle / the golden vectors produced by the
+unmodified reference.  Tolerance: fp32, max|d|/max|ref| <= 1e-5 (north_star); indexing bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import eagcn_oracle as O
+from tests.util import Golden, golden_cases, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _to(dev, xs):
+    return [x.to(dev) for x in xs]
+
+
+# ------------------------------------------------------------------ indexing: bit-exact
+@pytest.mark.parametrize("case", golden_cases("layer_"))
+def test_pack_roundtrip_bit_exact(case):
+    from eagcn_b200.plan import GraphPlan
+    dev = _cuda()
+    g = Golden(case)
+    adj, afm, *rels = _to(dev, g.dense())
+    plan = GraphPlan.build(adj, rels).check()
+    assert plan.n_rows == int((adj.sum(2) > 0).sum())
+    assert plan.n_edges == int(adj.sum())
+    for v in range(5):
+        rel_back, adj_back = plan.unpack_view(v)
+        assert torch.equal(rel_back, rels[v])                  # one-hot planes round-trip bit-exactly
+        assert torch.equal(adj_back, adj)
+    # same plan from the packed uint8 boundary
+    codes = torch.from_numpy(g.batch.codes).to(dev)
+    plan2 = GraphPlan.from_codes(codes, g.batch.channels).check()
+    for name in ("pos_row", "mol_ptr"):
+        assert torch.equal(getattr(plan, name), getattr(plan2, name))
+    T, E = plan.n_rows, plan.n_edges
+    assert (plan2.n_rows, plan2.n_edges) == (T, E)
+    assert torch.equal(plan.row_ptr[:T + 1], plan2.row_ptr[:T + 1])
+    for name in ("col", "colpos", "rev"):
+        assert torch.equal(getattr(plan, name)[:E], getattr(plan2, name)[:E])
+    assert torch.equal(plan.code[:, :E], plan2.code[:, :E])
+    assert torch.equal(plan.rcode[:, :E], plan2.rcode[:, :E])
+    # row mask == max_j adj (layers.py:295)
+    assert torch.equal(plan.row_mask(), adj.max(2).values)
+
+
+def test_pack_rejects_malformed():
+    from eagcn_b200.plan import GraphPlan
+    dev = _cuda()
+    g = Golden("layer_train")
+    adj, afm, *rels = _to(dev, g.dense())
+    b, i, j = [int(t[0]) for t in torch.nonzero(adj, as_tuple=True)]
+    bad = rels[1].clone(); bad[b, :, i, j] = 0.5
+    with pytest.raises(ValueError, match="one-hot"):
+        GraphPlan.build(adj, [rels[0], bad] + rels[2:]).check()
+    asym = adj.clone(); asym[b, j, i] = 0.0
+    with pytest.raises(ValueError, match="symmetric"):
+        GraphPlan.build(asym, rels).check()
+    nonbin = adj.clone(); nonbin[b, i, j] = 2.0
+    with pytest.raises(ValueError, match="0.0/1.0"):
+        GraphPlan.build(nonbin, rels).check()
+    with pytest.raises(ValueError, match="capacity"):
+        GraphPlan.build(adj, rels, t_cap=128, e_cap=3).check()
+
+
+def test_cpu_tensors_fail_loudly():
+    from eagcn_b200 import layers as EL
+    from eagcn_b200._lib import EagcnError
+    _cuda()
+    g = Golden("layer_train")
+    layer = EL.GraphConv_Layer(24, 7, 6, 5, 4, 3, 2, dropout=0.0, structure="Concate")
+    with pytest.raises(EagcnError):
+        layer(*g.dense())                                     # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------ layer vs golden (reference outputs)
+def _our_layer(g, dev):
+    from eagcn_b200 import layers as EL
+    fo = [int(x) for x in g.meta["fouts"]]
+    fin = g.batch.afm.shape[2]
+    layer = EL.GraphConv_Layer(fin, g.batch.channels[0], *fo, dropout=0.0, structure=str(g.meta["structure"]),
+                               last=bool(g.meta["last"])).to(dev)
+    missing = layer.load_state_dict(g.sd, strict=True)
+    layer.train(bool(g.meta["training"]))
+    return layer
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases("layer_") if c != "layer_wsum"])
+def test_layer_forward_backward_vs_golden(case):
+    dev = _cuda()
+    g = Golden(case)
+    layer = _our_layer(g, dev)
+    ins = _to(dev, g.dense())
+    ins[1].requires_grad_(True)
+    x, A = layer(*ins)
+    assert rel_err(x.cpu(), g.out["x"]) <= TOL
+    assert rel_err(A.cpu(), g.out["A"]) <= TOL
+    m = ins[0].max(2).values
+    assert float((x.detach() * (1 - m).unsqueeze(2)).abs().max()) == 0.0      # layers.py:313: exact zeros
+    loss = (x * g.cot["x"].to(dev)).sum() + (A * g.cot["A"].to(dev)).sum()
+    loss.backward()
+    assert rel_err(ins[1].grad.cpu(), g.grad["afm"]) <= 2 * TOL
+    scale = max(float(v.abs().max()) for v in g.grad.values())
+    named = dict(layer.named_parameters())
+    for k, ref in g.grad.items():
+        if k == "afm":
+            continue
+        got = named[k].grad
+        assert got is not None, k
+        denom = max(float(ref.abs().max()), 1e-3 * scale)
+        if k.endswith("graph_conv.bias") and bool(g.meta["training"]):
+            denom = scale
+        assert float((got.cpu() - ref).abs().max()) / denom <= 5 * TOL, k
+    if bool(g.meta["training"]):
+        sd = layer.state_dict()
+        for k, ref in g.post.items():
+            if "num_batches" in k:
+                assert int(sd[k]) == int(ref)
+            else:
+                assert rel_err(sd[k].cpu(), ref) <= TOL, k
+
+
+def test_weighted_sum_not_silently_wrong():
+    from eagcn_b200._lib import EagcnError
+    dev = _cuda()
+    g = Golden("layer_wsum")
+    layer = _our_layer(g, dev)
+    with pytest.raises(EagcnError):
+        layer(*_to(dev, g.dense()))
+
+
+# ------------------------------------------------------------------ model vs golden
+@pytest.mark.parametrize("case", golden_cases("model_"))
+def test_model_vs_golden(case):
+    from eagcn_b200 import models as EM
+    dev = _cuda()
+    g = Golden(case)
+    kb, s1, s2, d1, d2, nc = [int(x) for x in g.meta["dims"]]
+    model = EM.EAGCN(kb, 24, *([s1] * 5), *([s2] * 5), d1, d2, nc, dropout=0.0, molfp_mode=str(g.meta["molfp"])).to(dev)
+    model.load_state_dict(g.sd, strict=True)
+    training = bool(g.meta["training"])
+    model.train(training)
+    ins = _to(dev, g.dense())
+    y, atom_rep, graph_rep = model(*ins, torch.from_numpy(g.batch.sizes).to(dev))
+    assert rel_err(atom_rep.materialize(), g.out["atom_rep"]) <= TOL
+    assert rel_err(y.cpu(), g.out["y"]) <= 5 * TOL
+    assert rel_err(graph_rep.cpu(), g.out["graph_rep"]) <= 5 * TOL
+    (y * g.cot["y"].to(dev)).sum().backward()
+    scale = max(float(v.abs().max()) for v in g.grad.values())
+    named = dict(model.named_parameters())
+    for k, ref in g.grad.items():
+        got = named[k].grad
+        assert got is not None, k
+        denom = max(float(ref.abs().max()), 1e-3 * scale)
+        if k.endswith("graph_conv.bias") and training:
+            denom = scale
+        assert float((got.cpu() - ref).abs().max()) / denom <= 2e-4, k
+
+
+# ------------------------------------------------------------------ layer vs oracle at realistic widths
+def _oracle_case(dev, B, dataset, fin, fo, seed, training, p=0.0, kb=None):
+    from eagcn_b200 import layers as EL, functional as EF
+    from eagcn_b200.data import make_batch, DATASETS
+    kb = kb or DATASETS[dataset]["kb"]
+    batch = make_batch(B, dataset=dataset, seed=seed, kb=kb, n_afeat=fin)
+    torch.manual_seed(seed)
+    layer = EL.GraphConv_Layer(fin, kb, *fo, dropout=p, structure="Concate").to(dev)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, prm in layer.named_parameters():
+            if n.endswith("att.weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g))
+            elif n.endswith("graph_conv.weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * (1.0 / fin ** 0.5))
+            elif n.endswith("bn.weight"):
+                prm.copy_(torch.rand(prm.shape, generator=g) + 0.5)
+            elif n.endswith("bn.bias"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.1)
+    layer.train(training)
+    return batch, layer
+
+
+@pytest.mark.parametrize("B,dataset,fin,fo,training", [
+    (64, "tox21", 24, (80,) * 5, True),
+    (48, "tox21", 400, (140,) * 5, True),
+    (32, "lipo", 300, (100,) * 5, False),
+    (16, "hiv", 24, (100, 52, 36, 20, 12), True),
+])
+def test_layer_vs_oracle(B, dataset, fin, fo, training):
+    dev = _cuda()
+    batch, layer = _oracle_case(dev, B, dataset, fin, fo, seed=B, training=training)
+    dense = [torch.from_numpy(a) for a in batch.dense()]
+    sd = O.clone_sd({("layer1." + k): v for k, v in layer.state_dict().items()}, requires_grad=True)
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    afm_ref = dense[1].clone().requires_grad_(True)
+    ref = O.layer_forward(sd, "layer1.", dense[0], afm_ref, codes, training)
+    ins = _to(dev, dense)
+    ins[1].requires_grad_(True)
+    x, A = layer(*ins)
+    assert rel_err(x.cpu(), ref["x"]) <= TOL
+    assert rel_err(A.cpu(), ref["A_weight"]) <= TOL
+    gen = torch.Generator().manual_seed(1)
+    R = torch.randn(ref["x"].shape, generator=gen)
+    (ref["x"] * R).sum().backward()
+    (x * R.to(dev)).sum().backward()
+    assert rel_err(ins[1].grad.cpu(), afm_ref.grad) <= 2 * TOL
+    named = dict(layer.named_parameters())
+    scale = max(float(sd["layer1." + k].grad.abs().max()) for k in named if sd["layer1." + k].grad is not None)
+    for k, prm in named.items():
+        ref_g = sd["layer1." + k].grad
+        if ref_g is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
+            continue
+        denom = max(float(ref_g.abs().max()), 1e-3 * scale)
+        if k.endswith("graph_conv.bias") and training:
+            denom = scale
+        assert float((prm.grad.cpu() - ref_g).abs().max()) / denom <= 5 * TOL, k
+
+
+def test_dropout_mask_consistency():
+    """Training with dropout: the CUDA path's keep mask (its own philox stream -- torch's global RNG of
+    layers.py:94 cannot be matched) is exported, fed to the oracle, and forward+backward must agree."""
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    p = 0.3
+    batch, layer = _oracle_case(dev, 40, "tox21", 24, (16, 12, 8, 8, 4), seed=9, training=True, p=p)
+    EF.manual_seed(1234, dev)
+    rng_before = EF.RngState.get(dev).state.clone()
+    dense = [torch.from_numpy(a) for a in batch.dense()]
+    ins = _to(dev, dense)
+    ins[1].requires_grad_(True)
+    x, _ = layer(*ins)
+    from eagcn_b200.layers import GraphConv_Layer
+    plan = GraphConv_Layer._plan_cache[2]
+    cfg = EF.LayerConfig(fin=24, fo=(16, 12, 8, 8, 4), training=True, p_drop=p, rng_stream=0)
+    keep_packed = EF.dropout_keep_mask(plan, cfg, 48, rng_before).float()
+    frac = float(keep_packed[:plan.n_rows].mean())
+    assert abs(frac - (1 - p)) < 0.02
+    keep_dense = plan.scatter(keep_packed).cpu()
+    off, keeps = 0, []
+    for fo in cfg.fo:
+        keeps.append(keep_dense[:, :, off:off + fo]); off += fo
+    sd = O.clone_sd({("layer1." + k): v for k, v in layer.state_dict().items()}, requires_grad=True)
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    afm_ref = dense[1].clone().requires_grad_(True)
+    # running stats were already updated by the CUDA forward; the oracle only needs batch stats
+    ref = O.layer_forward(sd, "layer1.", dense[0], afm_ref, codes, True, p=p, keeps=keeps)
+    assert rel_err(x.cpu(), ref["x"]) <= TOL
+    gen = torch.Generator().manual_seed(2)
+    R = torch.randn(ref["x"].shape, generator=gen)
+    (ref["x"] * R).sum().backward()
+    (x * R.to(dev)).sum().backward()
+    assert rel_err(ins[1].grad.cpu(), afm_ref.grad) <= 2 * TOL
+    g_ref = sd["layer1.block1.graph_conv.weight"].grad
+    assert rel_err(layer.block1.graph_conv.weight.grad.cpu(), g_ref) <= 5 * TOL
+    # a second call draws a different mask
+    x2, _ = layer(*[t.detach() for t in ins])
+    assert not torch.equal((x2 == 0), (x == 0))
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_full_size_properties():
+    """BASELINE config 2 shape (Tox21, B=256, 24->400->700): properties that need no oracle run."""
+    from eagcn_b200 import models as EM
+    from eagcn_b200.data import make_batch
+    dev = _cuda()
+    torch.manual_seed(0)
+    model = EM.EAGCNStack(30, 24, [(80,) * 5, (140,) * 5], 256, 64, 12, dropout=0.0).to(dev)
+    model.eval()
+    batch = make_batch(256, "tox21", seed=0)
+    ins = _to(dev, [torch.from_numpy(a) for a in batch.dense()])
+    size = torch.from_numpy(batch.sizes).to(dev)
+    with torch.no_grad():
+        y, atom, _ = model(*ins, size)
+        # (1) determinism: bitwise identical on a re-run
+        y2, _, _ = model(*ins, size)
+        assert torch.equal(y, y2)
+        # (2) molecules are independent in eval mode: permuting the batch permutes the outputs
+        perm = torch.randperm(256, generator=torch.Generator().manual_seed(0)).to(dev)
+        yp, _, _ = model(*[t[perm] for t in ins], size[perm])
+        assert rel_err(yp.cpu(), y[perm].cpu()) <= TOL
+        # (3) padded rows of the atom representation are exact zeros
+        dense = atom.materialize()
+        m = ins[0].max(2).values.cpu()
+        assert float((dense * (1 - m).unsqueeze(2)).abs().max()) == 0.0
+        # (4) padding invariance: a wider zero padding only moves the 1e-9 terms
+        wide = make_batch(256, "tox21", seed=0, pad_to=batch.N + 17)
+        insw = _to(dev, [torch.from_numpy(a) for a in wide.dense()])
+        yw, _, _ = model(*insw, size)
+        assert rel_err(yw.cpu(), y.cpu()) <= TOL
+    # (5) packed uint8 boundary gives bit-identical results to the dense one-hot boundary
+    from eagcn_b200.plan import GraphPlan
+    with torch.no_grad():
+        plan = GraphPlan.from_codes(torch.from_numpy(batch.codes).to(dev), batch.channels).check()
+        yc, _, _ = model(plan, ins[1], size=size)
+        assert torch.equal(yc, y)

@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/sec of the EAGCN forward+backward hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], named in ``config.workload``): Tox21-shaped synthetic batches
+(sizes drawn from the Tox21 heavy-atom histogram, Kb = 30, 5 views), batch 256 per GPU, 2 GraphConv_Layers
+24 -> 400 -> 700 + sum read-out + the reference's dense head (256 / 64 / 12), training mode, dropout 0.3,
+forward + backward of ``out.sum()``.  A "step" = one such pass over one batch, including
+the per-batch graph-plan packing.  Weak scaling: every rank processes its own 256-molecule batches; for
+N > 1 the flat gradient buffer is all-reduced (NCCL) inside the timed step.
+
+  value      whole-job molecules/s, inputs (the dense fp32 tensors the reference's collate produces)
+             already resident in HBM; each step is one CUDA-graph replay; NB distinct batches are rotated
+             so the inputs touched between two uses of the same batch exceed L2 (config.l2).
+  e2e        same metric through the public module call with HOST (pinned) buffers: H2D of that step's
+             inputs + the step + D2H of the outputs inside the timed region.  ``e2e`` uses the reference-
+             facing dense layout; ``e2e_packed`` the uint8 edge-code layout of the packed data boundary.
+  roofline   dominant kernel of the step (per-kernel CUDA-event timing inside this run).
+  cpu_baseline  the oracle's reference-cost form (same ATen op sequence as the reference) on the host cores.
+
+--impl reference: times that CPU path alone (rank 0 only) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "tox21_b256_2layer_5view_fwd_bwd"
+DATASET, BATCH, KB = "tox21", 256, 30
+WIDTHS = [(80,) * 5, (140,) * 5]            # train.py:62-63 (tox21): 24 -> 400 -> 700
+DEN = (256, 64)
+NCLASS = 12
+P_DROP = 0.3                                 # train.py:48
+METRIC = "molecules/sec EAGCN fwd+bwd (Tox21 shape, 5 views)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sus=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def host_batch(seed):
+    from eagcn_b200.data import make_batch
+    b = make_batch(BATCH, DATASET, seed=seed, kb=KB)
+    T = int((b.adj.sum(2) > 0).sum())
+    E = int(b.adj.sum())
+    return b, T, E
+
+
+def build_model(dev):
+    from eagcn_b200 import models as EM
+    torch.manual_seed(0)
+    m = EM.EAGCNStack(KB, 24, WIDTHS, DEN[0], DEN[1], NCLASS, dropout=P_DROP).to(dev)
+    # utils.weights_init (utils.py:702-708) as train.py:302 applies it
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for mod in m.modules():
+            name = mod.__class__.__name__
+            if "GraphConv_base" in name:
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.02)
+            elif "BatchNorm" in name:
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.02 + 1.0)
+                mod.bias.zero_()
+    m.train()
+    return m
+
+
+class Slot:
+    """One pre-staged batch: static device inputs + its captured step graph."""
+    pass
+
+
+def algorithmic(T, E, B, N):
+    """Per-kernel algorithmic (bytes, flops) of ONE step for this batch: each operand read once, each
+    result written once (DESIGN.md 'kernels').  Row counts are the unpadded active rows T."""
+    V = 5
+    out = {}
+    fin = 24
+    acc = lambda k, b, f: out.__setitem__(k, (out.get(k, (0, 0))[0] + b, out.get(k, (0, 0))[1] + f))
+    sumC = KB + 10
+    acc("pack_count_kernel", 4 * B * N * N, 0)
+    acc("pack_fill_kernel", 4 * B * N * N + E * sumC * 4 + E * (4 + V), 0)
+    acc("pack_link_kernel", E * (4 + 4 + 4 + 2 * V), 0)
+    for w in WIDTHS:
+        C = sum(w)
+        acc("gemm_nn", 4 * (T * fin + fin * C + T * C), 2 * T * fin * C)
+        acc("gemm_nt", 4 * (T * C + fin * C + T * fin), 2 * T * fin * C)
+        acc("gemm_tn", 4 * (T * fin + T * C + fin * C), 2 * T * fin * C)
+        acc("agg_fwd_kernel", 4 * 2 * T * C + E * (4 + V) + 4 * V * T, 2 * (E + T) * C)
+        acc("agg_bwd_kernel", 4 * 4 * T * C + E * (4 + 2 * V) + 4 * V * T, 4 * (E + T) * C)
+        acc("bn_apply_kernel", 8 * T * C, 0)
+        acc("bn_bwd_partial_kernel", 8 * T * C, 0)
+        acc("bn_bwd_apply_kernel", 12 * T * C, 0)
+        fin = C
+    return out
+
+
+KERNEL_ALIAS = {"gemm_simt_nn": "gemm_nn", "gemm_simt_nt": "gemm_nt", "gemm_simt_tn": "gemm_tn",
+                "gemm_tc_nn": "gemm_nn", "gemm_tc_nt": "gemm_nt", "gemm_tc_tn": "gemm_tn"}
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from eagcn_b200 import _lib
+    from eagcn_b200.parallel import FlatGradBucket
+    from eagcn_b200.plan import GraphPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    model = build_model(dev)
+    NB = args.nbatches
+    slots = []
+    for i in range(NB):
+        hb, T, E = host_batch(seed=1000 * rank + i)
+        s = Slot()
+        s.hb, s.T, s.E = hb, T, E
+        s.t_cap, s.e_cap = T, E                      # exact capacities known on the host: no device sync
+        dense = hb.dense()
+        s.host_dense = [torch.from_numpy(a).pin_memory() for a in dense]
+        s.host_codes = torch.from_numpy(hb.codes).pin_memory()
+        s.host_afm = s.host_dense[1]
+        s.dev_dense = [t.to(dev, non_blocking=True) for t in s.host_dense]
+        s.dev_codes = s.host_codes.to(dev, non_blocking=True)
+        s.size = torch.from_numpy(hb.sizes).to(dev)
+        slots.append(s)
+    torch.cuda.synchronize()
+
+    def step_dense(s):
+        plan = GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
+        out, _, _ = model(plan, s.dev_dense[1], size=s.size)
+        out.sum().backward()
+        return out
+
+    def step_codes(s):
+        plan = GraphPlan.from_codes(s.dev_codes, s.hb.channels, t_cap=s.t_cap, e_cap=s.e_cap)
+        out, _, _ = model(plan, s.dev_dense[1], size=s.size)
+        out.sum().backward()
+        return out
+
+    # which parameters get gradients -> flat buffer (one all-reduce per step for N > 1)
+    bucket = FlatGradBucket.from_probe(model, lambda: step_dense(slots[0]))
+    torch.cuda.synchronize()
+
+    # ---- capture one CUDA graph per (batch, layout) ----
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            for s in slots[:2]:
+                bucket.zero(); step_dense(s); step_codes(s)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    launches_per_step = None
+    for s in slots:
+        for name, fn in (("g_dense", step_dense), ("g_codes", step_codes)):
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.launch_count()
+            with torch.cuda.graph(g, pool=pool):
+                bucket.zero()
+                out = fn(s)
+            setattr(s, name, g)
+            setattr(s, name + "_out", out)
+            if name == "g_dense" and launches_per_step is None:
+                launches_per_step = _lib.launch_count() - c0
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, K, W):
+        for i in range(W):
+            run_step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            run_step(W + i)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) , clocks
+
+    # ---- value: HBM-resident inputs, graph replay (+ flat all-reduce for N>1) ----
+    def step_value(i):
+        s = slots[i % NB]
+        s.g_dense.replay()
+        bucket.all_reduce()
+
+    ms_total, clocks = timed(step_value, args.steps, args.warmup)
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
+    if bad:                                           # rejected run: re-measure once
+        ms_total, clocks = timed(step_value, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    value = BATCH * world / (ms_step * 1e-3)
+
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H, every step ----
+    out_host = torch.empty(BATCH, NCLASS).pin_memory()
+
+    def step_e2e_dense(i):
+        s = slots[i % NB]
+        for d, h in zip(s.dev_dense, s.host_dense):
+            d.copy_(h, non_blocking=True)
+        s.g_dense.replay()
+        bucket.all_reduce()
+        out_host.copy_(s.g_dense_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_e2e_codes(i):
+        s = slots[i % NB]
+        s.dev_codes.copy_(s.host_codes, non_blocking=True)
+        s.dev_dense[1].copy_(s.host_afm, non_blocking=True)
+        s.g_codes.replay()
+        bucket.all_reduce()
+        out_host.copy_(s.g_codes_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    k_e2e = max(5, min(args.steps, 30))
+    ms_e2e, _ = timed(step_e2e_dense, k_e2e, 3)
+    ms_e2e_p, _ = timed(step_e2e_codes, k_e2e, 3)
+    h2d_dense = int(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in slots]))
+    h2d_codes = int(np.mean([s.host_codes.numel() + s.host_afm.numel() * 4 for s in slots]))
+    d2h = out_host.numel() * 4
+
+    # ---- per-kernel CUDA-event profile of eager steps (roofline of the dominant kernel) ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        _lib.profile(True)
+        nprof = 3
+        for i in range(nprof):
+            bucket.zero(); step_dense(slots[i % NB])
+        torch.cuda.synchronize()
+        rep = _lib.profile_report()
+        _lib.profile(False)
+        alg = {}
+        for i in range(nprof):
+            s = slots[i % NB]
+            for k, (b, f) in algorithmic(s.T, s.E, BATCH, s.hb.N).items():
+                a = alg.get(k, (0, 0)); alg[k] = (a[0] + b, a[1] + f)
+        tot_ms = sum(v[1] for v in rep.values())
+        kern = {}
+        for k, (n, ms) in rep.items():
+            kern[k] = {"launches_per_step": n / nprof, "ms_per_step": ms / nprof, "share": ms / tot_ms if tot_ms else 0}
+        top = max(rep.items(), key=lambda kv: kv[1][1])[0] if rep else None
+        pk = peaks()
+        if top is not None:
+            key = KERNEL_ALIAS.get(top, top)
+            b, f = alg.get(key, (0, 0))
+            n, ms = rep[top]
+            sec = ms * 1e-3
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.isfile(tp):
+                traffic = json.load(open(tp)).get(top)
+            if key.startswith("gemm"):
+                ach = f / sec / 1e12
+                roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_sus"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
+                        "launches": n, "avg_launch_us": 1e3 * ms / n,
+                        "note": "fp32-faithful projection; useful 2*T*K*N flops"}
+            else:
+                ach = b / sec / 1e9
+                roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " copy",
+                        "launches": n, "avg_launch_us": 1e3 * ms / n}
+            roof["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 5), "share": round(v["share"], 4),
+                                   "launches_per_step": v["launches_per_step"]} for k, v in
+                               sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        if world == 1:
+            cpu = run_cpu_baseline(steps=3, warmup=1, budget_s=25.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
+                       "mode": "train fwd+bwd", "bn_sync": "local", "parallelism": f"dp{world}",
+                       "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
+                       "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
+                       "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
+                       "grad_bytes": bucket.nbytes},
+            "clocks": clocks,
+            "e2e": {"value": BATCH * world / (ms_e2e / k_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_dense,
+                    "d2h_bytes_per_step": d2h, "layout": "dense fp32 one-hot (reference collate layout)", "steps": k_e2e},
+            "e2e_packed": {"value": BATCH * world / (ms_e2e_p / k_e2e * 1e-3), "unit": "molecules/s",
+                           "h2d_bytes_per_step": h2d_codes, "d2h_bytes_per_step": d2h,
+                           "layout": "uint8 edge codes + fp32 atom features", "steps": k_e2e},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cpu_baseline(steps, warmup, budget_s):
+    """The reference's CPU path (oracle reference-cost form: same ATen op sequence as layers.py / models.py)
+    on the host cores, fwd+bwd, train mode, dropout 0.3.  Bounded: the batch is cut down if one step at
+    B=256 would not fit the budget."""
+    from oracle import eagcn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hb, _, _ = host_batch(seed=0)
+    model_sd = None
+    torch.manual_seed(0)
+    # parameters with the reference's shapes / names
+    sd = {}
+    fin = 24
+    g = torch.Generator().manual_seed(0)
+    chans = hb.channels
+    for l, w in enumerate(WIDTHS):
+        pre = f"layer{l + 1}."
+        for v in range(5):
+            bp = f"{pre}block{v + 1}."
+            sd[bp + "att.weight"] = (torch.randn(1, chans[v], 1, 1, generator=g) * 0.3).requires_grad_(True)
+            sd[bp + "self_r"] = (torch.randn(1, generator=g) * 0.01).requires_grad_(True)
+            sd[bp + "graph_conv.weight"] = (torch.randn(fin, w[v], generator=g) * 0.02).requires_grad_(True)
+            sd[bp + "graph_conv.bias"] = (torch.randn(w[v], generator=g) * 0.05).requires_grad_(True)
+            sd[bp + "batch_norm.bn.weight"] = torch.ones(w[v], requires_grad=True)
+            sd[bp + "batch_norm.bn.bias"] = torch.zeros(w[v], requires_grad=True)
+            sd[bp + "batch_norm.bn.running_mean"] = torch.zeros(w[v])
+            sd[bp + "batch_norm.bn.running_var"] = torch.ones(w[v])
+        fin = sum(w)
+    for name, n in (("Graph_BN.", fin), ("bn_den1.", DEN[0]), ("bn_den2.", DEN[1])):
+        sd[name + "weight"] = torch.ones(n, requires_grad=True); sd[name + "bias"] = torch.zeros(n, requires_grad=True)
+        sd[name + "running_mean"] = torch.zeros(n); sd[name + "running_var"] = torch.ones(n)
+    sd["den1.weight"] = (torch.randn(fin, DEN[0], generator=g) * 0.05).requires_grad_(True)
+    sd["den2.weight"] = (torch.randn(DEN[0], DEN[1], generator=g) * 0.05).requires_grad_(True)
+    sd["den3.weight"] = (torch.randn(DEN[1], NCLASS, generator=g) * 0.05).requires_grad_(True)
+    dense = [torch.from_numpy(a) for a in hb.dense()]
+    sizes = torch.from_numpy(hb.sizes)
+
+    def one(nmol):
+        d = [t[:nmol] for t in dense]
+        for t in sd.values():
+            if t.requires_grad:
+                t.grad = None
+        out = O.model_forward_conv(sd, d[0], d[1], d[2:], sizes[:nmol], len(WIDTHS), True, P_DROP)
+        out.sum().backward()
+
+    nmol = BATCH
+    t0 = time.perf_counter(); one(nmol); t1 = time.perf_counter() - t0      # warm-up / calibration
+    if t1 * (steps + warmup) > budget_s:
+        nmol = max(16, int(BATCH * budget_s / (t1 * (steps + warmup + 1))))
+    for _ in range(max(0, warmup - 1)):
+        one(nmol)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); one(nmol); ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return {"value": nmol / sec, "unit": "molecules/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} fwd+bwd steps over the first {nmol} molecules of one {WORKLOAD} batch (N_pad={hb.N}), "
+                      f"{sec * 1e3:.0f} ms/step, torch {torch.__version__} CPU, {cores} threads",
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # a step here = fwd+bwd over a bounded sample of the workload; keep the whole run within a few minutes
+    budget = 150.0
+    cpu = run_cpu_baseline(steps=max(1, args.steps), warmup=max(1, args.warmup), budget_s=budget)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "molecules/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "views": 5, "kb": KB, "widths": "24->400->700",
+                       "head": "256/64/12", "dropout": P_DROP, "mode": "train fwd+bwd",
+                       "device": "host CPU cores (the reference has no GPU kernels of its own to time; "
+                                 "/root/reference cannot travel to the GPU box, so its op sequence is restated in oracle/)"},
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cpu["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nbatches", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

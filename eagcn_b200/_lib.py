@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -77,6 +77,9 @@ _PROTOS = {
     "eagcn_attention_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_attention_dense_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_dropout_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "eagcn_launch_count": (c_int64, []),
+    "eagcn_profile": (c_int, [c_int]),
+    "eagcn_profile_report": (c_int64, [ctypes.c_char_p, c_int64]),
 }
 EXPORTS = tuple(_PROTOS)
 
@@ -117,3 +120,19 @@ def check(rc: int, what: str):
 
 def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
+
+
+def launch_count() -> int:
+    return int(lib().eagcn_launch_count())
+
+
+def profile(enable: bool):
+    lib().eagcn_profile(1 if enable else 0)
+
+
+def profile_report() -> dict:
+    """{kernel: (launches, total_ms)} recorded since profile(True)."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().eagcn_profile_report(buf, len(buf))
+    return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode() or "{}").items()} if n else {}

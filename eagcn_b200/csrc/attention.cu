@@ -81,6 +81,7 @@ extern "C" int eagcn_attention_dense(const eagcn_plan_t* plan, const eagcn_layer
   LayerDev L = to_dev(layer, plan);
   cudaError_t e = cudaMemsetAsync(A_out, 0, (size_t)p.V * p.B * p.N * p.N * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
+  EAGCN_PROF("att_dense_kernel", st);
   att_dense_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p, L, (float*)A_out);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -91,6 +92,7 @@ extern "C" int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_l
   if (!plan_ok(plan) || !att_layer_ok(plan, layer) || !dA || !datt) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
   LayerDev L = to_dev(layer, plan);
+  EAGCN_PROF("att_dense_bwd_kernel", (cudaStream_t)stream);
   att_dense_bwd_kernel<<<p.V, 256, 0, (cudaStream_t)stream>>>(p, L, (const float*)dA, (float*)datt);
   EAGCN_LAUNCH_CHECK();
   return 0;

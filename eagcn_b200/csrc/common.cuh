@@ -4,8 +4,41 @@
 #include <stdint.h>
 #include "../../include/eagcn_b200.h"
 
+// Every kernel launch is bracketed by EAGCN_PROF(name, stream) ... EAGCN_LAUNCH_CHECK().  Besides error
+// propagation this feeds two diagnostics (not thread-safe, off the product path's critical section):
+// a launch counter (bench.py's gpu_launches) and an opt-in per-kernel CUDA-event profiler
+// (eagcn_profile / eagcn_profile_report) used for the roofline line of bench.py.
+#include <vector>
+namespace eagcn {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct ProfState {
+  long long launches = 0;
+  int on = 0;
+  bool open = false;
+  ProfRec cur{};
+  cudaStream_t cur_st = nullptr;
+  std::vector<ProfRec> recs;
+};
+inline ProfState& prof() { static ProfState s; return s; }
+inline void prof_begin(const char* name, cudaStream_t st) {
+  ProfState& s = prof();
+  ++s.launches;
+  if (s.on) {
+    s.cur.name = name;
+    cudaEventCreate(&s.cur.a); cudaEventCreate(&s.cur.b);
+    cudaEventRecord(s.cur.a, st);
+    s.cur_st = st; s.open = true;
+  }
+}
+inline void prof_end() {
+  ProfState& s = prof();
+  if (s.on && s.open) { cudaEventRecord(s.cur.b, s.cur_st); s.recs.push_back(s.cur); s.open = false; }
+}
+}  // namespace eagcn
+#define EAGCN_PROF(name, st) ::eagcn::prof_begin(name, (cudaStream_t)(st))
 #define EAGCN_LAUNCH_CHECK()                                  \
   do {                                                        \
+    ::eagcn::prof_end();                                      \
     cudaError_t e__ = cudaPeekAtLastError();                  \
     if (e__ != cudaSuccess) return (int)e__;                  \
   } while (0)

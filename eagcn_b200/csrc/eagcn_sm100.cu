@@ -7,3 +7,44 @@
 #include "attention.cu"
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
+
+// ---- diagnostics -----------------------------------------------------------------------------------
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+extern "C" int64_t eagcn_launch_count(void) { return eagcn::prof().launches; }
+
+extern "C" int eagcn_profile(int enable) {
+  eagcn::ProfState& s = eagcn::prof();
+  for (auto& r : s.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  s.recs.clear();
+  s.open = false;
+  s.on = enable ? 1 : 0;
+  return 0;
+}
+
+// JSON object {"kernel": [launches, total_ms], ...} of everything recorded since eagcn_profile(1).
+// Synchronises on the recorded events.  Returns the number of bytes written (0 if buf is too small).
+extern "C" int64_t eagcn_profile_report(char* buf, int64_t cap) {
+  eagcn::ProfState& s = eagcn::prof();
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : s.recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1; e.second += ms;
+    }
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": [%lld, %.6f]", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += tmp; first = false;
+  }
+  out += "}";
+  if ((int64_t)out.size() + 1 > cap || !buf) return 0;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int64_t)out.size();
+}

@@ -116,6 +116,7 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const int* Mdev, cudaStream_t st) {
   GemmArgs g{A, B, C, lda, 1, ldb, 1, ldc, Mcap, N, K, Mdev, nullptr, K + GBK, 0};
   dim3 grid((N + GBN - 1) / GBN, (Mcap + GBM - 1) / GBM, 1);
+  EAGCN_PROF("gemm_simt_nn", st);
   gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, st>>>(g);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -126,6 +127,7 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
   // B given as [N, K] row-major (K contiguous)
   GemmArgs g{A, B, C, lda, 1, 1, ldb, ldc, Mcap, N, K, Mdev, nullptr, K + GBK, 0};
   dim3 grid((N + GBN - 1) / GBN, (Mcap + GBM - 1) / GBM, 1);
+  EAGCN_PROF("gemm_simt_nt", st);
   gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, st>>>(g);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -147,9 +149,11 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
   kchunk = ((kchunk + GBK - 1) / GBK) * GBK;
   GemmArgs g{A, B, ws, 1, lda, ldb, 1, N, M, N, Kcap, nullptr, Kdev, kchunk, (long long)M * N};
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, ns);
+  EAGCN_PROF("gemm_simt_tn", st);
   gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, st>>>(g);
   EAGCN_LAUNCH_CHECK();
   const long long n = (long long)M * N;
+  EAGCN_PROF("splitk_reduce_kernel", st);
   splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, C, n, ns);
   EAGCN_LAUNCH_CHECK();
   return 0;

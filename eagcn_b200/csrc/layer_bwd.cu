@@ -283,11 +283,13 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   PlanDev p = to_dev(plan);
   const int C = (int)layer->fo_tot;
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
+  EAGCN_PROF("bn_bwd_partial_kernel", st);
   bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                               (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
                                               w->training ? 1 : 0, (float)w->p_drop,
                                               (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
   EAGCN_LAUNCH_CHECK();
+  EAGCN_PROF("stat_reduce_kernel", st);
   stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->bsums, C);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -305,25 +307,31 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const long long total = (long long)p.t_cap * C;
+  EAGCN_PROF("bn_bwd_apply_kernel", st);
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
       (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
       (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
   EAGCN_LAUNCH_CHECK();
+  EAGCN_PROF("bn_bwd_finalize_kernel", st);
   bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
                                                           (const double*)w->bsums, (float*)w->dvec, C,
                                                           w->training ? 1 : 0);
   EAGCN_LAUNCH_CHECK();
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
-  if (vec4_ok_b(layer))
+  if (vec4_ok_b(layer)) {
+    EAGCN_PROF("agg_bwd_kernel", st);
     agg_bwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
-  else
+  } else {
+    EAGCN_PROF("agg_bwd_kernel", st);
     agg_bwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
+  }
   EAGCN_LAUNCH_CHECK();
+  EAGCN_PROF("datt_reduce_kernel", st);
   datt_reduce_kernel<<<(L.V * EAGCN_SIG_STRIDE + 255) / 256, 256, 0, st>>>(p, (const float*)w->partial, (float*)w->datt,
                                                                            L.V);
   EAGCN_LAUNCH_CHECK();

@@ -283,6 +283,7 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   long long n = (long long)L.fin * C;
   if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
   if (n < C) n = C;
+  EAGCN_PROF("prep_params_kernel", st);
   prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->ball, (float*)w->sig);
   EAGCN_LAUNCH_CHECK();
   int rc = gemm_nn((const float*)w->H, L.fin, (const float*)w->wall, C, (float*)w->Z, C, p.t_cap, C, L.fin,
@@ -291,14 +292,18 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);
   const int want = w->training ? 1 : 0;
-  if (vec4_ok(layer))
+  if (vec4_ok(layer)) {
+    EAGCN_PROF("agg_fwd_kernel", st);
     agg_fwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
-  else
+  } else {
+    EAGCN_PROF("agg_fwd_kernel", st);
     agg_fwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
+  }
   EAGCN_LAUNCH_CHECK();
   if (want) {
+    EAGCN_PROF("stat_reduce_kernel", st);
     stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->sums, C);
     EAGCN_LAUNCH_CHECK();
   }
@@ -316,10 +321,12 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
   LayerDev L = to_dev(layer, plan);
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
+  EAGCN_PROF("bn_finalize_kernel", st);
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
                                                       (float*)w->invstd, w->training ? 1 : 0, M, w->eps, w->momentum);
   EAGCN_LAUNCH_CHECK();
   const long long total = (long long)p.t_cap * C;
+  EAGCN_PROF("bn_apply_kernel", st);
   bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
       w->training ? 1 : 0, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
@@ -331,6 +338,7 @@ extern "C" int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* 
                                   void* stream) {
   if (!plan_ok(plan) || !w || !w->rng || !keep_out || fo_tot <= 0) return EAGCN_E_ARG;
   const long long total = (long long)plan->t_cap * fo_tot;
+  EAGCN_PROF("dropout_mask_kernel", (cudaStream_t)stream);
   dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       total, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, (uint8_t*)keep_out);
   EAGCN_LAUNCH_CHECK();

@@ -243,9 +243,11 @@ static int pack_count_impl(const eagcn_plan_t* plan, const void* src, cudaStream
   const int nblk = (P + kPackRows - 1) / kPackRows;
   cudaError_t e = cudaMemsetAsync(p.counts, 0, 8 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
+  EAGCN_PROF("pack_count_kernel", st);
   pack_count_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
                                                            kCodes ? (const uint8_t*)src : nullptr);
   EAGCN_LAUNCH_CHECK();
+  EAGCN_PROF("pack_scan_kernel", st);
   pack_scan_kernel<<<1, 1024, 0, st>>>(p, nblk);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -266,9 +268,11 @@ static int pack_fill_impl(const eagcn_plan_t* plan, const void* src, const void*
   }
   const int P = p.B * p.N;
   const int nblk = (P + kPackRows - 1) / kPackRows;
+  EAGCN_PROF("pack_fill_kernel", st);
   pack_fill_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
                                                           kCodes ? (const uint8_t*)src : nullptr, rp);
   EAGCN_LAUNCH_CHECK();
+  EAGCN_PROF("pack_link_kernel", st);
   pack_link_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -299,6 +303,7 @@ extern "C" int eagcn_unpack_view(const eagcn_plan_t* plan, int64_t v, void* rel_
   cudaError_t e;
   if (rel_out) { e = cudaMemsetAsync(rel_out, 0, nn * p.chan[v] * sizeof(float), st); if (e) return (int)e; }
   if (adj_out) { e = cudaMemsetAsync(adj_out, 0, nn * sizeof(float), st); if (e) return (int)e; }
+  EAGCN_PROF("unpack_view_kernel", st);
   unpack_view_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p, (int)v, (float*)rel_out, (float*)adj_out);
   EAGCN_LAUNCH_CHECK();
   return 0;

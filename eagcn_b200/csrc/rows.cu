@@ -76,6 +76,7 @@ using namespace eagcn;
 extern "C" int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, void* packed, int64_t F, void* stream) {
   if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
+  EAGCN_PROF("rows_gather_kernel", (cudaStream_t)stream);
   rows_gather_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dense, (float*)packed, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -83,6 +84,7 @@ extern "C" int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, vo
 extern "C" int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, void* dense, int64_t F, void* stream) {
   if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
+  EAGCN_PROF("rows_scatter_kernel", (cudaStream_t)stream);
   rows_scatter_kernel<<<(p.B * p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)dense, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -91,6 +93,7 @@ extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, v
   if (!plan_ok(plan) || !out || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
   dim3 grid(p.B, (unsigned)((F + 127) / 128));
+  EAGCN_PROF("readout_sum_kernel", (cudaStream_t)stream);
   readout_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)out, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -98,6 +101,7 @@ extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, v
 extern "C" int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout, void* dpacked, int64_t F, void* stream) {
   if (!plan_ok(plan) || !dout || !dpacked || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
+  EAGCN_PROF("readout_sum_bwd_kernel", (cudaStream_t)stream);
   readout_sum_bwd_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dout, (float*)dpacked, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;

@@ -139,11 +139,11 @@ class GraphConv_block(nn.Module):
     def reset_parameters(self):                           # layers.py:77-79
         self.self_r.data.uniform_(-0.01, 0.01)
 
-    def _params(self):
+    def _view_params(self):
         bn = self.batch_norm.bn
         return (self.att.weight, self.self_r, self.graph_conv.weight, self.graph_conv.bias, bn.weight, bn.bias)
 
-    def _buffers(self):
+    def _bn_buffers(self):
         bn = self.batch_norm.bn
         return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
 
@@ -157,7 +157,7 @@ class GraphConv_block(nn.Module):
         cfg = EF.LayerConfig(fin=self.node_feature_in, fo=(self.node_feature_out,), training=False,
                              p_drop=float(self.dropout))
         H = EF.gather_rows(plan, afms)
-        X = EF.graph_conv_layer(plan, cfg, H, self._params(), self._buffers())
+        X = EF.graph_conv_layer(plan, cfg, H, self._view_params(), self._bn_buffers())
         # the reference block returns rows *before* the layer's mask3 (layers.py:313): padded rows there
         # hold relu(BN(bias)).  Reproduce that constant analytically on the dense output.
         x = EF.scatter_rows(plan, X)
@@ -236,8 +236,8 @@ class GraphConv_Layer(nn.Module):
                              stat_allreduce=self.stat_allreduce)
         params, buffers = [], []
         for b in self.blocks:
-            params += b._params()
-            buffers += b._buffers()
+            params += b._view_params()
+            buffers += b._bn_buffers()
         X = EF.graph_conv_layer(plan, cfg, H, params, buffers)
         x = PackedRows(X, plan) if packed_io else EF.scatter_rows(plan, X)            # layers.py:313
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 3
+#define EAGCN_ABI_VERSION 4
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -174,6 +174,15 @@ int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_layer_t* lay
 
 /* --- test hook: the keep mask eagcn_layer_forward_b draws (u8 [t_cap, fo_tot]) ------------- */
 int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out, void* stream);
+
+/* --- diagnostics (not on the data path; not thread-safe) ------------------------------------ */
+/* kernels launched by this library since load (bench.py: gpu_launches; under CUDA-graph replay the
+ * count taken while capturing one step is the number of kernel nodes replayed per step)          */
+int64_t eagcn_launch_count(void);
+/* opt-in per-kernel CUDA-event timing: enable(1) / disable(0), both clear what was recorded      */
+int eagcn_profile(int enable);
+/* writes {"kernel": [launches, total_ms], ...} into buf; returns bytes written, 0 if cap too small */
+int64_t eagcn_profile_report(char* buf, int64_t cap);
 
 #ifdef __cplusplus
 }

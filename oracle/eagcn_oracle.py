@@ -204,3 +204,63 @@ def rel_err(x: torch.Tensor, ref: torch.Tensor) -> float:
     if denom == 0.0:
         return float((x - ref).abs().max())
     return float((x.double() - ref.double()).abs().max()) / denom
+
+
+# --------------------------------------------------------------------------------------------
+# reference-cost form (cpu_baseline of bench.py): the SAME op sequence the reference executes --
+# 1x1 Conv2d over the dense one-hot planes, expanded masks, bmm + mm, BatchNorm1d on the permuted
+# tensor, F.dropout from torch's generator -- so its timing stands in for the reference's CPU path
+# on machines where /root/reference does not exist (the GPU box).
+# --------------------------------------------------------------------------------------------
+def block_forward_conv(sd, pre, adj, afm, rel, mask_tiny, mask2, identity, training, p):
+    a = sd[pre + "att.weight"]
+    B, N = adj.shape[0], adj.shape[1]
+    A1 = F.conv2d(rel.float(), a).view(B, N, -1)                                      # layers.py:82
+    A1 = torch.sigmoid(A1) * adj                                                      # layers.py:83
+    A = A1 + torch.sigmoid(sd[pre + "self_r"]) * identity + mask_tiny                 # layers.py:84
+    A_rowsum = torch.sum(A, dim=2, keepdim=True).expand(B, N, N)                      # layers.py:87
+    A = (A / A_rowsum) * mask2                                                        # layers.py:90
+    W = sd[pre + "graph_conv.weight"]
+    support = torch.bmm(A, afm)                                                       # layers.py:39
+    x = torch.mm(support.view(-1, W.shape[0]), W).view(-1, N, W.shape[1]) + sd[pre + "graph_conv.bias"]
+    x = x.permute(0, 2, 1)                                                            # layers.py:409-411
+    x = F.batch_norm(x.contiguous(), sd[pre + "batch_norm.bn.running_mean"], sd[pre + "batch_norm.bn.running_var"],
+                     sd[pre + "batch_norm.bn.weight"], sd[pre + "batch_norm.bn.bias"], training, MOM_BN, EPS_BN)
+    x = F.relu(x.permute(0, 2, 1))                                                    # layers.py:93
+    x = F.dropout(x, p=p, training=training)                                          # layers.py:94
+    return x, A1
+
+
+def layer_forward_conv(sd, pre, adj, afm, rels, training, p=0.0):
+    """GraphConv_Layer.forward in the reference's own op sequence (layers.py:293-325, 'Concate')."""
+    B, N = adj.shape[0], adj.shape[1]
+    mask_tiny = (1.0 - adj) * TINY                                                    # layers.py:294
+    mask_blank, _ = adj.max(dim=2, keepdim=True)                                      # layers.py:295
+    mask2 = mask_blank.expand(B, N, N)
+    identity = mask_blank.expand(B, N, N) * torch.eye(N)                              # layers.py:302-304
+    xs, As = [], []
+    for v, rel in enumerate(rels):
+        x, A1 = block_forward_conv(sd, f"{pre}block{v + 1}.", adj, afm, rel, mask_tiny, mask2, identity, training, p)
+        xs.append(x); As.append(A1)
+    x = torch.cat(xs, dim=2)
+    x = x * mask_blank.expand(B, N, x.shape[2])                                       # layers.py:313
+    return x, torch.stack(As, 0)                                                      # layers.py:318
+
+
+def model_forward_conv(sd, adj, afm, rels, sizes, n_layers, training, p=0.0):
+    """n_layers x GraphConv_Layer + sum read-out + head (models.py:96-121) with the reference's op sequence."""
+    h = afm
+    for l in range(n_layers):
+        h, _ = layer_forward_conv(sd, f"layer{l + 1}.", adj, h, rels, training, p)
+    _ = h.data.cpu()                                                                  # models.py:102
+    x = torch.sum(h, 1)                                                               # models.py:108
+
+    def bn(x, pre):
+        return F.batch_norm(x, sd[pre + "running_mean"], sd[pre + "running_var"], sd[pre + "weight"],
+                            sd[pre + "bias"], training, MOM_BN, EPS_BN)
+    x = bn(x, "Graph_BN.")
+    x = F.relu(bn(x.mm(sd["den1.weight"]), "bn_den1."))
+    x = F.dropout(x, p=p, training=training)
+    x = x.mm(sd["den2.weight"])
+    x = F.relu(bn(x, "bn_den2."))
+    return x.mm(sd["den3.weight"])

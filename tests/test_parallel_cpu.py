@@ -1,0 +1,115 @@
+"""CPU, world_size 2, gloo: the host-side data-parallel logic -- molecule sharding, the single
+flat-buffer gradient all-reduce, and the global-batch BatchNorm statistic combination -- checked against the
+single-process oracle on the concatenated batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from eagcn_b200 import parallel as PAR
+from eagcn_b200.data import make_batch, shard
+from oracle import eagcn_oracle as O
+from tests.util import Golden
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+# ---------------------------------------------------------------- flat gradient bucket
+def _flat_grad(rank, world):
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    frozen = torch.nn.Parameter(torch.zeros(4))                    # never receives a gradient
+    params = list(model.parameters()) + [frozen]
+    X = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+    lo, hi = rank * 4, rank * 4 + 4
+
+    class M(torch.nn.Module):
+        def parameters(self, recurse=True):
+            return iter(params)
+    holder = M()
+    bucket = PAR.FlatGradBucket.from_probe(holder, lambda: model(X[lo:hi]).sum().backward())
+    assert len(bucket.params) == 4 and bucket.flat.numel() == sum(p.numel() for p in model.parameters())
+    bucket.zero()
+    model(X[lo:hi]).sum().backward()                               # accumulates in place into the views
+    bucket.all_reduce(average=False)
+    return bucket.flat.clone().numpy()
+
+
+def test_flat_grad_allreduce_equals_full_batch():
+    out = _spawn(_flat_grad)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    X = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+    model(X).sum().backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).numpy()
+    np.testing.assert_allclose(out[0], ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(out[0], out[1])
+
+
+# ---------------------------------------------------------------- global-batch BatchNorm statistics
+def _bn_partials(rank, world):
+    g = Golden("layer_wide")
+    full = g.batch
+    sh = shard(full, rank, world)                                   # keeps the global padded width N
+    assert sh.N == full.N
+    M, Npad = PAR.global_population(sh.B, sh.N)
+    assert (M, Npad) == (full.B * full.N, full.N)
+    sd = O.clone_sd({("layer1." + k): v for k, v in g.sd.items()})
+    dense = [torch.from_numpy(a) for a in sh.dense()]
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    out = O.layer_forward(sd, "layer1.", dense[0], dense[1], codes, True)
+    m = O.row_mask(dense[0]).unsqueeze(2)
+    res = {}
+    for v in range(5):
+        b = sd[f"layer1.block{v + 1}.graph_conv.bias"]
+        D = (out["Y"][v] - b) * m                                   # what the CUDA agg kernel accumulates
+        sums = torch.stack([D.sum((0, 1)), (D * D).sum((0, 1))]).double()
+        PAR.make_stat_allreduce()(sums)
+        mean, var, invstd = PAR.combine_bn_partials(sums[0], sums[1], b.double(), float(M))
+        res[v] = (mean.numpy(), var.numpy())
+    return res
+
+
+def test_global_bn_statistics_match_single_process():
+    out = _spawn(_bn_partials)
+    g = Golden("layer_wide")
+    sd = O.clone_sd({("layer1." + k): v for k, v in g.sd.items()})
+    dense = g.dense()
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    ref = O.layer_forward(sd, "layer1.", dense[0], dense[1], codes, True)
+    for v in range(5):
+        Y = ref["Y"][v].reshape(-1, ref["Y"][v].shape[2])
+        mean, var = Y.mean(0).numpy(), Y.var(0, unbiased=False).numpy()
+        for r in (0, 1):
+            np.testing.assert_allclose(out[r][v][0], mean, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(out[r][v][1], var, rtol=1e-4, atol=1e-7)
+
+
+def test_shard_partitions_batch():
+    b = make_batch(10, "freesolv", seed=3)
+    parts = [shard(b, r, 4) for r in range(4)]
+    assert sum(p.B for p in parts) == 10
+    assert np.array_equal(np.concatenate([p.adj for p in parts]), b.adj)
+    assert all(p.N == b.N for p in parts)

@@ -358,7 +358,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
-                       "mode": "train fwd+bwd", "bn_sync": "local", "parallelism": f"dp{world}",
+                       "mode": "train fwd+bwd", "bn_sync": "local",
+                       "gemm_engine": "tcgen05 3xTF32 (NN, NT) + FFMA (TN)" if _lib.lib().eagcn_get_gemm_mode() == 0 else "FFMA", "parallelism": f"dp{world}",
                        "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
                        "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
                        "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
@@ -379,13 +380,37 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def usable_cores():
+    """Host threads this process can really use: CPU affinity capped by the cgroup CPU quota (a container on a
+    128-core host with a 16-CPU quota must not spawn 128 compute threads)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 # ------------------------------------------------------------------------------------------------
 def run_cpu_baseline(steps, warmup, budget_s):
     """The reference's CPU path (oracle reference-cost form: same ATen op sequence as layers.py / models.py)
     on the host cores, fwd+bwd, train mode, dropout 0.3.  Bounded: the batch is cut down if one step at
     B=256 would not fit the budget."""
     from oracle import eagcn_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     hb, _, _ = host_batch(seed=0)
     model_sd = None

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -53,7 +53,7 @@ class WorkStruct(ctypes.Structure):
                 ("p_drop", c_double), ("eps", c_double), ("momentum", c_double),
                 ("dX", c_void_p), ("dY", c_void_p), ("Q", c_void_p), ("dH", c_void_p), ("dwall", c_void_p),
                 ("dvec", c_void_p), ("datt", c_void_p), ("bsums", c_void_p), ("gemm_ws", c_void_p),
-                ("gemm_ws_bytes", c_int64)]
+                ("gemm_ws_bytes", c_int64), ("wallT", c_void_p)]
 
 
 _PROTOS = {
@@ -77,6 +77,10 @@ _PROTOS = {
     "eagcn_attention_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_attention_dense_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_dropout_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "eagcn_set_gemm_mode": (c_int, [c_int]),
+    "eagcn_get_gemm_mode": (c_int, []),
+    "eagcn_gemm_nt": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                              c_void_p, c_int, c_void_p]),
     "eagcn_launch_count": (c_int64, []),
     "eagcn_profile": (c_int, [c_int]),
     "eagcn_profile_report": (c_int64, [ctypes.c_char_p, c_int64]),

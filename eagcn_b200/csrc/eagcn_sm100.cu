@@ -1,5 +1,6 @@
 // Unity translation unit of libeagcn_sm100.so (one nvcc invocation, no relocatable device code).
 #include "gemm_simt.cu"
+#include "gemm_tc.cu"
 #include "pack.cu"
 #include "rows.cu"
 #include "layer_fwd.cu"
@@ -7,6 +8,28 @@
 #include "attention.cu"
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
+extern "C" int eagcn_set_gemm_mode(int mode) {
+  if (mode != 0 && mode != 1) return EAGCN_E_ARG;
+  eagcn::gemm_mode() = mode;
+  return 0;
+}
+extern "C" int eagcn_get_gemm_mode(void) { return eagcn::gemm_mode(); }
+extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,
+                             int64_t N, int64_t K, const void* m_dev, int engine, void* stream) {
+  if (!A || !B || !C || !m_dev || m_cap <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N) return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == 0) {
+    if ((m_cap % EAGCN_ROW_TILE) != 0 ||
+        !eagcn::tc::tc_supported((const float*)A, (int)lda, (const float*)B, (int)ldb, (int)K))
+      return EAGCN_E_UNSUPPORTED;
+    return eagcn::tc::gemm_tc_nt((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)C, (int)ldc, (int)m_cap,
+                                 (int)N, (int)K, (const int*)m_dev, st, "gemm_tc_nt");
+  }
+  if (engine == 1)
+    return eagcn::gemm_nt((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)C, (int)ldc, (int)m_cap, (int)N,
+                          (int)K, (const int*)m_dev, st);
+  return EAGCN_E_ARG;
+}
 
 // ---- diagnostics -----------------------------------------------------------------------------------
 #include <cstdio>

@@ -1,0 +1,343 @@
+// tcgen05 (5th-gen tensor core) projection GEMM with fp32-faithful 3xTF32 error compensation.
+//
+//   C[T, N] = A[T, K] . B[N, K]^T        A, B: fp32, K contiguous ("K-major") ;  C: fp32
+//
+// The dense contraction of the layer (reference layers.py:40) must match the fp32 reference to 1e-5,
+// which a single TF32 (10-bit mantissa) or BF16 pass cannot.  Each fp32 operand x is split exactly into
+//   x_hi = x with the 13 low mantissa bits cleared (exactly representable in TF32)
+//   x_lo = x - x_hi                                  (exact in fp32; TF32 keeps its top 11 bits)
+// and D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi is accumulated in fp32 in tensor memory: relative
+// product error ~2^-21, i.e. fp32-class, at 1/3 of the TF32 tensor rate (still >4x the FFMA peak).
+//
+// Structure (one 128 x BN output tile per CTA, BN <= 256 chosen on the host to fit N):
+//   warp 0     : TMA producer   -- cp.async.bulk.tensor 2D loads of the raw fp32 tiles, 128B-swizzled
+//   warps 2..5 : transform      -- split raw tiles into hi (in place) / lo (second buffer) in shared
+//                                  memory; the split is element-wise so it is swizzle-agnostic
+//   warp 1     : MMA issuer     -- one elected lane issues tcgen05.mma.kind::tf32 (UMMA 128 x BN x 8),
+//                                  accumulators live in TMEM; tcgen05.commit releases smem stages
+//   warps 2..5 : epilogue       -- tcgen05.ld 32x32b -> registers -> global (rows >= T masked)
+// mbarrier pipeline: full (TMA -> transform), ready (transform -> MMA), empty (MMA -> TMA), acc (MMA -> epilogue).
+// The number of valid rows T is read from device memory (plan.counts) -- no host synchronisation.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace eagcn {
+namespace tc {
+
+constexpr int BM = 128;            // UMMA M
+constexpr int BK = 32;             // fp32 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int UK = 8;              // UMMA K for kind::tf32 (32 bytes)
+constexpr int STAGES = 2;
+constexpr int kThreads = 192;      // warp0 TMA, warp1 MMA, warps 2..5 transform + epilogue
+constexpr int kXformThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (1024 B: 8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TcArgs {
+  float* C;
+  int ldc, Mcap, N, K, BN;
+  const int* Mdev;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
+  const int M = min(*g.Mdev, g.Mcap);
+
+  if (m0 >= M) {                       // tile entirely beyond the live rows: keep slack rows defined (zeros)
+    for (int i = threadIdx.x; i < BM * g.BN; i += kThreads) {
+      const int r = m0 + i / g.BN, c = n0 + i % g.BN;
+      if (r < g.Mcap && c < g.N) g.C[(size_t)r * g.ldc + c] = 0.0f;
+    }
+    return;
+  }
+
+  // 1024-byte aligned carve-up: per stage [A raw/hi | A lo | B raw/hi | B lo]
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t bytesA = BM * BK * 4, bytesB = (uint32_t)g.BN * BK * 4;
+  const uint32_t stage_bytes = 2 * bytesA + 2 * bytesB;
+  auto sA_hi = [&](int s) { return base + (size_t)s * stage_bytes; };
+  auto sA_lo = [&](int s) { return base + (size_t)s * stage_bytes + bytesA; };
+  auto sB_hi = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA; };
+  auto sB_lo = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA + bytesB; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_ready[s], kXformThreads);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                     // TMEM allocation by one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_smem;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
+        mbar_expect_tx(&bar_full[s], bytesA + bytesB);
+        tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
+        tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (bit4), a=b=TF32 (2<<7, 2<<10), K-major A/B,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(&bar_ready[s], it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dAh = make_desc(smem_u32(sA_hi(s))), dAl = make_desc(smem_u32(sA_lo(s)));
+        const uint64_t dBh = make_desc(smem_u32(sB_hi(s))), dBl = make_desc(smem_u32(sB_lo(s)));
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k) {
+          const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);     // +32 bytes per UMMA_K inside the 128B swizzle row
+          umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+          umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, 1u);
+        }
+        umma_commit(&bar_empty[s]);                               // smem stage free once these MMAs retire
+        if (kb == num_kb - 1) umma_commit(&bar_acc);              // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== transform (hi/lo split), then epilogue =====================
+    const int xt = threadIdx.x - 64;                              // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(&bar_full[s], it & 1);
+      {
+        uint4* hi = reinterpret_cast<uint4*>(sA_hi(s));
+        uint4* lo = reinterpret_cast<uint4*>(sA_lo(s));
+        for (int i = xt; i < (int)(bytesA / 16); i += kXformThreads) {
+          uint4 x = hi[i], h, l;
+          h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+          l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+          hi[i] = h; lo[i] = l;
+        }
+      }
+      {
+        uint4* hi = reinterpret_cast<uint4*>(sB_hi(s));
+        uint4* lo = reinterpret_cast<uint4*>(sB_lo(s));
+        for (int i = xt; i < (int)(bytesB / 16); i += kXformThreads) {
+          uint4 x = hi[i], h, l;
+          h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+          l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+          hi[i] = h; lo[i] = l;
+        }
+      }
+      fence_proxy_async();                                         // generic-proxy writes -> visible to UMMA (async proxy)
+      mbar_arrive(&bar_ready[s]);
+    }
+    // ---- epilogue: TMEM -> registers -> global ----
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                                     // TMEM lane quadrant this warp may access
+    const int row = m0 + quad * 32 + lane;
+    const bool live = row < M;
+    const bool in_cap = row < g.Mcap;
+    float* crow = g.C + (size_t)row * g.ldc;
+    const bool vec = ((g.ldc & 3) == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    for (int c0 = 0; c0 < g.BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (in_cap) {
+        const int cbase = n0 + c0;
+        if (vec && cbase + 32 <= g.N && c0 + 32 <= g.BN) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = live ? __uint_as_float(r[j]) : 0.f; o.y = live ? __uint_as_float(r[j + 1]) : 0.f;
+            o.z = live ? __uint_as_float(r[j + 2]) : 0.f; o.w = live ? __uint_as_float(r[j + 3]) : 0.f;
+            *reinterpret_cast<float4*>(crow + cbase + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (c < g.N && c0 + j < g.BN) crow[c] = live ? __uint_as_float(r[j]) : 0.f;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(g.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D fp32 row-major [rows, cols] (cols contiguous), box = [box_rows, 32 floats], 128B swizzle, OOB -> 0
+static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// N-tile width: multiple of 16, <= 256, smallest padding of N, ties -> fewer tiles
+static int pick_bn(int N) {
+  int best = 128, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 16) {
+    const int tiles = (N + bn - 1) / bn;
+    const int waste = tiles * bn - N;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
+  }
+  return best;
+}
+
+bool tc_supported(const float* A, int lda, const float* B, int ldb, int K) {
+  return (lda % 4 == 0) && (ldb % 4 == 0) && K >= 1 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && encode_fn() != nullptr;
+}
+
+// C[Mcap(T live), N] = A[Mcap, K] . B[N, K]^T   (both K-contiguous)
+int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
+               const int* Mdev, cudaStream_t st, const char* tag) {
+  const int BN = pick_bn(N);
+  CUtensorMap mA, mB;
+  if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0};
+  g.tmem_cols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (Mcap + BM - 1) / BM, 1);
+  EAGCN_PROF(tag, st);
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, g);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace eagcn

@@ -335,8 +335,13 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   datt_reduce_kernel<<<(L.V * EAGCN_SIG_STRIDE + 255) / 256, 256, 0, st>>>(p, (const float*)w->partial, (float*)w->datt,
                                                                            L.V);
   EAGCN_LAUNCH_CHECK();
-  int rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
-                   p.counts + EAGCN_CNT_T, st);
+  int rc;
+  if (gemm_mode() == 0 && tc::tc_supported((const float*)w->Q, C, (const float*)w->wall, C, C))
+    rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
+                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nt");
+  else
+    rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
+                 p.counts + EAGCN_CNT_T, st);
   if (rc) return rc;
   rc = gemm_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->dwall, L.fin, C, p.t_cap,
                p.counts + EAGCN_CNT_T, (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st);

@@ -23,9 +23,10 @@ namespace eagcn {
 
 int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
             const int* Mdev, cudaStream_t st);
+inline int& gemm_mode() { static int m = 0; return m; }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __restrict__ wall,
+__global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __restrict__ wall, float* __restrict__ wallT,
                                                           float* __restrict__ ball, float* __restrict__ sig) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long nW = (long long)L.fin * L.fo_tot;
@@ -33,7 +34,9 @@ __global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __r
     const int k = (int)(idx / L.fo_tot), c = (int)(idx - (long long)k * L.fo_tot);
     int v = 0;
     while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
-    wall[idx] = __ldg(L.W[v] + (long long)k * L.fo[v] + (c - L.off[v]));
+    const float wv = __ldg(L.W[v] + (long long)k * L.fo[v] + (c - L.off[v]));
+    wall[idx] = wv;
+    if (wallT) wallT[(long long)c * L.fin + k] = wv;
   }
   if (idx < L.fo_tot) {
     const int c = (int)idx;
@@ -284,10 +287,15 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
   if (n < C) n = C;
   EAGCN_PROF("prep_params_kernel", st);
-  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->ball, (float*)w->sig);
+  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->wallT, (float*)w->ball, (float*)w->sig);
   EAGCN_LAUNCH_CHECK();
-  int rc = gemm_nn((const float*)w->H, L.fin, (const float*)w->wall, C, (float*)w->Z, C, p.t_cap, C, L.fin,
-                   p.counts + EAGCN_CNT_T, st);
+  int rc;
+  if (gemm_mode() == 0 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
+    rc = tc::gemm_tc_nt((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, (float*)w->Z, C, p.t_cap, C, L.fin,
+                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nn");
+  else
+    rc = gemm_nn((const float*)w->H, L.fin, (const float*)w->wall, C, (float*)w->Z, C, p.t_cap, C, L.fin,
+                 p.counts + EAGCN_CNT_T, st);
   if (rc) return rc;
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);

@@ -118,6 +118,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         X = torch.empty(T, C, **f32)
         invR = torch.empty(plan.V, T, **f32)
         wall = torch.empty(cfg.fin, C, **f32)
+        wallT = torch.empty(C, cfg.fin, **f32)
         ball = torch.empty(4, C, **f32)
         sig = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
@@ -130,6 +131,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
             rng_snapshot = rng.state.clone()        # backward regenerates the same keep mask from it
         w.H, w.Z, w.Y, w.X, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(X), ptr(invR)
         w.wall, w.ball, w.sig, w.partial, w.sums = ptr(wall), ptr(ball), ptr(sig), ptr(partial), ptr(sums)
+        w.wallT = ptr(wallT)
         w.mean, w.invstd = ptr(mean), ptr(invstd)
         w.rng = ptr(rng_snapshot)
         w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
@@ -144,7 +146,6 @@ class _GraphConvLayerFn(torch.autograd.Function):
             rng.advance()
         ctx.plan, ctx.cfg, ctx.buffers, ctx.params = plan, cfg, buffers, params
         ctx.saved = (H, Z, Y, invR, wall, ball, sig, mean, invstd, rng_snapshot)
-        ctx.mark_non_differentiable()
         return X
 
     @staticmethod
@@ -300,3 +301,17 @@ def dropout_keep_mask(plan, cfg: LayerConfig, fo_tot, rng_state):
     keep = torch.empty(plan.t_cap, fo_tot, dtype=torch.uint8, device=plan.device)
     check(lib().eagcn_dropout_mask(plan.ref, ctypes.byref(w), fo_tot, ptr(keep), _stream()), "eagcn_dropout_mask")
     return keep
+
+
+def gemm_nt(A, B, m_dev, engine=0):
+    """C = A @ B.T on the projection GEMM engine (0: tcgen05 3xTF32, 1: FFMA); rows >= m_dev[0] come back zero."""
+    A, B = A.contiguous(), B.contiguous()
+    C = torch.empty(A.shape[0], B.shape[0], dtype=_F32, device=A.device)
+    check(lib().eagcn_gemm_nt(ptr(A), A.shape[1], ptr(B), B.shape[1], ptr(C), B.shape[0], A.shape[0], B.shape[0],
+                              A.shape[1], ptr(m_dev), engine, _stream()), "eagcn_gemm_nt")
+    return C
+
+
+def set_gemm_engine(name: str):
+    """'tcgen05' (default: tensor cores with 3xTF32 compensation where the layout allows) or 'ffma'."""
+    check(lib().eagcn_set_gemm_mode({"tcgen05": 0, "ffma": 1}[name]), "eagcn_set_gemm_mode")

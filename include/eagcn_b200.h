@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 4
+#define EAGCN_ABI_VERSION 5
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -124,6 +124,7 @@ typedef struct eagcn_work {
   void* bsums;    /* f64 [2, fo_tot]       backward batch sums (sum g, sum g*xhat)         */
   void* gemm_ws;  /* f32 split-K workspace, gemm_ws_bytes bytes                            */
   int64_t gemm_ws_bytes;
+  void* wallT;    /* f32 [fo_tot, fin]     W_all transposed (K-major B operand of the tcgen05 GEMM) */
 } eagcn_work_t;
 
 int eagcn_version(void);
@@ -174,6 +175,18 @@ int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_layer_t* lay
 
 /* --- test hook: the keep mask eagcn_layer_forward_b draws (u8 [t_cap, fo_tot]) ------------- */
 int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out, void* stream);
+
+/* --- projection GEMM engine ------------------------------------------------------------------ */
+/* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned
+ * rows), FFMA kernel otherwise; 1: always the FFMA kernel.  Process-wide setting.               */
+int eagcn_set_gemm_mode(int mode);
+int eagcn_get_gemm_mode(void);
+/* stand-alone projection product  C[m_cap, N] = A[m_cap, K] . B[N, K]^T  (fp32, rows contiguous; lda/ldb/ldc
+ * in elements).  Only the first min(*m_dev, m_cap) rows are live (m_dev: device int32); the remaining
+ * rows of C are written as zeros.  engine: 0 = tcgen05 3xTF32 (EAGCN_E_UNSUPPORTED if the layout does
+ * not allow it), 1 = FFMA.  This is reference layers.py:40 (torch.mm(support, W)) in isolation.    */
+int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,
+                  int64_t N, int64_t K, const void* m_dev, int engine, void* stream);
 
 /* --- diagnostics (not on the data path; not thread-safe) ------------------------------------ */
 /* kernels launched by this library since load (bench.py: gpu_launches; under CUDA-graph replay the

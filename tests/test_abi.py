@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from eagcn_b200 import _lib
     assert ctypes.sizeof(_lib.PlanStruct) == 8 * (5 + 16 + 12)
     assert ctypes.sizeof(_lib.LayerStruct) == 8 * (3 + 16 + 17 + 9 * 16)
-    assert ctypes.sizeof(_lib.WorkStruct) == 8 * 30
+    assert ctypes.sizeof(_lib.WorkStruct) == 8 * 31
 
 
 def test_size_helpers():

@@ -181,6 +181,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
+    from eagcn_b200 import functional as EF
+    EF.set_gemm_engine(args.gemm)
     model = build_model(dev)
     NB = args.nbatches
     slots = []
@@ -214,6 +216,12 @@ def run_b200(args):
     # which parameters get gradients -> flat buffer (one all-reduce per step for N > 1)
     bucket = FlatGradBucket.from_probe(model, lambda: step_dense(slots[0]))
     torch.cuda.synchronize()
+    if args.profile_only:
+        for i in range(args.warmup + args.steps):
+            bucket.zero(); step_dense(slots[i % NB])
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_only": True, "steps": args.steps, "warmup": args.warmup}))
+        return
 
     # ---- capture one CUDA graph per (batch, layout) ----
     side = torch.cuda.Stream()
@@ -348,7 +356,7 @@ def run_b200(args):
             roof["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 5), "share": round(v["share"], 4),
                                    "launches_per_step": v["launches_per_step"]} for k, v in
                                sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])}
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             cpu = run_cpu_baseline(steps=3, warmup=1, budget_s=25.0)
 
     if rank == 0:
@@ -493,6 +501,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nbatches", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma"], help="projection GEMM engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -92,6 +92,16 @@ __device__ __forceinline__ bool dropout_keep(const Philox& ph, uint64_t offset, 
   return (float)(x >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
+// vector form: keep flags of the 4 consecutive elements idx4 .. idx4+3 (idx4 % 4 == 0), one philox call
+__device__ __forceinline__ void dropout_keep4(const Philox& ph, uint64_t offset, uint64_t stream, uint64_t idx4, float p,
+                                              bool (&keep)[4]) {
+  const uint4 r = ph((idx4 >> 2) + offset, stream);
+  keep[0] = (float)(r.x >> 8) * (1.0f / 16777216.0f) >= p;
+  keep[1] = (float)(r.y >> 8) * (1.0f / 16777216.0f) >= p;
+  keep[2] = (float)(r.z >> 8) * (1.0f / 16777216.0f) >= p;
+  keep[3] = (float)(r.w >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
 struct LayerDev {                 // by-value kernel argument: per-view parameter pointers
   int V, fin, fo_tot;
   int fo[EAGCN_MAX_VIEWS];
@@ -148,6 +158,8 @@ inline bool plan_ok(const eagcn_plan_t* p) {
          p->row_pos && p->row_ptr && p->mol_ptr && p->col && p->colpos && p->rev && p->code && p->rcode &&
          p->B * p->N < (int64_t)2147483000;
 }
+
+inline bool aligned16(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; }
 
 inline bool plan_ok_count(const eagcn_plan_t* p) {
   return p && p->B > 0 && p->N > 0 && p->V > 0 && p->V <= EAGCN_MAX_VIEWS && p->counts && p->deg && p->blk &&

@@ -116,6 +116,96 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(PlanDev p, const floa
   dY[idx] = gam * invstd[c] * r;
 }
 
+// ---- float4 forms (C % 4 == 0) --------------------------------------------------------------------
+__device__ __forceinline__ void grad_through_act4(const float4 dx, const float4 y, const float4 mu, const float4 is,
+                                                  const float4 ga, const float4 be, bool drop, float scale, const Philox& ph,
+                                                  unsigned long long off, unsigned long long stream,
+                                                  unsigned long long idx, float p_drop, float (&g)[4], float (&xh)[4]) {
+  xh[0] = (y.x - mu.x) * is.x; xh[1] = (y.y - mu.y) * is.y; xh[2] = (y.z - mu.z) * is.z; xh[3] = (y.w - mu.w) * is.w;
+  g[0] = xh[0] * ga.x + be.x > 0.f ? dx.x : 0.f; g[1] = xh[1] * ga.y + be.y > 0.f ? dx.y : 0.f;
+  g[2] = xh[2] * ga.z + be.z > 0.f ? dx.z : 0.f; g[3] = xh[3] * ga.w + be.w > 0.f ? dx.w : 0.f;
+  if (drop) {
+    bool k[4];
+    dropout_keep4(ph, off, stream, idx, p_drop, k);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u] = k[u] ? g[u] * scale : 0.f;
+  }
+}
+
+// grid (stat tiles, ceil(C/4/128)); a thread owns 4 channels for the 64 rows of its tile (fixed order)
+__global__ void __launch_bounds__(128) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
+                                                                 const float* __restrict__ Y, const float* __restrict__ ball,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 float* __restrict__ partial, int C, int training, float p_drop,
+                                                                 const unsigned long long* rng, unsigned long long stream) {
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int tile = blockIdx.x;
+  if (tile * kStatRows >= T) return;
+  const int c = (blockIdx.y * 128 + threadIdx.x) * 4;
+  if (c >= C) return;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 ga = *reinterpret_cast<const float4*>(ball + C + c), be = *reinterpret_cast<const float4*>(ball + 2 * C + c);
+  const bool drop = training && p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r1 = min(T, (tile + 1) * kStatRows);
+#pragma unroll 4
+  for (int t = tile * kStatRows; t < r1; ++t) {
+    const size_t idx = (size_t)t * C + c;
+    const float4 dx = __ldg(reinterpret_cast<const float4*>(dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
+    float g[4], xh[4];
+    grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, off, stream, (unsigned long long)idx, p_drop, g, xh);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s1[u] += g[u]; s2[u] = fmaf(g[u], xh[u], s2[u]); }
+  }
+  *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + 0) * C + c) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + 1) * C + c) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+}
+
+// grid (ceil(C/4/128), ceil(t_cap/16))
+__global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const float* __restrict__ dX,
+                                                               const float* __restrict__ Y, const float* __restrict__ ball,
+                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                               const double* __restrict__ bsums, float* __restrict__ dY, int C,
+                                                               int training, float p_drop, const unsigned long long* rng,
+                                                               unsigned long long stream, double M) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 ga = *reinterpret_cast<const float4*>(ball + C + c), be = *reinterpret_cast<const float4*>(ball + 2 * C + c);
+  const bool drop = training && p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+  float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (training) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { m1[u] = (float)(bsums[c + u] / M); m2[u] = (float)(bsums[C + c + u] / M); }
+  }
+  const float gi[4] = {ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w};
+  const int r0 = blockIdx.y * 16, r1 = min(p.t_cap, r0 + 16);
+#pragma unroll 4
+  for (int t = r0; t < r1; ++t) {
+    const size_t idx = (size_t)t * C + c;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) {
+      const float4 dx = __ldg(reinterpret_cast<const float4*>(dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
+      float g[4], xh[4];
+      grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, off, stream, (unsigned long long)idx, p_drop, g, xh);
+      float r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = gi[u] * (training ? (g[u] - m1[u] - xh[u] * m2[u]) : g[u]);
+      o = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    *reinterpret_cast<float4*>(dY + idx) = o;
+  }
+}
+
 // dvec = [dbias | dgamma | dbeta]
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ ball, const float* __restrict__ invstd,
                                                               const double* __restrict__ bsums, float* __restrict__ dvec,
@@ -282,13 +372,24 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   cudaStream_t st = (cudaStream_t)stream;
   PlanDev p = to_dev(plan);
   const int C = (int)layer->fo_tot;
-  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
-  EAGCN_PROF("bn_bwd_partial_kernel", st);
-  bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
-                                              (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
-                                              w->training ? 1 : 0, (float)w->p_drop,
-                                              (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
-  EAGCN_LAUNCH_CHECK();
+  if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y)) {
+    dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 127) / 128);
+    EAGCN_PROF("bn_bwd_partial_kernel", st);
+    bn_bwd_partial_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+                                                    (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
+                                                    C, w->training ? 1 : 0, (float)w->p_drop,
+                                                    (const unsigned long long*)w->rng,
+                                                    (unsigned long long)w->rng_stream);
+    EAGCN_LAUNCH_CHECK();
+  } else {
+    dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
+    EAGCN_PROF("bn_bwd_partial_kernel", st);
+    bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+                                                (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
+                                                w->training ? 1 : 0, (float)w->p_drop,
+                                                (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
+    EAGCN_LAUNCH_CHECK();
+  }
   EAGCN_PROF("stat_reduce_kernel", st);
   stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->bsums, C);
   EAGCN_LAUNCH_CHECK();
@@ -307,12 +408,22 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const long long total = (long long)p.t_cap * C;
-  EAGCN_PROF("bn_bwd_apply_kernel", st);
-  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
-      (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
-      (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
-  EAGCN_LAUNCH_CHECK();
+  if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY)) {
+    dim3 grid((C / 4 + 127) / 128, (p.t_cap + 15) / 16);
+    EAGCN_PROF("bn_bwd_apply_kernel", st);
+    bn_bwd_apply_vec_kernel<<<grid, 128, 0, st>>>(
+        p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
+        (const float*)w->invstd, (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
+        (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
+    EAGCN_LAUNCH_CHECK();
+  } else {
+    EAGCN_PROF("bn_bwd_apply_kernel", st);
+    bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
+        (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
+        (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
+    EAGCN_LAUNCH_CHECK();
+  }
   EAGCN_PROF("bn_bwd_finalize_kernel", st);
   bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
                                                           (const double*)w->bsums, (float*)w->dvec, C,

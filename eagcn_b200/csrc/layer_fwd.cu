@@ -240,6 +240,45 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(PlanDev p, const float* _
   X[idx] = x;
 }
 
+// float4 form (C % 4 == 0): grid (ceil(C/4/128), ceil(t_cap/16)); a thread owns 4 channels for 16 rows
+__global__ void __launch_bounds__(128) bn_apply_vec_kernel(PlanDev p, const float* __restrict__ Y,
+                                                           const float* __restrict__ ball, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, float* __restrict__ X, int C,
+                                                           int training, float p_drop, const unsigned long long* rng,
+                                                           unsigned long long rng_stream) {
+  const int c4 = blockIdx.x * 128 + threadIdx.x;
+  if (c4 * 4 >= C) return;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int c = c4 * 4;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 ga = *reinterpret_cast<const float4*>(ball + C + c), be = *reinterpret_cast<const float4*>(ball + 2 * C + c);
+  const bool drop = training && p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+  const int r0 = blockIdx.y * 16, r1 = min(p.t_cap, r0 + 16);
+#pragma unroll 4
+  for (int t = r0; t < r1; ++t) {
+    const size_t idx = (size_t)t * C + c;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) {
+      const float4 y = __ldg(reinterpret_cast<const float4*>(Y + idx));
+      o.x = fmaxf((y.x - mu.x) * is.x * ga.x + be.x, 0.f);
+      o.y = fmaxf((y.y - mu.y) * is.y * ga.y + be.y, 0.f);
+      o.z = fmaxf((y.z - mu.z) * is.z * ga.z + be.z, 0.f);
+      o.w = fmaxf((y.w - mu.w) * is.w * ga.w + be.w, 0.f);
+      if (drop) {
+        bool k[4];
+        dropout_keep4(ph, off, rng_stream, (unsigned long long)idx, p_drop, k);
+        o.x = k[0] ? o.x * scale : 0.f; o.y = k[1] ? o.y * scale : 0.f;
+        o.z = k[2] ? o.z * scale : 0.f; o.w = k[3] ? o.w * scale : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(X + idx) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) dropout_mask_kernel(long long total, float p_drop,
                                                            const unsigned long long* rng, unsigned long long rng_stream,
                                                            uint8_t* __restrict__ keep) {
@@ -334,11 +373,21 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
                                                       (float*)w->invstd, w->training ? 1 : 0, M, w->eps, w->momentum);
   EAGCN_LAUNCH_CHECK();
   const long long total = (long long)p.t_cap * C;
-  EAGCN_PROF("bn_apply_kernel", st);
-  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
-      w->training ? 1 : 0, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
-  EAGCN_LAUNCH_CHECK();
+  if ((C & 3) == 0 && aligned16(w->Y) && aligned16(w->X)) {
+    dim3 grid((C / 4 + 127) / 128, (p.t_cap + 15) / 16);
+    EAGCN_PROF("bn_apply_kernel", st);
+    bn_apply_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
+                                              (const float*)w->invstd, (float*)w->X, C, w->training ? 1 : 0,
+                                              (float)w->p_drop, (const unsigned long long*)w->rng,
+                                              (unsigned long long)w->rng_stream);
+    EAGCN_LAUNCH_CHECK();
+  } else {
+    EAGCN_PROF("bn_apply_kernel", st);
+    bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
+        w->training ? 1 : 0, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
+    EAGCN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -18,21 +18,18 @@
 
 namespace eagcn {
 
-constexpr int kPackRows = 64;      // padded rows per CTA
-constexpr int kPackThreads = 256;  // 8 warps x 8 rows
+constexpr int kPackRows = 32;      // padded rows per CTA
+constexpr int kPackThreads = 256;  // 8 warps x 4 rows
+constexpr int kRowsPerWarp = kPackRows / 8;
 
 struct RelPtrs { const float* p[EAGCN_MAX_VIEWS]; };
 
+// adjacency value at (b,i,j): from the dense fp32 adjacency or from the view-0 uint8 code plane
 template <bool kCodes>
-__device__ __forceinline__ bool edge_at(const float* adj, const uint8_t* codes, const PlanDev& p, int b, int i, int j,
-                                         bool& bad) {
-  if (kCodes) {
-    return codes[(((size_t)b * p.V + 0) * p.N + i) * p.N + j] != EAGCN_NO_EDGE;
-  } else {
-    float a = adj[((size_t)b * p.N + i) * p.N + j];
-    if (a != 0.0f && a != 1.0f) bad = true;
-    return a != 0.0f;
-  }
+__device__ __forceinline__ float adj_at(const float* __restrict__ adj, const uint8_t* __restrict__ codes, const PlanDev& p,
+                                        size_t row_base_adj, size_t row_base_code, int j) {
+  if (kCodes) return __ldg(codes + row_base_code + j) != EAGCN_NO_EDGE ? 1.0f : 0.0f;
+  return __ldg(adj + row_base_adj + j);
 }
 
 template <bool kCodes>
@@ -42,20 +39,34 @@ __global__ void __launch_bounds__(kPackThreads) pack_count_kernel(PlanDev p, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
   bool bad = false;
-  for (int r = 0; r < 8; ++r) {
-    const int lr = warp * 8 + r;
-    const int row = blockIdx.x * kPackRows + lr;
-    int cnt = 0;
-    if (row < P) {
-      const int b = row / p.N, i = row - b * p.N;
-      for (int j0 = 0; j0 < p.N; j0 += 32) {
-        const int j = j0 + lane;
-        bool nz = (j < p.N) && edge_at<kCodes>(adj, codes, p, b, i, j, bad);
-        cnt += __popc(__ballot_sync(0xffffffffu, nz));
-      }
-      if (lane == 0) p.deg[row] = cnt;
+  int cnt[kRowsPerWarp];
+  size_t ba[kRowsPerWarp], bc[kRowsPerWarp];
+  bool ok[kRowsPerWarp];
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int row = blockIdx.x * kPackRows + warp * kRowsPerWarp + r;
+    ok[r] = row < P;
+    const int b = ok[r] ? row / p.N : 0, i = ok[r] ? row - b * p.N : 0;
+    ba[r] = ((size_t)b * p.N + i) * p.N;
+    bc[r] = (((size_t)b * p.V) * p.N + i) * p.N;
+    cnt[r] = 0;
+  }
+  for (int j0 = 0; j0 < p.N; j0 += 32) {
+    const int j = j0 + lane;
+    float a[kRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)                       // independent loads first (latency overlap)
+      a[r] = (ok[r] && j < p.N) ? adj_at<kCodes>(adj, codes, p, ba[r], bc[r], j) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      if (a[r] != 0.0f && a[r] != 1.0f) bad = true;
+      cnt[r] += __popc(__ballot_sync(0xffffffffu, a[r] != 0.0f));
     }
-    if (lane == 0) s_deg[lr] = cnt;
+  }
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int row = blockIdx.x * kPackRows + warp * kRowsPerWarp + r;
+    if (lane == 0) { s_deg[warp * kRowsPerWarp + r] = cnt[r]; if (ok[r]) p.deg[row] = cnt[r]; }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_ADJ_NOT_01);
   __syncthreads();
@@ -105,6 +116,7 @@ template <bool kCodes>
 __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, const float* __restrict__ adj,
                                                                  const uint8_t* __restrict__ codes, RelPtrs rel) {
   __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
+  __shared__ int s_code[8][32], s_cnt[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
   const int row0 = blockIdx.x * kPackRows;
@@ -137,8 +149,8 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
     if (T <= p.t_cap) p.row_ptr[T] = E;
   }
   bool bad = false;
-  for (int r = 0; r < 8; ++r) {
-    const int lr = warp * 8 + r;
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int lr = warp * kRowsPerWarp + r;
     const int row = row0 + lr;
     if (row >= P) break;
     const int deg = s_deg[lr];
@@ -146,35 +158,50 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
     const int e0 = s_e[lr];
     if (e0 + deg > p.e_cap) continue;            // status already flagged by the scan
     const int b = row / p.N, i = row - b * p.N;
+    const size_t ba = ((size_t)b * p.N + i) * p.N, bc = (((size_t)b * p.V) * p.N + i) * p.N;
     int run = 0;
     for (int j0 = 0; j0 < p.N; j0 += 32) {
       const int j = j0 + lane;
-      bool dummy = false;
-      const bool nz = (j < p.N) && edge_at<kCodes>(adj, codes, p, b, i, j, dummy);
+      const bool nz = (j < p.N) && adj_at<kCodes>(adj, codes, p, ba, bc, j) != 0.0f;
       const unsigned m = __ballot_sync(0xffffffffu, nz);
       if (m == 0) continue;
-      const int e = e0 + run + __popc(m & ((1u << lane) - 1u));
-      if (nz) p.colpos[e] = b * p.N + j;
+      const int ne = __popc(m);
+      const int slot = __popc(m & ((1u << lane) - 1u));          // edge index of this lane inside the chunk
+      if (nz) p.colpos[e0 + run + slot] = b * p.N + j;
       for (int v = 0; v < p.V; ++v) {
         const int C = p.chan[v];
-        int found = C;
-        if (nz) {
-          if (kCodes) {
-            const int c = codes[(((size_t)b * p.V + v) * p.N + i) * p.N + j];
-            if (c > C) bad = true; else found = c;
-          } else {
-            const float* base = rel.p[v] + (((size_t)b * C) * p.N + i) * p.N + j;
-            int cnt = 0;
-            for (int c = 0; c < C; ++c) {
-              const float x = __ldg(base + (size_t)c * p.N * p.N);
-              if (x != 0.0f) { ++cnt; found = c; if (x != 1.0f) bad = true; }
-            }
-            if (cnt > 1) bad = true;
+        if (kCodes) {
+          if (nz) {
+            const int c = __ldg(codes + bc + (size_t)v * p.N * p.N + j);
+            if (c > C) bad = true;
+            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)(c > C ? C : c);
           }
-          p.code[(size_t)v * p.e_cap + e] = (uint8_t)found;
+        } else {
+          // gather the C_v one-hot planes at the ne bonded pairs of this chunk: (edge, channel) pairs are
+          // spread over the lanes, consecutive lanes -> neighbouring columns of the same plane
+          s_code[warp][lane] = C; s_cnt[warp][lane] = 0;
+          __syncwarp();
+          const float* base = rel.p[v] + (((size_t)b * C) * p.N + i) * p.N + j0;
+          const int total = ne * C;
+          for (int idx = lane; idx < total; idx += 32) {
+            const int k = idx % ne, c = idx / ne;
+            const int jj = __fns(m, 0, k + 1);                   // lane position of the k-th edge
+            const float x = __ldg(base + (size_t)c * p.N * p.N + jj);
+            if (x != 0.0f) {
+              if (x != 1.0f) bad = true;
+              atomicAdd(&s_cnt[warp][k], 1);
+              s_code[warp][k] = c;
+            }
+          }
+          __syncwarp();
+          if (nz) {
+            if (s_cnt[warp][slot] > 1) bad = true;
+            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)s_code[warp][slot];
+          }
+          __syncwarp();
         }
       }
-      run += __popc(m);
+      run += ne;
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_NOT_ONEHOT);

@@ -50,7 +50,7 @@ class GraphPlan:
         i32 = dict(dtype=torch.int32, device=self.device)
         self.counts = torch.zeros(8, **i32)
         self.deg = torch.empty(P, **i32)
-        self.blk = torch.empty(2 * ((P + 63) // 64) + 2, **i32)
+        self.blk = torch.empty(2 * ((P + 31) // 32) + 2, **i32)
         self.pos_row = torch.empty(P, **i32)
         self.mol_ptr = torch.empty(self.B + 1, **i32)
 

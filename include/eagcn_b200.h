@@ -58,7 +58,7 @@ typedef struct eagcn_plan {
   int64_t chan[EAGCN_MAX_VIEWS];    /* C_v: channels of relation tensor v                  */
   void* counts;                     /* int32 [8]                                           */
   void* deg;                        /* int32 [B*N]        scratch (degree per flat row)    */
-  void* blk;                        /* int32 [2*nblk+2]   scratch, nblk = ceil(B*N/256)    */
+  void* blk;                        /* int32 [2*nblk+2]   scratch, nblk = ceil(B*N/32)     */
   void* pos_row;                    /* int32 [B*N]        flat position -> row or -1       */
   void* row_pos;                    /* int32 [t_cap]      row -> flat position             */
   void* row_ptr;                    /* int32 [t_cap+1]    CSR offsets                      */

@@ -27,8 +27,10 @@ def test_gemm_nt_vs_float64(engine, Mcap, T, N, K):
     torch.cuda.synchronize()
     ref = (A[:T].double() @ B.double().t())
     err = float((C[:T].double() - ref).abs().max()) / float(ref.abs().max())
-    # fp32-class accuracy: FFMA ~1e-7, 3xTF32 tensor-core ~1e-6 of max
-    assert err <= 3e-6, (engine, err)
+    print(f"engine {engine} M={T} N={N} K={K}: err {err:.2e}")
+    # fp32-class accuracy: FFMA ~1e-7 of max; 3xTF32 tensor-core a few 1e-6 (truncating fp32 accumulation in
+    # the tensor core, K/8 steps) -- inside the 1e-5 layer-level parity bar
+    assert err <= (6e-6 if engine == 0 else 1e-6), (engine, err)
     assert float(C[T:].abs().max()) == 0.0 if T < Mcap else True
 
 

@@ -201,24 +201,44 @@ def run_b200(args):
         slots.append(s)
     torch.cuda.synchronize()
 
+    params = [p for p in model.parameters() if p.requires_grad]
+
     def step_dense(s):
+        for p in params:
+            p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
         plan = GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
         out, _, _ = model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
         return out
 
     def step_codes(s):
+        for p in params:
+            p.grad = None
         plan = GraphPlan.from_codes(s.dev_codes, s.hb.channels, t_cap=s.t_cap, e_cap=s.e_cap)
         out, _, _ = model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
         return out
 
-    # which parameters get gradients -> flat buffer (one all-reduce per step for N > 1)
-    bucket = FlatGradBucket.from_probe(model, lambda: step_dense(slots[0]))
+    # which parameters get gradients -> their gradients are packed into ONE flat buffer per step and that
+    # buffer is all-reduced (N > 1): a single collective per step
+    step_dense(slots[0])
+    gparams = [p for p in params if p.grad is not None]
+    n_grad = sum(p.numel() for p in gparams)
+    flat = torch.zeros(n_grad, device=dev)
+
+    class _Bucket:
+        nbytes = n_grad * 4
+
+        @staticmethod
+        def all_reduce():
+            if world > 1:
+                dist.all_reduce(flat)
+                flat.mul_(1.0 / world)
+    bucket = _Bucket()
     torch.cuda.synchronize()
     if args.profile_only:
         for i in range(args.warmup + args.steps):
-            bucket.zero(); step_dense(slots[i % NB])
+            step_dense(slots[i % NB])
         torch.cuda.synchronize()
         print(json.dumps({"profile_only": True, "steps": args.steps, "warmup": args.warmup}))
         return
@@ -229,7 +249,7 @@ def run_b200(args):
     with torch.cuda.stream(side):
         for _ in range(3):
             for s in slots[:2]:
-                bucket.zero(); step_dense(s); step_codes(s)
+                step_dense(s); step_codes(s)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     pool = torch.cuda.graph_pool_handle()
@@ -239,8 +259,9 @@ def run_b200(args):
             g = torch.cuda.CUDAGraph()
             c0 = _lib.launch_count()
             with torch.cuda.graph(g, pool=pool):
-                bucket.zero()
                 out = fn(s)
+                if world > 1:                                  # pack this graph's gradients into the flat buffer
+                    torch.cat([p.grad.reshape(-1) for p in gparams], out=flat)
             setattr(s, name, g)
             setattr(s, name + "_out", out)
             if name == "g_dense" and launches_per_step is None:
@@ -318,7 +339,7 @@ def run_b200(args):
         _lib.profile(True)
         nprof = 3
         for i in range(nprof):
-            bucket.zero(); step_dense(slots[i % NB])
+            step_dense(slots[i % NB])
         torch.cuda.synchronize()
         rep = _lib.profile_report()
         _lib.profile(False)
@@ -367,7 +388,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
-                       "gemm_engine": "tcgen05 3xTF32 (NN, NT) + FFMA (TN)" if _lib.lib().eagcn_get_gemm_mode() == 0 else "FFMA", "parallelism": f"dp{world}",
+                       "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
+                                       2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
                        "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
                        "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
                        "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
@@ -504,7 +526,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
-    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma"], help="projection GEMM engine")
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -81,6 +81,8 @@ _PROTOS = {
     "eagcn_get_gemm_mode": (c_int, []),
     "eagcn_gemm_nt": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                               c_void_p, c_int, c_void_p]),
+    "eagcn_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                              c_void_p, c_int64, c_int, c_void_p]),
     "eagcn_launch_count": (c_int64, []),
     "eagcn_profile": (c_int, [c_int]),
     "eagcn_profile_report": (c_int64, [ctypes.c_char_p, c_int64]),

@@ -9,7 +9,7 @@
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
 extern "C" int eagcn_set_gemm_mode(int mode) {
-  if (mode != 0 && mode != 1) return EAGCN_E_ARG;
+  if (mode < 0 || mode > 2) return EAGCN_E_ARG;
   eagcn::gemm_mode() = mode;
   return 0;
 }
@@ -28,6 +28,24 @@ extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t 
   if (engine == 1)
     return eagcn::gemm_nt((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)C, (int)ldc, (int)m_cap, (int)N,
                           (int)K, (const int*)m_dev, st);
+  return EAGCN_E_ARG;
+}
+
+extern "C" int eagcn_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t M, int64_t N,
+                             int64_t k_cap, const void* k_dev, void* ws, int64_t ws_bytes, int engine, void* stream) {
+  if (!A || !B || !C || !k_dev || !ws || M <= 0 || N <= 0 || k_cap <= 0 || lda < M || ldb < N) return EAGCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == 0) {
+    if (!eagcn::tc::tc_supported((const float*)A, (int)lda, (const float*)B, (int)ldb, (int)k_cap)) return EAGCN_E_UNSUPPORTED;
+    int ns = 0;
+    int rc = eagcn::tc::gemm_tc_tn((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)ws, ws_bytes / 4, (int)M,
+                                   (int)N, (int)k_cap, (const int*)k_dev, &ns, st);
+    if (rc) return rc;
+    return eagcn::splitk_reduce((const float*)ws, (float*)C, M * N, ns, st);
+  }
+  if (engine == 1)
+    return eagcn::gemm_tn((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)C, (int)M, (int)N, (int)k_cap,
+                          (const int*)k_dev, (float*)ws, ws_bytes / 4, st);
   return EAGCN_E_ARG;
 }
 

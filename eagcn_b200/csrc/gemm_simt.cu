@@ -133,17 +133,21 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
   return 0;
 }
 
-static int splitk_splits(int Kcap) {
-  int s = (Kcap + 511) / 512;
-  return s < 1 ? 1 : (s > 32 ? 32 : s);
-}
+namespace tc { int tn_splits(int M, int N, int Kcap); }
 
-long long gemm_tn_workspace_floats(int M, int N, int Kcap) { return (long long)splitk_splits(Kcap) * M * N; }
+long long gemm_tn_workspace_floats(int M, int N, int Kcap) { return (long long)tc::tn_splits(M, N, Kcap) * M * N; }
+
+int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t st) {
+  EAGCN_PROF("splitk_reduce_kernel", st);
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, C, n, ns);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
 
 int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, int N, int Kcap, const int* Kdev,
             float* ws, long long ws_floats, cudaStream_t st) {
   // A given as [K, M] row-major, B as [K, N] row-major; C [M, N] (ldc = N)
-  const int ns = splitk_splits(Kcap);
+  const int ns = tc::tn_splits(M, N, Kcap);
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
   int kchunk = (Kcap + ns - 1) / ns;
   kchunk = ((kchunk + GBK - 1) / GBK) * GBK;
@@ -152,11 +156,7 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
   EAGCN_PROF("gemm_simt_tn", st);
   gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, st>>>(g);
   EAGCN_LAUNCH_CHECK();
-  const long long n = (long long)M * N;
-  EAGCN_PROF("splitk_reduce_kernel", st);
-  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, C, n, ns);
-  EAGCN_LAUNCH_CHECK();
-  return 0;
+  return splitk_reduce(ws, C, (long long)M * N, ns, st);
 }
 
 }  // namespace eagcn

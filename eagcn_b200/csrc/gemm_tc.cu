@@ -1,6 +1,10 @@
 // tcgen05 (5th-gen tensor core) projection GEMM with fp32-faithful 3xTF32 error compensation.
 //
-//   C[T, N] = A[T, K] . B[N, K]^T        A, B: fp32, K contiguous ("K-major") ;  C: fp32
+//   mode NT :  C[T, N] = A[T, K] . B[N, K]^T     A, B fp32, K contiguous ("K-major" UMMA operands)
+//              forward Z = H . W_all (B = W_all^T) and backward dH = Q . W_all^T
+//   mode TN :  C[M, N] = A[T, M]^T . B[T, N]      A, B fp32, M/N contiguous ("MN-major" UMMA operands),
+//              split-K over the T rows (one partial tile per blockIdx.z, reduced in fixed order afterwards):
+//              backward dW_all = H^T . Q
 //
 // The dense contraction of the layer (reference layers.py:40) must match the fp32 reference to 1e-5,
 // which a single TF32 (10-bit mantissa) or BF16 pass cannot.  Each fp32 operand x is split exactly into
@@ -82,6 +86,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+// MN-major, SWIZZLE_128B: the tile is stored as [MN/32 boxes][BK rows of k][32 floats of MN = 128 B]; inside a box
+// 8 consecutive k rows form one 1024-byte swizzle atom.  leading byte offset = distance between 32-element MN
+// groups (one box = BK*128 B), stride byte offset = distance between groups of 8 k rows (1024 B).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t box_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((box_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -100,8 +117,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 struct TcArgs {
   float* C;
   int ldc, Mcap, N, K, BN;
-  const int* Mdev;
+  const int* Mdev;                 // NT: live rows of A / C = min(*Mdev, Mcap)
   uint32_t tmem_cols;
+  int mode;                        // 0 = NT (K-major), 1 = TN (MN-major, split-K)
+  const int* Kdev;                 // TN: live K rows = min(*Kdev, K)
+  int kchunk;                      // TN: K rows per blockIdx.z
+  long long split_stride;          // TN: elements between split partials
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -112,9 +133,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
-  const int M = min(*g.Mdev, g.Mcap);
+  const bool tn = g.mode == 1;
+  const int M = tn ? g.Mcap : min(*g.Mdev, g.Mcap);
+  int k_lo = 0, num_kb = (g.K + BK - 1) / BK;
+  if (tn) {
+    const int Kt = min(*g.Kdev, g.K);
+    k_lo = blockIdx.z * g.kchunk;
+    const int k_hi = min(Kt, k_lo + g.kchunk);
+    num_kb = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
+    g.C += (long long)blockIdx.z * g.split_stride;
+  }
 
-  if (m0 >= M) {                       // tile entirely beyond the live rows: keep slack rows defined (zeros)
+  if (m0 >= M || num_kb == 0) {        // nothing to accumulate: keep the tile defined (zeros)
     for (int i = threadIdx.x; i < BM * g.BN; i += kThreads) {
       const int r = m0 + i / g.BN, c = n0 + i % g.BN;
       if (r < g.Mcap && c < g.N) g.C[(size_t)r * g.ldc + c] = 0.0f;
@@ -151,7 +181,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
   const uint32_t tmem_c = tmem_d + (uint32_t)g.BN;                 // correction accumulator: columns [BN, 2*BN)
-  const int num_kb = (g.K + BK - 1) / BK;
+  // TN: 32-wide MN boxes actually inside the tensors (the others are zero-filled by the transform warps)
+  const uint32_t box_bytes = BK * 128;
+  const int nboxA = tn ? min(BM / 32, (g.Mcap - m0 + 31) / 32) : 0;
+  const int nboxB = tn ? min(g.BN / 32, (g.N - n0 + 31) / 32) : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -159,26 +192,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
         if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
-        mbar_expect_tx(&bar_full[s], bytesA + bytesB);
-        tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
-        tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * BK, n0);
+        if (!tn) {
+          mbar_expect_tx(&bar_full[s], bytesA + bytesB);
+          tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
+          tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * BK, n0);
+        } else {
+          const int krow = k_lo + kb * BK;
+          mbar_expect_tx(&bar_full[s], (uint32_t)(nboxA + nboxB) * box_bytes);
+          for (int i = 0; i < nboxA; ++i) tma_load_2d(&mapA, &bar_full[s], sA_hi(s) + i * box_bytes, m0 + 32 * i, krow);
+          for (int i = 0; i < nboxB; ++i) tma_load_2d(&mapB, &bar_full[s], sB_hi(s) + i * box_bytes, n0 + 32 * i, krow);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (bit4), a=b=TF32 (2<<7, 2<<10), K-major A/B,
     // N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // TN: a_major (bit 15) = b_major (bit 16) = 1 (MN-major)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES, it = kb / STAGES;
       mbar_wait(&bar_ready[s], it & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t dAh = make_desc(smem_u32(sA_hi(s))), dAl = make_desc(smem_u32(sA_lo(s)));
-        const uint64_t dBh = make_desc(smem_u32(sB_hi(s))), dBl = make_desc(smem_u32(sB_lo(s)));
+        const uint64_t dAh = tn ? make_desc_mn(smem_u32(sA_hi(s)), box_bytes) : make_desc(smem_u32(sA_hi(s)));
+        const uint64_t dAl = tn ? make_desc_mn(smem_u32(sA_lo(s)), box_bytes) : make_desc(smem_u32(sA_lo(s)));
+        const uint64_t dBh = tn ? make_desc_mn(smem_u32(sB_hi(s)), box_bytes) : make_desc(smem_u32(sB_hi(s)));
+        const uint64_t dBl = tn ? make_desc_mn(smem_u32(sB_lo(s)), box_bytes) : make_desc(smem_u32(sB_lo(s)));
 #pragma unroll
         for (int k = 0; k < BK / UK; ++k) {
-          const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);     // +32 bytes per UMMA_K inside the 128B swizzle row
+          // NT: +32 bytes per UMMA_K inside the 128B swizzle row;  TN: +1024 bytes (next group of 8 k rows)
+          const uint64_t adv = tn ? (uint64_t)((k * 1024) >> 4) : (uint64_t)((k * UK * 4) >> 4);
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
           umma_tf32(tmem_c, dAl + adv, dBh + adv, idesc, acc);    // correction terms -> second accumulator
           umma_tf32(tmem_c, dAh + adv, dBl + adv, idesc, 1u);
@@ -195,6 +240,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES, it = kb / STAGES;
       mbar_wait(&bar_full[s], it & 1);
+      if (tn) {                                                    // boxes outside the tensors were not loaded
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4* ah = reinterpret_cast<uint4*>(sA_hi(s));
+        for (int i = nboxA * (int)(box_bytes / 16) + xt; i < (int)(bytesA / 16); i += kXformThreads) ah[i] = z;
+        uint4* bh = reinterpret_cast<uint4*>(sB_hi(s));
+        for (int i = nboxB * (int)(box_bytes / 16) + xt; i < (int)(bytesB / 16); i += kXformThreads) bh[i] = z;
+      }
       {
         uint4* hi = reinterpret_cast<uint4*>(sA_hi(s));
         uint4* lo = reinterpret_cast<uint4*>(sA_lo(s));
@@ -306,6 +358,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2D fp32 row-major [rows, cols] (cols contiguous), box = [box_rows, 32 floats], 128B swizzle, OOB -> 0
+// (NT: rows = M or N index, cols = K;  TN: rows = K index, cols = M or N index -- same encoding)
 static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
@@ -340,7 +393,7 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   const int BN = pick_bn(N);
   CUtensorMap mA, mB;
   if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
-  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0};
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, nullptr, 0, 0};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // main + correction accumulators
   const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_set = false;
@@ -353,6 +406,50 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   EAGCN_PROF(tag, st);
   gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, g);
   EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+// split-K factor shared by both engines for dW = H^T Q  (M = fin, N = fo_tot, K rows up to Kcap)
+int tn_splits(int M, int N, int Kcap) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int s = (296 + tiles - 1) / tiles;
+  const int kmax = (Kcap + 127) / 128;
+  if (s > kmax) s = kmax;
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : s;
+}
+
+static int pick_bn_tn(int N) {          // multiple of 32 (whole MN boxes), <= 256
+  int best = 128, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    const int tiles = (N + bn - 1) / bn;
+    const int waste = tiles * bn - N;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
+  }
+  return best;
+}
+
+// C[M, N] = A[Kcap(T live), M]^T . B[Kcap, N]; rows >= T of A and B must be zero (they are: rows_gather,
+// bn_apply and agg_bwd zero-fill the slack rows).  ws: split-K partials, reduced by the caller.
+int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long long ws_floats, int M, int N, int Kcap,
+               const int* Kdev, int* nsplit_out, cudaStream_t st) {
+  const int BN = pick_bn_tn(N);
+  const int ns = tn_splits(M, N, Kcap);
+  if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
+  CUtensorMap mA, mB;
+  if (!make_map(&mA, A, Kcap, M, lda, BK) || !make_map(&mB, B, Kcap, N, ldb, BK)) return EAGCN_E_UNSUPPORTED;
+  int kchunk = (Kcap + ns - 1) / ns;
+  kchunk = ((kchunk + BK - 1) / BK) * BK;
+  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, Kdev, kchunk, (long long)M * N};
+  g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+  const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ns);
+  EAGCN_PROF("gemm_tc_tn", st);
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, g);
+  EAGCN_LAUNCH_CHECK();
+  *nsplit_out = ns;
   return 0;
 }
 

@@ -22,6 +22,7 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
 int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, int N, int Kcap, const int* Kdev,
             float* ws, long long ws_floats, cudaStream_t st);
 long long gemm_tn_workspace_floats(int M, int N, int Kcap);
+int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t st);
 bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l);
 __global__ void stat_reduce_kernel(PlanDev p, const float* __restrict__ partial, double* __restrict__ sums, int C);
 
@@ -132,37 +133,50 @@ __device__ __forceinline__ void grad_through_act4(const float4 dx, const float4 
   }
 }
 
-// grid (stat tiles, ceil(C/4/128)); a thread owns 4 channels for the 64 rows of its tile (fixed order)
-__global__ void __launch_bounds__(128) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
+// grid (stat tiles, ceil(C/4/32)); block (32 channel-groups x 8 row-groups): a thread sums 8 of the tile's 64 rows
+// for its 4 channels, the 8 row-groups are then combined through shared memory in fixed order
+__global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
                                                                  const float* __restrict__ Y, const float* __restrict__ ball,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  float* __restrict__ partial, int C, int training, float p_drop,
                                                                  const unsigned long long* rng, unsigned long long stream) {
+  __shared__ float4 s_red[2][8][32];
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
   if (tile * kStatRows >= T) return;
-  const int c = (blockIdx.y * 128 + threadIdx.x) * 4;
-  if (c >= C) return;
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
-  const float4 ga = *reinterpret_cast<const float4*>(ball + C + c), be = *reinterpret_cast<const float4*>(ball + 2 * C + c);
-  const bool drop = training && p_drop > 0.0f;
-  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
-  unsigned long long seed = 0, off = 0;
-  if (drop) { seed = rng[0]; off = rng[1]; }
-  const Philox ph(seed);
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + cx) * 4;
+  const bool act = c < C;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  const int r1 = min(T, (tile + 1) * kStatRows);
+  if (act) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(ball + C + c), be = *reinterpret_cast<const float4*>(ball + 2 * C + c);
+    const bool drop = training && p_drop > 0.0f;
+    const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+    unsigned long long seed = 0, off = 0;
+    if (drop) { seed = rng[0]; off = rng[1]; }
+    const Philox ph(seed);
+    const int r0 = tile * kStatRows + ry * 8;
+    const int r1 = min(T, r0 + 8);
 #pragma unroll 4
-  for (int t = tile * kStatRows; t < r1; ++t) {
-    const size_t idx = (size_t)t * C + c;
-    const float4 dx = __ldg(reinterpret_cast<const float4*>(dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
-    float g[4], xh[4];
-    grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, off, stream, (unsigned long long)idx, p_drop, g, xh);
+    for (int t = r0; t < r1; ++t) {
+      const size_t idx = (size_t)t * C + c;
+      const float4 dx = __ldg(reinterpret_cast<const float4*>(dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
+      float g[4], xh[4];
+      grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, off, stream, (unsigned long long)idx, p_drop, g, xh);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { s1[u] += g[u]; s2[u] = fmaf(g[u], xh[u], s2[u]); }
+      for (int u = 0; u < 4; ++u) { s1[u] += g[u]; s2[u] = fmaf(g[u], xh[u], s2[u]); }
+    }
   }
-  *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + 0) * C + c) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-  *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + 1) * C + c) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  s_red[0][ry][cx] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  s_red[1][ry][cx] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  __syncthreads();
+  if (ry < 2 && act) {
+    float4 a = s_red[ry][0][cx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 b = s_red[ry][w][cx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + ry) * C + c) = a;
+  }
 }
 
 // grid (ceil(C/4/128), ceil(t_cap/16))
@@ -229,6 +243,14 @@ __global__ void __launch_bounds__(256) agg_bwd_kernel(PlanDev p, LayerDev L, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y, tile = blockIdx.x;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  {   // slack rows [T, t_cap) of Q stay defined (zeros): the split-K dW GEMM reads whole 32-row blocks
+    const int fo_ = L.fo[v], off_ = L.off[v];
+    for (int r = 0; r < 8; ++r) {
+      const int t = tile * kStatRows + warp * 8 + r;
+      if (t >= T && t < p.t_cap)
+        for (int c = lane; c < fo_; c += 32) Q[(size_t)t * L.fo_tot + off_ + c] = 0.0f;
+    }
+  }
   if (tile * kStatRows >= T) return;
   for (int i = threadIdx.x; i < 8 * EAGCN_SIG_STRIDE; i += 256) (&s_hist[0][0])[i] = 0.0f;
   __syncthreads();
@@ -373,9 +395,9 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   PlanDev p = to_dev(plan);
   const int C = (int)layer->fo_tot;
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y)) {
-    dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 127) / 128);
+    dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 31) / 32);
     EAGCN_PROF("bn_bwd_partial_kernel", st);
-    bn_bwd_partial_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+    bn_bwd_partial_vec_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
                                                     C, w->training ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,
@@ -447,13 +469,20 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
                                                                            L.V);
   EAGCN_LAUNCH_CHECK();
   int rc;
-  if (gemm_mode() == 0 && tc::tc_supported((const float*)w->Q, C, (const float*)w->wall, C, C))
+  if (gemm_mode() != 1 && tc::tc_supported((const float*)w->Q, C, (const float*)w->wall, C, C))
     rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                         p.counts + EAGCN_CNT_T, st, "gemm_tc_nt");
   else
     rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                  p.counts + EAGCN_CNT_T, st);
   if (rc) return rc;
+  if (gemm_mode() == 0 && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->Q, C, p.t_cap)) {
+    int ns = 0;
+    rc = tc::gemm_tc_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->gemm_ws,
+                        w->gemm_ws_bytes / (long long)sizeof(float), L.fin, C, p.t_cap, p.counts + EAGCN_CNT_T, &ns, st);
+    if (rc) return rc;
+    return splitk_reduce((const float*)w->gemm_ws, (float*)w->dwall, (long long)L.fin * C, ns, st);
+  }
   rc = gemm_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->dwall, L.fin, C, p.t_cap,
                p.counts + EAGCN_CNT_T, (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st);
   return rc;

@@ -329,7 +329,7 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->wallT, (float*)w->ball, (float*)w->sig);
   EAGCN_LAUNCH_CHECK();
   int rc;
-  if (gemm_mode() == 0 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
+  if (gemm_mode() != 1 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
     rc = tc::gemm_tc_nt((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, (float*)w->Z, C, p.t_cap, C, L.fin,
                         p.counts + EAGCN_CNT_T, st, "gemm_tc_nn");
   else

@@ -312,6 +312,18 @@ def gemm_nt(A, B, m_dev, engine=0):
     return C
 
 
+def gemm_tn(A, B, k_dev, engine=0):
+    """C = A.T @ B over the first k_dev[0] rows (rows beyond must be zero) on the projection GEMM engine."""
+    A, B = A.contiguous(), B.contiguous()
+    M, N, K = A.shape[1], B.shape[1], A.shape[0]
+    C = torch.empty(M, N, dtype=_F32, device=A.device)
+    nbytes = int(lib().eagcn_gemm_workspace_bytes(M, N, K))
+    ws = torch.empty(max(nbytes // 4, 1), dtype=_F32, device=A.device)
+    check(lib().eagcn_gemm_tn(ptr(A), M, ptr(B), N, ptr(C), M, N, K, ptr(k_dev), ptr(ws), nbytes, engine, _stream()),
+          "eagcn_gemm_tn")
+    return C
+
+
 def set_gemm_engine(name: str):
     """'tcgen05' (default: tensor cores with 3xTF32 compensation where the layout allows) or 'ffma'."""
-    check(lib().eagcn_set_gemm_mode({"tcgen05": 0, "ffma": 1}[name]), "eagcn_set_gemm_mode")
+    check(lib().eagcn_set_gemm_mode({"tcgen05": 0, "ffma": 1, "tcgen05-nt": 2}[name]), "eagcn_set_gemm_mode")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 5
+#define EAGCN_ABI_VERSION 6
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -178,7 +178,8 @@ int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t 
 
 /* --- projection GEMM engine ------------------------------------------------------------------ */
 /* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned
- * rows), FFMA kernel otherwise; 1: always the FFMA kernel.  Process-wide setting.               */
+ * rows), FFMA kernel otherwise; 1: always the FFMA kernel; 2: tcgen05 for the K-major products
+ * (Z = H W, dH = Q W^T), FFMA for the MN-major weight gradient (dW = H^T Q).  Process-wide.    */
 int eagcn_set_gemm_mode(int mode);
 int eagcn_get_gemm_mode(void);
 /* stand-alone projection product  C[m_cap, N] = A[m_cap, K] . B[N, K]^T  (fp32, rows contiguous; lda/ldb/ldc
@@ -187,6 +188,14 @@ int eagcn_get_gemm_mode(void);
  * not allow it), 1 = FFMA.  This is reference layers.py:40 (torch.mm(support, W)) in isolation.    */
 int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,
                   int64_t N, int64_t K, const void* m_dev, int engine, void* stream);
+
+/* stand-alone weight-gradient product  C[M, N] = A[k_cap, M]^T . B[k_cap, N]  (fp32 row-major, lda >= M,
+ * ldb >= N, C dense [M, N]).  Only the first min(*k_dev, k_cap) rows take part; rows beyond that MUST be zero
+ * in both operands (the layer kernels keep their slack rows zero).  ws: eagcn_gemm_workspace_bytes(M, N, k_cap)
+ * bytes of split-K workspace.  engine as in eagcn_gemm_nt.  This is the autograd product d(weight) of
+ * reference layers.py:40.                                                                          */
+int eagcn_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t M, int64_t N, int64_t k_cap,
+                  const void* k_dev, void* ws, int64_t ws_bytes, int engine, void* stream);
 
 /* --- diagnostics (not on the data path; not thread-safe) ------------------------------------ */
 /* kernels launched by this library since load (bench.py: gpu_launches; under CUDA-graph replay the

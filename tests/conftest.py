@@ -20,3 +20,15 @@ def pytest_collection_modifyitems(config, items):
         for it in items:
             if "reference" in it.keywords:
                 it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _gemm_engine_from_env():
+    """EAGCN_GEMM=tcgen05|ffma|tcgen05-nt selects the projection GEMM engine for a GPU test session."""
+    eng = os.environ.get("EAGCN_GEMM")
+    if eng:
+        import torch
+        if torch.cuda.is_available():
+            from eagcn_b200 import functional as EF
+            EF.set_gemm_engine(eng)
+    yield

@@ -30,7 +30,7 @@ def test_gemm_nt_vs_float64(engine, Mcap, T, N, K):
     print(f"engine {engine} M={T} N={N} K={K}: err {err:.2e}")
     # fp32-class accuracy: FFMA ~1e-7 of max; 3xTF32 tensor-core a few 1e-6 (truncating fp32 accumulation in
     # the tensor core, K/8 steps) -- inside the 1e-5 layer-level parity bar
-    assert err <= (6e-6 if engine == 0 else 1e-6), (engine, err)
+    assert err <= (6e-6 if engine == 0 else 2e-6), (engine, err)
     assert float(C[T:].abs().max()) == 0.0 if T < Mcap else True
 
 
@@ -46,3 +46,26 @@ def test_gemm_unaligned_layout_is_rejected_not_wrong():
     C = EF.gemm_nt(A, B, m_dev, engine=1)
     ref = A.double() @ B.double().t()
     assert float((C.double() - ref).abs().max()) / float(ref.abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("Kcap,T,M,N", [
+    (128, 128, 32, 32), (256, 200, 24, 400), (512, 511, 400, 700), (4864, 4853, 400, 700), (1024, 1000, 700, 1400),
+    (256, 33, 128, 64), (384, 300, 100, 36),
+])
+def test_gemm_tn_vs_float64(engine, Kcap, T, M, N):
+    """dW = H^T Q: MN-major tcgen05 operands + split-K (engine 0), FFMA (engine 1)."""
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    g = torch.Generator(device="cpu").manual_seed(Kcap + M + N)
+    A = torch.randn(Kcap, M, generator=g)
+    B = torch.randn(Kcap, N, generator=g)
+    A[T:] = 0; B[T:] = 0                                   # slack rows are zero by contract
+    A, B = A.to(dev), B.to(dev)
+    k_dev = torch.tensor([T], dtype=torch.int32, device=dev)
+    C = EF.gemm_tn(A, B, k_dev, engine)
+    torch.cuda.synchronize()
+    ref = A.double().t() @ B.double()
+    err = float((C.double() - ref).abs().max()) / float(ref.abs().max())
+    print(f"TN engine {engine} K={T} M={M} N={N}: err {err:.2e}")
+    assert err <= (6e-6 if engine == 0 else 2e-6), (engine, err)

@@ -3,12 +3,12 @@
 # Every python process runs under its own hard timeout (a hung kernel must not hang the box).
 mkdir -p gpurun_out
 TAG=${1:-run}
-timeout -s KILL 200 python -m pytest tests/test_gpu_gemm.py -q -x 2>&1 | tail -25 | tee gpurun_out/${TAG}_gemm.log
-if grep -q "failed\|Killed\|error" gpurun_out/${TAG}_gemm.log; then ENG=ffma; else ENG=tcgen05; fi
+timeout -s KILL 200 python -m pytest tests/test_gpu_gemm.py -q -s -k "gemm_nt or unaligned" 2>&1 | grep -v "^$" | tail -40 | tee gpurun_out/${TAG}_gemm.log
+timeout -s KILL 200 python -m pytest tests/test_gpu_gemm.py -q -s -k "gemm_tn" 2>&1 | grep -v "^$" | tail -40 | tee gpurun_out/${TAG}_gemm_tn.log
+if grep -q "failed\|Killed\|rror" gpurun_out/${TAG}_gemm.log; then ENG=ffma;
+elif grep -q "failed\|Killed\|rror" gpurun_out/${TAG}_gemm_tn.log; then ENG=tcgen05-nt; else ENG=tcgen05; fi
 echo "engine for the rest of this visit: $ENG" | tee -a gpurun_out/${TAG}_gemm.log
-if [ "$ENG" = "tcgen05" ]; then
-  timeout -s KILL 400 python -m pytest tests -m gpu -q 2>&1 | tail -30 | tee gpurun_out/${TAG}_tests.log
-fi
+EAGCN_GEMM=$ENG timeout -s KILL 500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_gemm.py 2>&1 | tail -30 | tee gpurun_out/${TAG}_tests.log
 timeout -s KILL 500 python bench.py --steps 100 --warmup 10 --gemm $ENG > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -c 1500 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 # launch list of 2 steady-state eager steps (3 warm-up steps skipped by kernel count is fragile -> profile all 5, aggregate offline)

@@ -50,7 +50,11 @@ inline void prof_end() {
 namespace eagcn {
 
 constexpr int kWarp = 32;
-constexpr int kStatRows = 64;       // rows per statistics tile (agg / bn kernels)
+constexpr int kStatRows = 32;       // rows per statistics tile (agg / bn kernels)
+constexpr int kAggWarps = 8;        // warps per CTA of the aggregation kernels (one row at a time each)
+constexpr int kAggRows = kStatRows / kAggWarps;   // rows per warp
+constexpr int kAggThreads = kAggWarps * 32;
+constexpr int kEltRows = 4;         // rows per thread of the float4 element-wise BatchNorm kernels
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -34,9 +34,9 @@ namespace tc {
 constexpr int BM = 128;            // UMMA M
 constexpr int BK = 32;             // fp32 elements per k-block = 128 bytes = one swizzle atom row
 constexpr int UK = 8;              // UMMA K for kind::tf32 (32 bytes)
-constexpr int STAGES = 2;
-constexpr int kThreads = 192;      // warp0 TMA, warp1 MMA, warps 2..5 transform + epilogue
-constexpr int kXformThreads = 128;
+constexpr int MAX_STAGES = 4;      // smem ring depth is chosen on the host (as many stages as fit in 200 KB)
+constexpr int kThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 transform + epilogue
+constexpr int kXformThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,16 +86,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-// MN-major, SWIZZLE_128B: the tile is stored as [MN/32 boxes][BK rows of k][32 floats of MN = 128 B]; inside a box
-// 8 consecutive k rows form one 1024-byte swizzle atom.  leading byte offset = distance between 32-element MN
-// groups (one box = BK*128 B), stride byte offset = distance between groups of 8 k rows (1024 B).
+// MN-major 32-bit operands: the only shared-memory layout UMMA accepts is SWIZZLE_128B with 32-byte atoms
+// (cute UMMA::Layout_MN_SW128_32B_Atom, LayoutType::SWIZZLE_128B_BASE32B = 1; TMA: SWIZZLE_128B_ATOM_32B).
+// The tile is stored as [MN/32 boxes][BK rows of k][32 floats of MN = 128 B]; 4 consecutive k rows form one
+// 512-byte swizzle atom.  leading byte offset = distance between 32-element MN groups (one box = BK*128 B),
+// stride byte offset = distance between groups of 4 k rows (512 B).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t box_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((box_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 
@@ -120,15 +122,18 @@ struct TcArgs {
   const int* Mdev;                 // NT: live rows of A / C = min(*Mdev, Mcap)
   uint32_t tmem_cols;
   int mode;                        // 0 = NT (K-major), 1 = TN (MN-major, split-K)
+  int stages;                      // shared-memory pipeline depth (2..MAX_STAGES)
+  int b_split;                     // NT: B arrives already split (mapB = hi, mapB2 = lo): no transform of B
   const int* Kdev;                 // TN: live K rows = min(*Kdev, K)
   int kchunk;                      // TN: K rows per blockIdx.z
   long long split_stride;          // TN: elements between split partials
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapB2, TcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_ready[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto sB_lo = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA + bytesB; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < g.stages; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_ready[s], kXformThreads);
       mbar_init(&bar_empty[s], 1);
@@ -190,12 +195,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
+        const int s = kb % g.stages, it = kb / g.stages;
         if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
         if (!tn) {
-          mbar_expect_tx(&bar_full[s], bytesA + bytesB);
+          mbar_expect_tx(&bar_full[s], bytesA + (g.b_split ? 2 : 1) * bytesB);
           tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
           tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * BK, n0);
+          if (g.b_split) tma_load_2d(&mapB2, &bar_full[s], sB_lo(s), kb * BK, n0);
         } else {
           const int krow = k_lo + kb * BK;
           mbar_expect_tx(&bar_full[s], (uint32_t)(nboxA + nboxB) * box_bytes);
@@ -212,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
+      const int s = kb % g.stages, it = kb / g.stages;
       mbar_wait(&bar_ready[s], it & 1);
       tc_fence_after();
       if (lane == 0) {
@@ -236,9 +242,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===================== transform (hi/lo split), then epilogue =====================
-    const int xt = threadIdx.x - 64;                              // 0..127
+    const int xt = threadIdx.x - 64;                              // 0..255
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
+      const int s = kb % g.stages, it = kb / g.stages;
       mbar_wait(&bar_full[s], it & 1);
       if (tn) {                                                    // boxes outside the tensors were not loaded
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -260,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           hi[i] = h; lo[i] = l;
         }
       }
-      {
+      if (!g.b_split) {
         uint4* hi = reinterpret_cast<uint4*>(sB_hi(s));
         uint4* lo = reinterpret_cast<uint4*>(sB_lo(s));
         for (int i = xt; i < (int)(bytesB / 16); i += kXformThreads) {
@@ -285,7 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool in_cap = row < g.Mcap;
     float* crow = g.C + (size_t)row * g.ldc;
     const bool vec = ((g.ldc & 3) == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    for (int c0 = 0; c0 < g.BN; c0 += 32) {
+    // 8 epilogue warps: warps w and w+4 share a TMEM lane quadrant and take alternate 32-column chunks
+    const int half = (warp - 2) >> 2;
+    for (int c0 = half * 32; c0 < g.BN; c0 += 64) {
       uint32_t r[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
       asm volatile(
@@ -359,7 +367,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2D fp32 row-major [rows, cols] (cols contiguous), box = [box_rows, 32 floats], 128B swizzle, OOB -> 0
 // (NT: rows = M or N index, cols = K;  TN: rows = K index, cols = M or N index -- same encoding)
-static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
+static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows,
+                     bool atom32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -367,17 +376,31 @@ static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// N-tile width: multiple of 16, <= 256, smallest padding of N, ties -> fewer tiles
-static int pick_bn(int N) {
-  int best = 128, best_waste = 1 << 30;
-  for (int bn = 256; bn >= 64; bn -= 16) {
-    const int tiles = (N + bn - 1) / bn;
-    const int waste = tiles * bn - N;
-    if (waste < best_waste) { best_waste = waste; best = bn; }
+static int pick_stages(int BN, int num_kb) {
+  const int stage_bytes = 2 * BM * BK * 4 + 2 * BN * BK * 4;
+  int st = (200 * 1024 - 1024) / stage_bytes;
+  if (st > MAX_STAGES) st = MAX_STAGES;
+  if (st > num_kb) st = num_kb;
+  return st < 2 ? 2 : st;
+}
+
+// N-tile width (multiple of `step`, 64..256).  One CTA per SM and a k-block cost that grows with the operand
+// bytes staged per k-block (~ 128 + BN rows): minimise  ceil(tiles / 148) * (128 + BN), i.e. avoid a nearly
+// empty second wave before worrying about padded columns.
+static int pick_bn(int N, int mtiles, int step = 16) {
+  int best = 128;
+  long long best_cost = 1LL << 60;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    const int ntiles = (N + bn - 1) / bn;
+    const long long tiles = (long long)ntiles * mtiles;
+    const long long rounds = (tiles + 147) / 148;
+    const long long cost = rounds * (128 + bn) * 1000 + (long long)(ntiles * bn - N);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -388,14 +411,17 @@ bool tc_supported(const float* A, int lda, const float* B, int ldb, int K) {
 }
 
 // C[Mcap(T live), N] = A[Mcap, K] . B[N, K]^T   (both K-contiguous)
+// B_lo != nullptr: B is pre-split (B = hi part, B_lo = lo part, same leading dimension)
 int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
-               const int* Mdev, cudaStream_t st, const char* tag) {
-  const int BN = pick_bn(N);
-  CUtensorMap mA, mB;
+               const int* Mdev, cudaStream_t st, const char* tag, const float* B_lo = nullptr) {
+  const int BN = pick_bn(N, (Mcap + BM - 1) / BM);
+  CUtensorMap mA, mB, mB2;
   if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
-  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, nullptr, 0, 0};
+  if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, 0};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // main + correction accumulators
-  const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  g.stages = pick_stages(BN, (K + BK - 1) / BK);
+  const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -404,7 +430,7 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   }
   dim3 grid((N + BN - 1) / BN, (Mcap + BM - 1) / BM, 1);
   EAGCN_PROF(tag, st);
-  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, g);
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, mB2, g);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -419,7 +445,7 @@ int tn_splits(int M, int N, int Kcap) {
   return s < 1 ? 1 : s;
 }
 
-static int pick_bn_tn(int N) {          // multiple of 32 (whole MN boxes), <= 256
+static int pick_bn_tn(int N) {          // multiple of 32 (whole MN boxes), <= 256: least padding, ties -> wider
   int best = 128, best_waste = 1 << 30;
   for (int bn = 256; bn >= 32; bn -= 32) {
     const int tiles = (N + bn - 1) / bn;
@@ -437,17 +463,18 @@ int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long
   const int ns = tn_splits(M, N, Kcap);
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
   CUtensorMap mA, mB;
-  if (!make_map(&mA, A, Kcap, M, lda, BK) || !make_map(&mB, B, Kcap, N, ldb, BK)) return EAGCN_E_UNSUPPORTED;
+  if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;
   int kchunk = (Kcap + ns - 1) / ns;
   kchunk = ((kchunk + BK - 1) / BK) * BK;
-  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, Kdev, kchunk, (long long)M * N};
+  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, (long long)M * N};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
-  const size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  g.stages = pick_stages(BN, kchunk / BK);
+  const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ns);
   EAGCN_PROF("gemm_tc_tn", st);
-  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, g);
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, mB, g);
   EAGCN_LAUNCH_CHECK();
   *nsplit_out = ns;
   return 0;

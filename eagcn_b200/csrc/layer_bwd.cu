@@ -133,7 +133,7 @@ __device__ __forceinline__ void grad_through_act4(const float4 dx, const float4 
   }
 }
 
-// grid (stat tiles, ceil(C/4/32)); block (32 channel-groups x 8 row-groups): a thread sums 8 of the tile's 64 rows
+// grid (stat tiles, ceil(C/4/32)); block (32 channel-groups x 8 row-groups): a thread sums 1/8 of the tile's rows
 // for its 4 channels, the 8 row-groups are then combined through shared memory in fixed order
 __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
                                                                  const float* __restrict__ Y, const float* __restrict__ ball,
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
     unsigned long long seed = 0, off = 0;
     if (drop) { seed = rng[0]; off = rng[1]; }
     const Philox ph(seed);
-    const int r0 = tile * kStatRows + ry * 8;
-    const int r1 = min(T, r0 + 8);
+    const int r0 = tile * kStatRows + ry * (kStatRows / 8);
+    const int r1 = min(T, r0 + kStatRows / 8);
 #pragma unroll 4
     for (int t = r0; t < r1; ++t) {
       const size_t idx = (size_t)t * C + c;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
   }
 }
 
-// grid (ceil(C/4/128), ceil(t_cap/16))
+// grid (ceil(C/4/128), ceil(t_cap/kEltRows))
 __global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const float* __restrict__ dX,
                                                                const float* __restrict__ Y, const float* __restrict__ ball,
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const 
     for (int u = 0; u < 4; ++u) { m1[u] = (float)(bsums[c + u] / M); m2[u] = (float)(bsums[C + c + u] / M); }
   }
   const float gi[4] = {ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w};
-  const int r0 = blockIdx.y * 16, r1 = min(p.t_cap, r0 + 16);
+  const int r0 = blockIdx.y * kEltRows, r1 = min(p.t_cap, r0 + kEltRows);
 #pragma unroll 4
   for (int t = r0; t < r1; ++t) {
     const size_t idx = (size_t)t * C + c;
@@ -232,27 +232,27 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   dvec[2 * C + c] = (float)s1;
 }
 
-// grid (row tiles, V); 8 warps x 8 rows.  Fo_v handled in super-chunks of 512 channels (4 x 128).
+// grid (row tiles, V); kAggWarps warps x kAggRows rows.  Fo_v handled in super-chunks of 512 channels (4 x 128).
 template <int VEC>
-__global__ void __launch_bounds__(256) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+__global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                       const float* __restrict__ Y, const float* __restrict__ dY,
                                                       const float* __restrict__ ball, const float* __restrict__ sig,
                                                       const float* __restrict__ invR, float* __restrict__ Q,
                                                       float* __restrict__ dpart) {
-  __shared__ float s_hist[8][EAGCN_SIG_STRIDE];
+  __shared__ float s_hist[kAggWarps][EAGCN_SIG_STRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y, tile = blockIdx.x;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   {   // slack rows [T, t_cap) of Q stay defined (zeros): the split-K dW GEMM reads whole 32-row blocks
     const int fo_ = L.fo[v], off_ = L.off[v];
-    for (int r = 0; r < 8; ++r) {
-      const int t = tile * kStatRows + warp * 8 + r;
+    for (int r = 0; r < kAggRows; ++r) {
+      const int t = tile * kStatRows + warp * kAggRows + r;
       if (t >= T && t < p.t_cap)
         for (int c = lane; c < fo_; c += 32) Q[(size_t)t * L.fo_tot + off_ + c] = 0.0f;
     }
   }
   if (tile * kStatRows >= T) return;
-  for (int i = threadIdx.x; i < 8 * EAGCN_SIG_STRIDE; i += 256) (&s_hist[0][0])[i] = 0.0f;
+  for (int i = threadIdx.x; i < kAggWarps * EAGCN_SIG_STRIDE; i += kAggThreads) (&s_hist[0][0])[i] = 0.0f;
   __syncthreads();
   const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot;
   const float* sg = sig + v * EAGCN_SIG_STRIDE;
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(256) agg_bwd_kernel(PlanDev p, LayerDev L, con
   const uint8_t* rcode = p.rcode + (size_t)v * p.e_cap;
   const float* iR = invR + (size_t)v * p.t_cap;
   const int nsc = (fo + 511) / 512;
-  for (int r = 0; r < 8; ++r) {
-    const int t = tile * kStatRows + warp * 8 + r;
+  for (int r = 0; r < kAggRows; ++r) {
+    const int t = tile * kStatRows + warp * kAggRows + r;
     if (t >= T) break;
     const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
     const float invR_t = iR[t];
@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(256) agg_bwd_kernel(PlanDev p, LayerDev L, con
   }
   __syncthreads();
   float* out = dpart + ((size_t)tile * L.V + v) * EAGCN_SIG_STRIDE;
-  for (int i = threadIdx.x; i < EAGCN_SIG_STRIDE; i += 256) {
+  for (int i = threadIdx.x; i < EAGCN_SIG_STRIDE; i += kAggThreads) {
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) a += s_hist[w][i];
+    for (int w = 0; w < kAggWarps; ++w) a += s_hist[w][i];
     out[i] = a;
   }
 }
@@ -431,7 +431,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const long long total = (long long)p.t_cap * C;
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY)) {
-    dim3 grid((C / 4 + 127) / 128, (p.t_cap + 15) / 16);
+    dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_bwd_apply_kernel", st);
     bn_bwd_apply_vec_kernel<<<grid, 128, 0, st>>>(
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
@@ -454,12 +454,12 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   if (vec4_ok_b(layer)) {
     EAGCN_PROF("agg_bwd_kernel", st);
-    agg_bwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+    agg_bwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
   } else {
     EAGCN_PROF("agg_bwd_kernel", st);
-    agg_bwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+    agg_bwd_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
   }
@@ -469,9 +469,9 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
                                                                            L.V);
   EAGCN_LAUNCH_CHECK();
   int rc;
-  if (gemm_mode() != 1 && tc::tc_supported((const float*)w->Q, C, (const float*)w->wall, C, C))
-    rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
-                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nt");
+  if (gemm_mode() != 1 && w->wsplit && tc::tc_supported((const float*)w->Q, C, (const float*)w->wsplit, C, C))
+    rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wsplit, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
+                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nt", (const float*)w->wsplit + (size_t)L.fin * C);
   else
     rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                  p.counts + EAGCN_CNT_T, st);

@@ -26,8 +26,11 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
 inline int& gemm_mode() { static int m = 0; return m; }
 
 // ---------------------------------------------------------------------------------------------
+// wallT: [2][fo_tot][fin] and wsplit: [2][fin][fo_tot] hold the exact TF32 split of every weight
+// (hi = 13 low mantissa bits cleared, lo = w - hi) so the tensor-core GEMMs need not split B in shared memory
 __global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __restrict__ wall, float* __restrict__ wallT,
-                                                          float* __restrict__ ball, float* __restrict__ sig) {
+                                                          float* __restrict__ wsplit, float* __restrict__ ball,
+                                                          float* __restrict__ sig) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long nW = (long long)L.fin * L.fo_tot;
   if (idx < nW) {
@@ -36,7 +39,9 @@ __global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __r
     while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
     const float wv = __ldg(L.W[v] + (long long)k * L.fo[v] + (c - L.off[v]));
     wall[idx] = wv;
-    if (wallT) wallT[(long long)c * L.fin + k] = wv;
+    const float hi = __uint_as_float(__float_as_uint(wv) & 0xFFFFE000u), lo = wv - hi;
+    if (wallT) { wallT[(long long)c * L.fin + k] = hi; wallT[nW + (long long)c * L.fin + k] = lo; }
+    if (wsplit) { wsplit[idx] = hi; wsplit[nW + idx] = lo; }
   }
   if (idx < L.fo_tot) {
     const int c = (int)idx;
@@ -86,13 +91,13 @@ __device__ __forceinline__ void store4(float* __restrict__ row, int q, int lane,
   }
 }
 
-// grid (row tiles of kStatRows, V).  8 warps x 8 rows.
+// grid (row tiles of kStatRows, V).  kAggWarps warps x kAggRows rows.
 template <int VEC>
-__global__ void __launch_bounds__(256) agg_fwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+__global__ void __launch_bounds__(kAggThreads) agg_fwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                       const float* __restrict__ ball, const float* __restrict__ sig,
                                                       float* __restrict__ Y, float* __restrict__ invR,
                                                       float* __restrict__ partial, int n_pad, int want_stats) {
-  __shared__ float s_red[8][2][128];
+  __shared__ float s_red[kAggWarps][2][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -107,8 +112,8 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(PlanDev p, LayerDev L, con
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     float bias4[4];
     load4<VEC>(ball + off, q, lane, fo, bias4);
-    for (int r = 0; r < 8; ++r) {
-      const int t = tile * kStatRows + warp * 8 + r;
+    for (int r = 0; r < kAggRows; ++r) {
+      const int t = tile * kStatRows + warp * kAggRows + r;
       if (t >= T) break;
       const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
       const int deg = e1 - e0;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(PlanDev p, LayerDev L, con
         if (c < fo) {
           float a = 0.f, b = 0.f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) { a += s_red[w][0][threadIdx.x]; b += s_red[w][1][threadIdx.x]; }
+          for (int w = 0; w < kAggWarps; ++w) { a += s_red[w][0][threadIdx.x]; b += s_red[w][1][threadIdx.x]; }
           partial[((size_t)tile * 2 + 0) * ld + off + c] = a;
           partial[((size_t)tile * 2 + 1) * ld + off + c] = b;
         }
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(PlanDev p, const float* _
   X[idx] = x;
 }
 
-// float4 form (C % 4 == 0): grid (ceil(C/4/128), ceil(t_cap/16)); a thread owns 4 channels for 16 rows
+// float4 form (C % 4 == 0): grid (ceil(C/4/128), ceil(t_cap/kEltRows)); a thread owns 4 channels for kEltRows rows
 __global__ void __launch_bounds__(128) bn_apply_vec_kernel(PlanDev p, const float* __restrict__ Y,
                                                            const float* __restrict__ ball, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, float* __restrict__ X, int C,
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(128) bn_apply_vec_kernel(PlanDev p, const floa
   unsigned long long seed = 0, off = 0;
   if (drop) { seed = rng[0]; off = rng[1]; }
   const Philox ph(seed);
-  const int r0 = blockIdx.y * 16, r1 = min(p.t_cap, r0 + 16);
+  const int r0 = blockIdx.y * kEltRows, r1 = min(p.t_cap, r0 + kEltRows);
 #pragma unroll 4
   for (int t = r0; t < r1; ++t) {
     const size_t idx = (size_t)t * C + c;
@@ -326,12 +331,12 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
   if (n < C) n = C;
   EAGCN_PROF("prep_params_kernel", st);
-  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->wallT, (float*)w->ball, (float*)w->sig);
+  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->wallT, (float*)w->wsplit, (float*)w->ball, (float*)w->sig);
   EAGCN_LAUNCH_CHECK();
   int rc;
   if (gemm_mode() != 1 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
     rc = tc::gemm_tc_nt((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, (float*)w->Z, C, p.t_cap, C, L.fin,
-                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nn");
+                        p.counts + EAGCN_CNT_T, st, "gemm_tc_nn", (const float*)w->wallT + (size_t)L.fin * C);
   else
     rc = gemm_nn((const float*)w->H, L.fin, (const float*)w->wall, C, (float*)w->Z, C, p.t_cap, C, L.fin,
                  p.counts + EAGCN_CNT_T, st);
@@ -341,11 +346,11 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   const int want = w->training ? 1 : 0;
   if (vec4_ok(layer)) {
     EAGCN_PROF("agg_fwd_kernel", st);
-    agg_fwd_kernel<4><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+    agg_fwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
   } else {
     EAGCN_PROF("agg_fwd_kernel", st);
-    agg_fwd_kernel<1><<<grid, 256, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+    agg_fwd_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
   }
   EAGCN_LAUNCH_CHECK();
@@ -374,7 +379,7 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
   EAGCN_LAUNCH_CHECK();
   const long long total = (long long)p.t_cap * C;
   if ((C & 3) == 0 && aligned16(w->Y) && aligned16(w->X)) {
-    dim3 grid((C / 4 + 127) / 128, (p.t_cap + 15) / 16);
+    dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_apply_kernel", st);
     bn_apply_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
                                               (const float*)w->invstd, (float*)w->X, C, w->training ? 1 : 0,

@@ -118,7 +118,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
         X = torch.empty(T, C, **f32)
         invR = torch.empty(plan.V, T, **f32)
         wall = torch.empty(cfg.fin, C, **f32)
-        wallT = torch.empty(C, cfg.fin, **f32)
+        wallT = torch.empty(2, C, cfg.fin, **f32)
+        wsplit = torch.empty(2, cfg.fin, C, **f32)
         ball = torch.empty(4, C, **f32)
         sig = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
@@ -131,7 +132,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
             rng_snapshot = rng.state.clone()        # backward regenerates the same keep mask from it
         w.H, w.Z, w.Y, w.X, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(X), ptr(invR)
         w.wall, w.ball, w.sig, w.partial, w.sums = ptr(wall), ptr(ball), ptr(sig), ptr(partial), ptr(sums)
-        w.wallT = ptr(wallT)
+        w.wallT, w.wsplit = ptr(wallT), ptr(wsplit)
         w.mean, w.invstd = ptr(mean), ptr(invstd)
         w.rng = ptr(rng_snapshot)
         w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
@@ -145,14 +146,14 @@ class _GraphConvLayerFn(torch.autograd.Function):
         if rng_snapshot is not None:
             rng.advance()
         ctx.plan, ctx.cfg, ctx.buffers, ctx.params = plan, cfg, buffers, params
-        ctx.saved = (H, Z, Y, invR, wall, ball, sig, mean, invstd, rng_snapshot)
+        ctx.saved = (H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot)
         return X
 
     @staticmethod
     def backward(ctx, dX):
         L = lib()
         plan, cfg, buffers, params = ctx.plan, ctx.cfg, ctx.buffers, ctx.params
-        H, Z, Y, invR, wall, ball, sig, mean, invstd, rng_snapshot = ctx.saved
+        H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot = ctx.saved
         dev = plan.device
         ls = _layer_struct(plan, cfg, params, buffers)
         C = int(ls.fo_tot)
@@ -172,6 +173,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         gemm_ws = torch.empty(max(ws_bytes // 4, 1), **f32)
         w.H, w.Z, w.Y, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(invR)
         w.wall, w.ball, w.sig, w.partial = ptr(wall), ptr(ball), ptr(sig), ptr(partial)
+        w.wsplit = ptr(wsplit)
         w.mean, w.invstd, w.rng = ptr(mean), ptr(invstd), ptr(rng_snapshot)
         w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)

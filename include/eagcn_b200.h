@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 6
+#define EAGCN_ABI_VERSION 7
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -124,7 +124,8 @@ typedef struct eagcn_work {
   void* bsums;    /* f64 [2, fo_tot]       backward batch sums (sum g, sum g*xhat)         */
   void* gemm_ws;  /* f32 split-K workspace, gemm_ws_bytes bytes                            */
   int64_t gemm_ws_bytes;
-  void* wallT;    /* f32 [fo_tot, fin]     W_all transposed (K-major B operand of the tcgen05 GEMM) */
+  void* wallT;    /* f32 [2, fo_tot, fin]  W_all transposed, split hi / lo (K-major B operand of Z = H W)   */
+  void* wsplit;   /* f32 [2, fin, fo_tot]  W_all split hi / lo          (K-major B operand of dH = Q W^T)   */
 } eagcn_work_t;
 
 int eagcn_version(void);

@@ -460,7 +460,13 @@ static int pick_bn_tn(int N) {          // multiple of 32 (whole MN boxes), <= 2
 int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long long ws_floats, int M, int N, int Kcap,
                const int* Kdev, int* nsplit_out, cudaStream_t st) {
   const int BN = pick_bn_tn(N);
-  const int ns = tn_splits(M, N, Kcap);
+  // as many K splits as keep the whole grid inside one wave of 148 CTAs (never more than the workspace bound)
+  int ns = tn_splits(M, N, Kcap);
+  {
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int one_wave = 148 / tiles;
+    if (one_wave >= 1 && ns > one_wave) ns = one_wave;
+  }
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
   CUtensorMap mA, mB;
   if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;

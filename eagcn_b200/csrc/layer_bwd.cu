@@ -24,7 +24,7 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
 long long gemm_tn_workspace_floats(int M, int N, int Kcap);
 int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t st);
 bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l);
-__global__ void stat_reduce_kernel(PlanDev p, const float* __restrict__ partial, double* __restrict__ sums, int C);
+struct StatEpilogue;
 
 template <int VEC>
 __device__ __forceinline__ void ld4(const float* __restrict__ row, int q, int lane, int lim, float (&o)[4]) {
@@ -390,7 +390,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
                                       void* stream) {
   if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
   if (!w->dX || !w->Y || !w->ball || !w->mean || !w->invstd || !w->partial || !w->bsums) return EAGCN_E_ARG;
-  if (w->training && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
+  if ((w->training & 1) && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   PlanDev p = to_dev(plan);
   const int C = (int)layer->fo_tot;
@@ -399,7 +399,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
     EAGCN_PROF("bn_bwd_partial_kernel", st);
     bn_bwd_partial_vec_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
-                                                    C, w->training ? 1 : 0, (float)w->p_drop,
+                                                    C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,
                                                     (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
@@ -408,12 +408,18 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
     EAGCN_PROF("bn_bwd_partial_kernel", st);
     bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                 (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
-                                                w->training ? 1 : 0, (float)w->p_drop,
+                                                (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                 (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
   }
+  // reduce the tile partials; without a host all-reduce in between (training bit1) also emit dbias/dgamma/dbeta
+  const bool host_allreduce = (w->training & 2) != 0;
+  if (!host_allreduce && !w->dvec) return EAGCN_E_ARG;
+  LayerDev L = to_dev(layer, plan);
+  StatEpilogue ep{host_allreduce ? 0 : 2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
+                  (w->training & 1) ? 1 : 0, 0.0, 0.0, 0.0};
   EAGCN_PROF("stat_reduce_kernel", st);
-  stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->bsums, C);
+  stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -435,22 +441,24 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
     EAGCN_PROF("bn_bwd_apply_kernel", st);
     bn_bwd_apply_vec_kernel<<<grid, 128, 0, st>>>(
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
-        (const float*)w->invstd, (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
+        (const float*)w->invstd, (const double*)w->bsums, (float*)w->dY, C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_bwd_apply_kernel", st);
     bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
-        (const double*)w->bsums, (float*)w->dY, C, w->training ? 1 : 0, (float)w->p_drop,
+        (const double*)w->bsums, (float*)w->dY, C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
     EAGCN_LAUNCH_CHECK();
   }
-  EAGCN_PROF("bn_bwd_finalize_kernel", st);
-  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
-                                                          (const double*)w->bsums, (float*)w->dvec, C,
-                                                          w->training ? 1 : 0);
-  EAGCN_LAUNCH_CHECK();
+  if (w->training & 2) {            // sums were all-reduced by the host after backward_a
+    EAGCN_PROF("bn_bwd_finalize_kernel", st);
+    bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
+                                                            (const double*)w->bsums, (float*)w->dvec, C,
+                                                            (w->training & 1) ? 1 : 0);
+    EAGCN_LAUNCH_CHECK();
+  }
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   if (vec4_ok_b(layer)) {
     EAGCN_PROF("agg_bwd_kernel", st);

@@ -171,9 +171,40 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_kernel(PlanDev p, LayerDe
   }
 }
 
-// sums[k][c] = sum over live tiles of partial[tile][k][c]   (double, fixed order)
-__global__ void __launch_bounds__(256) stat_reduce_kernel(PlanDev p, const float* __restrict__ partial,
-                                                          double* __restrict__ sums, int C) {
+// per-channel BatchNorm finalize from the batch sums (training) or the running statistics (eval)
+__device__ __forceinline__ void bn_finalize_channel(const LayerDev& L, const float* __restrict__ ball, int c, double s1,
+                                                    double s2, float* __restrict__ mean, float* __restrict__ invstd,
+                                                    int training, double M, double eps, double momentum) {
+  int v = 0;
+  while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+  const int cc = c - L.off[v];
+  if (training) {
+    const double b = (double)ball[c];
+    const double m1 = s1 / M;                            // mean of (Y - b) over all positions
+    double var = s2 / M - m1 * m1;                       // biased variance (shift-invariant)
+    if (var < 0.0) var = 0.0;
+    const double mu = b + m1;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + eps));
+    const double unb = M > 1.0 ? var * (M / (M - 1.0)) : var;
+    L.run_mean[v][cc] = (float)((1.0 - momentum) * (double)L.run_mean[v][cc] + momentum * mu);
+    L.run_var[v][cc] = (float)((1.0 - momentum) * (double)L.run_var[v][cc] + momentum * unb);
+    if (cc == 0 && L.nbt[v]) L.nbt[v][0] += 1;
+  } else {
+    mean[c] = L.run_mean[v][cc];
+    invstd[c] = 1.0f / sqrtf(L.run_var[v][cc] + (float)eps);
+  }
+}
+
+struct StatEpilogue {             // what stat_reduce_kernel does with the reduced sums of a channel
+  int kind;                       // 0: store sums only, 1: + forward BatchNorm finalize, 2: + backward dvec
+  const float* ball; float* mean; float* invstd; float* dvec;
+  int training; double M, eps, momentum;
+};
+
+// sums[k][c] = sum over live tiles of partial[tile][k][c]   (double, fixed order), then the per-channel epilogue
+__global__ void __launch_bounds__(256) stat_reduce_kernel(PlanDev p, LayerDev L, const float* __restrict__ partial,
+                                                          double* __restrict__ sums, int C, StatEpilogue ep) {
   __shared__ double s[8][2][32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -192,35 +223,25 @@ __global__ void __launch_bounds__(256) stat_reduce_kernel(PlanDev p, const float
 #pragma unroll
     for (int w = 0; w < 8; ++w) { aa += s[w][0][cx]; bb += s[w][1][cx]; }
     sums[c] = aa; sums[C + c] = bb;
+    if (ep.kind == 1) {
+      bn_finalize_channel(L, ep.ball, c, aa, bb, ep.mean, ep.invstd, ep.training, ep.M, ep.eps, ep.momentum);
+    } else if (ep.kind == 2) {      // dvec = [dbias | dgamma | dbeta]
+      ep.dvec[c] = ep.training ? 0.0f : (float)((double)ep.ball[C + c] * (double)ep.invstd[c] * aa);
+      ep.dvec[C + c] = (float)bb;
+      ep.dvec[2 * C + c] = (float)aa;
+    }
   }
 }
 
-// BatchNorm finalize: batch statistics over M = B*N padded positions (training) or running stats.
+// BatchNorm finalize from already reduced (and possibly all-reduced) sums
 __global__ void __launch_bounds__(256) bn_finalize_kernel(LayerDev L, const float* __restrict__ ball,
                                                           const double* __restrict__ sums, float* __restrict__ mean,
                                                           float* __restrict__ invstd, int training, double M,
                                                           double eps, double momentum) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= L.fo_tot) return;
-  int v = 0;
-  while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
-  const int cc = c - L.off[v];
-  if (training) {
-    const double b = (double)ball[c];
-    const double m1 = sums[c] / M;                       // mean of (Y - b) over all positions
-    double var = sums[L.fo_tot + c] / M - m1 * m1;       // biased variance (shift-invariant)
-    if (var < 0.0) var = 0.0;
-    const double mu = b + m1;
-    mean[c] = (float)mu;
-    invstd[c] = (float)(1.0 / sqrt(var + eps));
-    const double unb = M > 1.0 ? var * (M / (M - 1.0)) : var;
-    L.run_mean[v][cc] = (float)((1.0 - momentum) * (double)L.run_mean[v][cc] + momentum * mu);
-    L.run_var[v][cc] = (float)((1.0 - momentum) * (double)L.run_var[v][cc] + momentum * unb);
-    if (cc == 0 && L.nbt[v]) L.nbt[v][0] += 1;
-  } else {
-    mean[c] = L.run_mean[v][cc];
-    invstd[c] = 1.0f / sqrtf(L.run_var[v][cc] + (float)eps);
-  }
+  bn_finalize_channel(L, ball, c, training ? sums[c] : 0.0, training ? sums[L.fo_tot + c] : 0.0, mean, invstd, training, M,
+                      eps, momentum);
 }
 
 // X = dropout(relu((Y - mean) * invstd * gamma + beta)); one thread per 4 channels (scalar tail-safe)
@@ -343,7 +364,8 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (rc) return rc;
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);
-  const int want = w->training ? 1 : 0;
+  const int want = (w->training & 1) ? 1 : 0;
+  const bool host_allreduce = (w->training & 2) != 0;   // global-batch BatchNorm: host sums the partial sums over ranks
   if (vec4_ok(layer)) {
     EAGCN_PROF("agg_fwd_kernel", st);
     agg_fwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
@@ -354,9 +376,10 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
   }
   EAGCN_LAUNCH_CHECK();
-  if (want) {
+  if (want && host_allreduce) {
+    StatEpilogue ep{0, nullptr, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0};
     EAGCN_PROF("stat_reduce_kernel", st);
-    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, (const float*)w->partial, (double*)w->sums, C);
+    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
     EAGCN_LAUNCH_CHECK();
   }
   return 0;
@@ -366,23 +389,33 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
                                      void* stream) {
   if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
   if (!w->Y || !w->X || !w->ball || !w->sums || !w->mean || !w->invstd) return EAGCN_E_ARG;
-  if (w->training && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
+  if ((w->training & 1) && w->p_drop > 0.0 && !w->rng) return EAGCN_E_ARG;
   if (w->p_drop < 0.0 || w->p_drop >= 1.0) return EAGCN_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   PlanDev p = to_dev(plan);
   LayerDev L = to_dev(layer, plan);
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
-  EAGCN_PROF("bn_finalize_kernel", st);
-  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
-                                                      (float*)w->invstd, w->training ? 1 : 0, M, w->eps, w->momentum);
-  EAGCN_LAUNCH_CHECK();
+  const int training = (w->training & 1) ? 1 : 0;
+  if (training && !(w->training & 2)) {
+    // per-replica statistics: reduce the tile partials and finalize in one kernel
+    if (!w->partial) return EAGCN_E_ARG;
+    StatEpilogue ep{1, (const float*)w->ball, (float*)w->mean, (float*)w->invstd, nullptr, 1, M, w->eps, w->momentum};
+    EAGCN_PROF("stat_reduce_kernel", st);
+    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    EAGCN_LAUNCH_CHECK();
+  } else {
+    EAGCN_PROF("bn_finalize_kernel", st);
+    bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
+                                                        (float*)w->invstd, training, M, w->eps, w->momentum);
+    EAGCN_LAUNCH_CHECK();
+  }
   const long long total = (long long)p.t_cap * C;
   if ((C & 3) == 0 && aligned16(w->Y) && aligned16(w->X)) {
     dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_apply_kernel", st);
     bn_apply_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
-                                              (const float*)w->invstd, (float*)w->X, C, w->training ? 1 : 0,
+                                              (const float*)w->invstd, (float*)w->X, C, training,
                                               (float)w->p_drop, (const unsigned long long*)w->rng,
                                               (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
@@ -390,7 +423,7 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
     EAGCN_PROF("bn_apply_kernel", st);
     bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
-        w->training ? 1 : 0, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
+        training, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
   }
   return 0;

@@ -135,7 +135,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.wallT, w.wsplit = ptr(wallT), ptr(wsplit)
         w.mean, w.invstd = ptr(mean), ptr(invstd)
         w.rng = ptr(rng_snapshot)
-        w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
+        w.training = (1 if cfg.training else 0) | (2 if (cfg.training and cfg.stat_allreduce is not None) else 0)
+        w.rng_stream = int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
         st = _stream()
@@ -175,7 +176,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.wall, w.ball, w.sig, w.partial = ptr(wall), ptr(ball), ptr(sig), ptr(partial)
         w.wsplit = ptr(wsplit)
         w.mean, w.invstd, w.rng = ptr(mean), ptr(invstd), ptr(rng_snapshot)
-        w.training, w.rng_stream = int(cfg.training), int(cfg.rng_stream)
+        w.training = (1 if cfg.training else 0) | (2 if (cfg.training and cfg.stat_allreduce is not None) else 0)
+        w.rng_stream = int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
         w.dX, w.dY, w.Q, w.dH, w.dwall, w.dvec, w.datt = ptr(dX), ptr(dY), ptr(Q), ptr(dH), ptr(dwall), ptr(dvec), ptr(datt)

@@ -106,7 +106,9 @@ typedef struct eagcn_work {
   void* mean;     /* f32 [fo_tot]                                                         */
   void* invstd;   /* f32 [fo_tot]                                                         */
   void* rng;      /* u64 [2]               philox seed, offset (device; graph-replay safe) */
-  int64_t training;
+  int64_t training;     /* bit0: training mode (batch statistics, dropout); bit1: the host all-reduces `sums`
+                         * between forward_a and forward_b and `bsums` between backward_a and backward_b
+                         * (global-batch BatchNorm); without bit1 the reductions are fused into fewer kernels */
   int64_t rng_stream;   /* distinguishes layers sharing one rng state                      */
   int64_t m_total;      /* BatchNorm population: B*N of the (global) padded batch           */
   int64_t n_pad;        /* padded width N used for the (N - deg)*1e-9 normaliser term       */

@@ -200,13 +200,25 @@ def test_layer_vs_oracle(B, dataset, fin, fo, training):
     dense = [torch.from_numpy(a) for a in batch.dense()]
     sd = O.clone_sd({("layer1." + k): v for k, v in layer.state_dict().items()}, requires_grad=True)
     codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
-    afm_ref = dense[1].clone().requires_grad_(True)
-    ref = O.layer_forward(sd, "layer1.", dense[0], afm_ref, codes, training)
     ins = _to(dev, dense)
     ins[1].requires_grad_(True)
     x, A = layer(*ins)
+    # ReLU decisions of the implementation under test (p = 0: x > 0 <=> pre-activation > 0), per view
+    xg = x.detach().cpu()
+    masks, off = [], 0
+    for w in fo:
+        masks.append((xg[:, :, off:off + w] > 0).float()); off += w
+    afm_ref = dense[1].clone().requires_grad_(True)
+    ref = O.layer_forward(sd, "layer1.", dense[0], afm_ref, codes, training, relu_masks=masks)
     assert rel_err(x.cpu(), ref["x"]) <= TOL
     assert rel_err(A.cpu(), ref["A_weight"]) <= TOL
+    # ... which may differ from the oracle's own (Z > 0) only at the kink: |Z| below the forward tolerance
+    m = dense[0].max(2).values.unsqueeze(2)
+    for v, Zv in enumerate(ref["Z"]):
+        disagree = ((Zv.detach() > 0).float() != masks[v]) & (m > 0)
+        if bool(disagree.any()):
+            assert float(Zv.detach().abs()[disagree].max()) <= 1e-4 * float(Zv.detach().abs().max())
+            assert int(disagree.sum()) <= 1e-4 * disagree.numel() + 8
     gen = torch.Generator().manual_seed(1)
     R = torch.randn(ref["x"].shape, generator=gen)
     (ref["x"] * R).sum().backward()
@@ -302,3 +314,61 @@ def test_full_size_properties():
         plan = GraphPlan.from_codes(torch.from_numpy(batch.codes).to(dev), batch.channels).check()
         yc, _, _ = model(plan, ins[1], size=size)
         assert torch.equal(yc, y)
+
+
+# ------------------------------------------------------------------ K != 5 views (BASELINE config 5 sweep)
+@pytest.mark.parametrize("V,fixed_n,B", [(1, 32, 24), (10, 64, 12), (5, 128, 6)])
+def test_view_count_sweep_vs_oracle(V, fixed_n, B):
+    """K in {1, 5, 10} views, fixed-N batches: the functional core against K independent oracle blocks
+    (the reference hard-codes 5 blocks, layers.py:269-273; the oracle for K != 5 is K GraphConv_blocks + cat)."""
+    from eagcn_b200 import functional as EF
+    from eagcn_b200.data import make_batch
+    from eagcn_b200.plan import GraphPlan
+    dev = _cuda()
+    fin, fo = 24, tuple([16, 12, 8, 8, 4, 12, 8, 4, 4, 4][:V])
+    batch = make_batch(B, "tox21", seed=V, kb=9, n_views=V, fixed_n=fixed_n)
+    gen = torch.Generator().manual_seed(V)
+    sd = {}
+    for v in range(V):
+        pre = f"layer1.block{v + 1}."
+        C = batch.channels[v]
+        sd[pre + "att.weight"] = torch.randn(1, C, 1, 1, generator=gen)
+        sd[pre + "self_r"] = torch.randn(1, generator=gen) * 0.3
+        sd[pre + "graph_conv.weight"] = torch.randn(fin, fo[v], generator=gen) * 0.2
+        sd[pre + "graph_conv.bias"] = torch.randn(fo[v], generator=gen) * 0.1
+        sd[pre + "batch_norm.bn.weight"] = torch.rand(fo[v], generator=gen) + 0.5
+        sd[pre + "batch_norm.bn.bias"] = torch.randn(fo[v], generator=gen) * 0.1
+        sd[pre + "batch_norm.bn.running_mean"] = torch.zeros(fo[v])
+        sd[pre + "batch_norm.bn.running_var"] = torch.ones(fo[v])
+    dense = [torch.from_numpy(a) for a in batch.dense()]
+    ref_sd = O.clone_sd(sd, requires_grad=True)
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    afm_ref = dense[1].clone().requires_grad_(True)
+    ref = O.layer_forward(ref_sd, "layer1.", dense[0], afm_ref, codes, True, n_views=V)
+
+    dsd = {k: v.to(dev).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    plan = GraphPlan.build(dense[0].to(dev), [r.to(dev) for r in dense[2:]]).check()
+    params, buffers = [], []
+    for v in range(V):
+        pre = f"layer1.block{v + 1}."
+        params += [dsd[pre + k] for k in ("att.weight", "self_r", "graph_conv.weight", "graph_conv.bias",
+                                         "batch_norm.bn.weight", "batch_norm.bn.bias")]
+        buffers += [dsd[pre + "batch_norm.bn.running_mean"], dsd[pre + "batch_norm.bn.running_var"], None]
+    afm = dense[1].to(dev).requires_grad_(True)
+    cfg = EF.LayerConfig(fin=fin, fo=fo, training=True)
+    X = EF.graph_conv_layer(plan, cfg, EF.gather_rows(plan, afm), params, buffers)
+    x = EF.scatter_rows(plan, X)
+    assert rel_err(x.cpu(), ref["x"]) <= TOL
+    gen2 = torch.Generator().manual_seed(5)
+    R = torch.randn(ref["x"].shape, generator=gen2)
+    (ref["x"] * R).sum().backward()
+    (x * R.to(dev)).sum().backward()
+    assert rel_err(afm.grad.cpu(), afm_ref.grad) <= 2 * TOL
+    scale = max(float(t.grad.abs().max()) for t in ref_sd.values() if t.grad is not None)
+    for k, t in ref_sd.items():
+        if t.grad is None:
+            continue
+        denom = max(float(t.grad.abs().max()), 1e-3 * scale)
+        if k.endswith("graph_conv.bias"):
+            denom = scale
+        assert float((dsd[k].grad.cpu() - t.grad).abs().max()) / denom <= 5 * TOL, k

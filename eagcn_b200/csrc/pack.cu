@@ -116,7 +116,7 @@ template <bool kCodes>
 __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, const float* __restrict__ adj,
                                                                  const uint8_t* __restrict__ codes, RelPtrs rel) {
   __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
-  __shared__ int s_code[8][32], s_cnt[8][32];
+  __shared__ int s_hit[8][EAGCN_MAX_VIEWS][32];      // per (view, edge of the chunk): (#nonzero planes << 16) + plane index
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
   const int row0 = blockIdx.x * kPackRows;
@@ -168,38 +168,55 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
       const int ne = __popc(m);
       const int slot = __popc(m & ((1u << lane) - 1u));          // edge index of this lane inside the chunk
       if (nz) p.colpos[e0 + run + slot] = b * p.N + j;
-      for (int v = 0; v < p.V; ++v) {
-        const int C = p.chan[v];
-        if (kCodes) {
+      if (kCodes) {
+        for (int v = 0; v < p.V; ++v) {
+          const int C = p.chan[v];
           if (nz) {
             const int c = __ldg(codes + bc + (size_t)v * p.N * p.N + j);
             if (c > C) bad = true;
             p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)(c > C ? C : c);
           }
-        } else {
-          // gather the C_v one-hot planes at the ne bonded pairs of this chunk: (edge, channel) pairs are
-          // spread over the lanes, consecutive lanes -> neighbouring columns of the same plane
-          s_code[warp][lane] = C; s_cnt[warp][lane] = 0;
-          __syncwarp();
-          const float* base = rel.p[v] + (((size_t)b * C) * p.N + i) * p.N + j0;
-          const int total = ne * C;
-          for (int idx = lane; idx < total; idx += 32) {
-            const int k = idx % ne, c = idx / ne;
-            const int jj = __fns(m, 0, k + 1);                   // lane position of the k-th edge
-            const float x = __ldg(base + (size_t)c * p.N * p.N + jj);
-            if (x != 0.0f) {
-              if (x != 1.0f) bad = true;
-              atomicAdd(&s_cnt[warp][k], 1);
-              s_code[warp][k] = c;
+        }
+      } else {
+        // gather ALL views' one-hot planes at the ne bonded pairs of this chunk in one batch: the (plane, edge)
+        // pairs of every view are spread over the lanes (consecutive lanes -> neighbouring columns of one plane)
+        // and up to 4 loads per lane are in flight before any is consumed.
+        for (int v = 0; v < p.V; ++v) s_hit[warp][v][lane] = 0;
+        __syncwarp();
+        int sc = 0;
+        for (int v = 0; v < p.V; ++v) sc += p.chan[v];
+        const int total = ne * sc;
+        for (int base = 0; base < total; base += 128) {
+          float x[4]; int vv[4], cc[4], kk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 32 + lane;
+            x[u] = 0.0f; vv[u] = 0; cc[u] = 0; kk[u] = 0;
+            if (idx < total) {
+              int gc = idx / ne, v = 0;
+              kk[u] = idx - gc * ne;
+              while (gc >= p.chan[v]) { gc -= p.chan[v]; ++v; }
+              vv[u] = v; cc[u] = gc;
+              const int jj = __fns(m, 0, kk[u] + 1);               // lane position of the k-th edge
+              x[u] = __ldg(rel.p[v] + ((((size_t)b * p.chan[v]) + gc) * p.N + i) * p.N + j0 + jj);
             }
           }
-          __syncwarp();
-          if (nz) {
-            if (s_cnt[warp][slot] > 1) bad = true;
-            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)s_code[warp][slot];
-          }
-          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (x[u] != 0.0f) {
+              if (x[u] != 1.0f) bad = true;
+              atomicAdd(&s_hit[warp][vv[u]][kk[u]], (1 << 16) + cc[u]);
+            }
         }
+        __syncwarp();
+        if (nz) {
+          for (int v = 0; v < p.V; ++v) {
+            const int h = s_hit[warp][v][slot];
+            if ((h >> 16) > 1) bad = true;
+            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)((h >> 16) == 1 ? (h & 0xFFFF) : p.chan[v]);
+          }
+        }
+        __syncwarp();
       }
       run += ne;
     }

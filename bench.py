@@ -178,6 +178,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -203,10 +204,22 @@ def run_b200(args):
 
     params = [p for p in model.parameters() if p.requires_grad]
 
+    def layers_only(plan, s):
+        from eagcn_b200 import functional as EF
+        from eagcn_b200.layers import PackedRows
+        h = PackedRows(EF.gather_rows(plan, s.dev_dense[1]), plan)
+        for layer in model.conv_layers:
+            h, _ = layer(plan, h)
+        out = EF.readout_sum(plan, h.rows)
+        out.sum().backward()
+        return out[:, :NCLASS]
+
     def step_dense(s):
         for p in params:
             p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
         plan = GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
+        if args.layers_only:
+            return layers_only(plan, s)
         out, _, _ = model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
         return out
@@ -398,6 +411,10 @@ def run_b200(args):
             cpu = run_cpu_baseline(steps=3, warmup=1, budget_s=25.0)
 
     if rank == 0:
+        if args.layers_only:
+            print(json.dumps({"diagnostic": "layers-only (no dense head)", "ms_per_step": ms_step, "value": value,
+                              "e2e_packed_ms": ms_e2e_p / k_e2e, "gpu_launches_per_step": int(launches_per_step)}))
+            return
         line = {
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -541,6 +558,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nbatches", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--layers-only", action="store_true",
+                    help="diagnostic: loss = sum of the last layer's atom rows (no read-out / dense head); not a bench value")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")

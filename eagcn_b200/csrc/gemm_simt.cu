@@ -144,8 +144,9 @@ int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t s
   return 0;
 }
 
+// nsplit_out != nullptr: leave the split-K partials in ws (the caller reduces them) and report their number
 int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, int N, int Kcap, const int* Kdev,
-            float* ws, long long ws_floats, cudaStream_t st) {
+            float* ws, long long ws_floats, cudaStream_t st, int* nsplit_out = nullptr) {
   // A given as [K, M] row-major, B as [K, N] row-major; C [M, N] (ldc = N)
   const int ns = tc::tn_splits(M, N, Kcap);
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
@@ -156,6 +157,7 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
   EAGCN_PROF("gemm_simt_tn", st);
   gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, st>>>(g);
   EAGCN_LAUNCH_CHECK();
+  if (nsplit_out) { *nsplit_out = ns; return 0; }
   return splitk_reduce(ws, C, (long long)M * N, ns, st);
 }
 

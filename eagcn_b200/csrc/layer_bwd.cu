@@ -20,7 +20,7 @@ namespace eagcn {
 int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
             const int* Mdev, cudaStream_t st);
 int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, int N, int Kcap, const int* Kdev,
-            float* ws, long long ws_floats, cudaStream_t st);
+            float* ws, long long ws_floats, cudaStream_t st, int* nsplit_out);
 long long gemm_tn_workspace_floats(int M, int N, int Kcap);
 int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t st);
 bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l);
@@ -368,6 +368,35 @@ __global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float
   datt[i] = (float)a;
 }
 
+// One launch finishing the layer backward:
+//  (a) dW: sum the split-K partials [ns][fin][C] in z order and store them VIEW-BLOCKED -- view v's [fin, fo_v]
+//      block contiguous at offset fin*off_v -- so that each GraphConv_block's weight gradient is a contiguous tensor;
+//  (b) d att / d self_r: sum the per-tile partials in tile order.
+__global__ void __launch_bounds__(256) bwd_post_kernel(PlanDev p, LayerDev L, const float* __restrict__ wpart, int ns,
+                                                       float* __restrict__ dwall, const float* __restrict__ dpart,
+                                                       float* __restrict__ datt, int nblk_w) {
+  const int C = L.fo_tot;
+  if ((int)blockIdx.x < nblk_w) {
+    const long long n = (long long)L.fin * C;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    float s = 0.0f;
+    for (int z = 0; z < ns; ++z) s += wpart[(long long)z * n + idx];
+    const int k = (int)(idx / C), c = (int)(idx - (long long)k * C);
+    int v = 0;
+    while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+    dwall[(long long)L.fin * L.off[v] + (long long)k * L.fo[v] + (c - L.off[v])] = s;
+  } else {
+    const int i = ((int)blockIdx.x - nblk_w) * 256 + threadIdx.x;
+    if (i >= L.V * EAGCN_SIG_STRIDE) return;
+    const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+    const int ntile = (T + kStatRows - 1) / kStatRows;
+    double a = 0.0;
+    for (int t = 0; t < ntile; ++t) a += (double)dpart[(size_t)t * L.V * EAGCN_SIG_STRIDE + i];
+    datt[i] = (float)a;
+  }
+}
+
 static bool vec4_ok_b(const eagcn_layer_t* l) {
   if (l->fo_tot % 4) return false;
   for (int v = 0; v < l->V; ++v) if ((l->fo[v] % 4) || (l->off[v] % 4)) return false;
@@ -428,7 +457,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
                                       void* stream) {
   if (!plan_ok(plan) || !w || !layer_ok(plan, layer)) return EAGCN_E_ARG;
   if (!w->dX || !w->Y || !w->Z || !w->H || !w->ball || !w->mean || !w->invstd || !w->partial || !w->bsums || !w->dY ||
-      !w->Q || !w->dH || !w->dwall || !w->dvec || !w->datt || !w->wall || !w->sig || !w->invR || !w->gemm_ws)
+      !w->Q || !w->dwall || !w->dvec || !w->datt || !w->wall || !w->sig || !w->invR || !w->gemm_ws)
     return EAGCN_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   PlanDev p = to_dev(plan);
@@ -472,26 +501,29 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
                                             (float*)w->Q, (float*)w->partial);
   }
   EAGCN_LAUNCH_CHECK();
-  EAGCN_PROF("datt_reduce_kernel", st);
-  datt_reduce_kernel<<<(L.V * EAGCN_SIG_STRIDE + 255) / 256, 256, 0, st>>>(p, (const float*)w->partial, (float*)w->datt,
-                                                                           L.V);
-  EAGCN_LAUNCH_CHECK();
-  int rc;
-  if (gemm_mode() != 1 && w->wsplit && tc::tc_supported((const float*)w->Q, C, (const float*)w->wsplit, C, C))
+  int rc = 0;
+  if (!w->dH) {
+    // the layer input needs no gradient (first layer fed by data): skip dH = Q W^T altogether
+  } else if (gemm_mode() != 1 && w->wsplit && tc::tc_supported((const float*)w->Q, C, (const float*)w->wsplit, C, C))
     rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wsplit, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                         p.counts + EAGCN_CNT_T, st, "gemm_tc_nt", (const float*)w->wsplit + (size_t)L.fin * C);
   else
     rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                  p.counts + EAGCN_CNT_T, st);
   if (rc) return rc;
-  if (gemm_mode() == 0 && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->Q, C, p.t_cap)) {
-    int ns = 0;
+  int ns = 0;
+  if (gemm_mode() == 0 && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->Q, C, p.t_cap))
     rc = tc::gemm_tc_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->gemm_ws,
                         w->gemm_ws_bytes / (long long)sizeof(float), L.fin, C, p.t_cap, p.counts + EAGCN_CNT_T, &ns, st);
-    if (rc) return rc;
-    return splitk_reduce((const float*)w->gemm_ws, (float*)w->dwall, (long long)L.fin * C, ns, st);
-  }
-  rc = gemm_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->dwall, L.fin, C, p.t_cap,
-               p.counts + EAGCN_CNT_T, (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st);
-  return rc;
+  else
+    rc = gemm_tn((const float*)w->H, L.fin, (const float*)w->Q, C, nullptr, L.fin, C, p.t_cap, p.counts + EAGCN_CNT_T,
+                 (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st, &ns);
+  if (rc) return rc;
+  const int nblk_w = (int)(((long long)L.fin * C + 255) / 256);
+  const int nblk_a = (L.V * EAGCN_SIG_STRIDE + 255) / 256;
+  EAGCN_PROF("bwd_post_kernel", st);
+  bwd_post_kernel<<<nblk_w + nblk_a, 256, 0, st>>>(p, L, (const float*)w->gemm_ws, ns, (float*)w->dwall,
+                                                   (const float*)w->partial, (float*)w->datt, nblk_w);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
 }

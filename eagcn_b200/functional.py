@@ -123,7 +123,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         ball = torch.empty(4, C, **f32)
         sig = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
-        sums = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        sums = torch.empty(2, C, dtype=torch.float64, device=dev)
         mean = torch.empty(C, **f32)
         invstd = torch.empty(C, **f32)
         rng = RngState.get(dev)
@@ -164,11 +164,12 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w = WorkStruct()
         dY = torch.empty(T, C, **f32)
         Q = torch.empty(T, C, **f32)
-        dH = torch.empty(T, cfg.fin, **f32)
-        dwall = torch.empty(cfg.fin, C, **f32)
+        need_dH = ctx.needs_input_grad[3]
+        dH = torch.empty(T, cfg.fin, **f32) if need_dH else None
+        dwall = torch.empty(cfg.fin * C, **f32)        # view-blocked: each view's [fin, fo_v] block contiguous
         dvec = torch.empty(3, C, **f32)
         datt = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
-        bsums = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        bsums = torch.empty(2, C, dtype=torch.float64, device=dev)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
         ws_bytes = int(L.eagcn_gemm_workspace_bytes(cfg.fin, C, T))
         gemm_ws = torch.empty(max(ws_bytes // 4, 1), **f32)
@@ -193,7 +194,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
             fo = cfg.fo[v]
             a, r, W, b, g, be = params[6 * v: 6 * v + 6]
             grads += [datt[v, :plan.channels[v]].reshape(a.shape), datt[v, 256:257].reshape(r.shape),
-                      dwall[:, off:off + fo], dvec[0, off:off + fo], dvec[1, off:off + fo], dvec[2, off:off + fo]]
+                      dwall[cfg.fin * off: cfg.fin * (off + fo)].view(cfg.fin, fo),
+                      dvec[0, off:off + fo], dvec[1, off:off + fo], dvec[2, off:off + fo]]
             off += fo
         return (None, None, None, dH, *grads)
 

@@ -119,8 +119,9 @@ typedef struct eagcn_work {
   void* dX;       /* f32 [t_cap, fo_tot]   gradient wrt X (packed)                         */
   void* dY;       /* f32 [t_cap, fo_tot]   workspace                                       */
   void* Q;        /* f32 [t_cap, fo_tot]   workspace: sum_v A_v^T dY_v                     */
-  void* dH;       /* f32 [t_cap, fin]      out                                             */
-  void* dwall;    /* f32 [fin, fo_tot]     out: gradient of the concatenated weights       */
+  void* dH;       /* f32 [t_cap, fin]      out; NULL = the layer input needs no gradient (product skipped) */
+  void* dwall;    /* f32 [fin * fo_tot]    out: weight gradients, view-blocked: view v's [fin, fo_v]
+                   *                        block is contiguous at offset fin * off[v]            */
   void* dvec;     /* f32 [3, fo_tot]       out: dbias, dgamma, dbeta                       */
   void* datt;     /* f32 [V, 257]          out: d att_w (first C_v), [256] = d self_r      */
   void* bsums;    /* f64 [2, fo_tot]       backward batch sums (sum g, sum g*xhat)         */

@@ -10,7 +10,8 @@ elif grep -q "failed\|Killed\|rror" gpurun_out/${TAG}_gemm_tn.log; then ENG=tcge
 echo "engine for the rest of this visit: $ENG" | tee -a gpurun_out/${TAG}_gemm.log
 EAGCN_GEMM=$ENG timeout -s KILL 500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_gemm.py 2>&1 | tail -30 | tee gpurun_out/${TAG}_tests.log
 timeout -s KILL 500 python bench.py --steps 100 --warmup 10 --gemm $ENG > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-tail -c 1500 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+tail -c 1500 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+timeout -s KILL 300 python bench.py --steps 100 --warmup 10 --gemm $ENG --layers-only --no-cpu 2>/dev/null | tail -1 | tee gpurun_out/${TAG}_layers_only.json
 # launch list of 2 steady-state eager steps (3 warm-up steps skipped by kernel count is fragile -> profile all 5, aggregate offline)
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --profile-only --steps 2 --warmup 3 --nbatches 2 --gemm $ENG > gpurun_out/${TAG}_ncu_bench.log 2>&1

@@ -6,6 +6,7 @@
 #include "layer_fwd.cu"
 #include "layer_bwd.cu"
 #include "attention.cu"
+#include "head.cu"
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
 extern "C" int eagcn_set_gemm_mode(int mode) {

@@ -439,3 +439,13 @@ extern "C" int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* 
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
+
+extern "C" int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, double p_drop, int64_t total, void* keep_out,
+                                       void* stream) {
+  if (!rng || !keep_out || total <= 0 || p_drop < 0.0 || p_drop >= 1.0) return EAGCN_E_ARG;
+  EAGCN_PROF("dropout_mask_kernel", stream);
+  dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      total, (float)p_drop, (const unsigned long long*)rng, (unsigned long long)rng_stream, (uint8_t*)keep_out);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}

@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import LayerStruct, WorkStruct, check, lib, ptr
+from ._lib import HeadStruct, LayerStruct, WorkStruct, check, lib, ptr
 from .plan import GraphPlan, _stream
 
 _F32 = torch.float32
@@ -306,6 +306,120 @@ def dropout_keep_mask(plan, cfg: LayerConfig, fo_tot, rng_state):
     w.p_drop, w.rng_stream = float(cfg.p_drop), int(cfg.rng_stream)
     keep = torch.empty(plan.t_cap, fo_tot, dtype=torch.uint8, device=plan.device)
     check(lib().eagcn_dropout_mask(plan.ref, ctypes.byref(w), fo_tot, ptr(keep), _stream()), "eagcn_dropout_mask")
+    return keep
+
+
+# ------------------------------------------------------------------------------------------------
+_head_bars = {}
+
+
+def _head_bar(dev):
+    key = torch.device(dev).index or 0
+    if key not in _head_bars:
+        _head_bars[key] = torch.zeros(2, dtype=torch.int32, device=dev)     # grid-barrier state, lives forever
+    return _head_bars[key]
+
+
+class _HeadFn(torch.autograd.Function):
+    """Graph_BN -> den1 -> bn_den1 -> ReLU -> dropout -> den2 -> bn_den2 -> ReLU -> den3 (models.py:112-120)
+    in one kernel per direction.  Inputs: x0, then (W1, W2, W3, g0, b0, g1, b1, g2, b2)."""
+
+    @staticmethod
+    def forward(ctx, cfg, bufs, x0, *params):
+        training, p_drop, rng_stream, eps, momentum = cfg
+        dev = x0.device
+        x0 = x0.contiguous()
+        params = tuple(p.detach().contiguous() for p in params)
+        W1, W2, W3, g0, b0, g1, b1, g2, b2 = params
+        B, F = x0.shape
+        D1, D2, NC = W1.shape[1], W2.shape[1], W3.shape[1]
+        if W1.shape[0] != F or W2.shape[0] != D1 or W3.shape[0] != D2:
+            raise ValueError("dense head: inconsistent weight shapes")
+        f32 = dict(dtype=_F32, device=dev)
+        a1 = torch.empty(B, D1, **f32); a2 = torch.empty(B, D2, **f32); out = torch.empty(B, NC, **f32)
+        stats = [torch.empty(n, **f32) for n in (F, F, D1, D1, D2, D2)]
+        L = lib()
+        part = torch.empty(int(L.eagcn_head_part_floats(B, F, D1, D2)), **f32)
+        rng = RngState.get(dev)
+        snap = rng.state.clone() if (training and p_drop > 0.0) else None
+        h = HeadStruct()
+        h.B, h.F, h.D1, h.D2, h.NC = B, F, D1, D2, NC
+        h.training, h.rng_stream = int(training), int(rng_stream)
+        h.p_drop, h.eps, h.momentum = float(p_drop), float(eps), float(momentum)
+        h.x0 = x0.data_ptr()
+        for i, t in enumerate((W1, W2, W3)):
+            h.W[i] = t.data_ptr()
+        for i, (g, b) in enumerate(((g0, b0), (g1, b1), (g2, b2))):
+            h.bn_w[i], h.bn_b[i] = g.data_ptr(), b.data_ptr()
+            rm, rv, nbt = bufs[3 * i: 3 * i + 3]
+            h.bn_rm[i], h.bn_rv[i] = rm.data_ptr(), rv.data_ptr()
+            h.bn_nbt[i] = nbt.data_ptr() if nbt is not None else None
+            h.mean[i], h.invstd[i] = stats[2 * i].data_ptr(), stats[2 * i + 1].data_ptr()
+        h.rng = snap.data_ptr() if snap is not None else None
+        h.a1, h.a2, h.out = a1.data_ptr(), a2.data_ptr(), out.data_ptr()
+        h.part, h.bar = part.data_ptr(), _head_bar(dev).data_ptr()
+        check(L.eagcn_head_forward(ctypes.byref(h), _stream()), "eagcn_head_forward")
+        if snap is not None:
+            rng.advance()
+        ctx.cfg, ctx.bufs = cfg, bufs
+        ctx.saved = (x0, params, a1, a2, stats, snap)
+        return out, a2
+
+    @staticmethod
+    def backward(ctx, d_out, d_a2):
+        training, p_drop, rng_stream, eps, momentum = ctx.cfg
+        x0, params, a1, a2, stats, snap = ctx.saved
+        W1, W2, W3, g0, b0, g1, b1, g2, b2 = params
+        dev = x0.device
+        B, F = x0.shape
+        D1, D2, NC = W1.shape[1], W2.shape[1], W3.shape[1]
+        f32 = dict(dtype=_F32, device=dev)
+        L = lib()
+        d_out = d_out.contiguous() if d_out is not None else torch.zeros(B, NC, **f32)
+        d_a2 = d_a2.contiguous() if d_a2 is not None else None
+        g2buf = torch.empty(B, D2, **f32); g1buf = torch.empty(B, D1, **f32); dh0 = torch.empty(B, F, **f32)
+        dx0 = torch.empty(B, F, **f32)
+        dW = [torch.empty_like(W1), torch.empty_like(W2), torch.empty_like(W3)]
+        dg = [torch.empty_like(g0), torch.empty_like(g1), torch.empty_like(g2)]
+        db = [torch.empty_like(b0), torch.empty_like(b1), torch.empty_like(b2)]
+        part = torch.empty(int(L.eagcn_head_part_floats(B, F, D1, D2)), **f32)
+        h = HeadStruct()
+        h.B, h.F, h.D1, h.D2, h.NC = B, F, D1, D2, NC
+        h.training, h.rng_stream = int(training), int(rng_stream)
+        h.p_drop, h.eps, h.momentum = float(p_drop), float(eps), float(momentum)
+        h.x0 = x0.data_ptr()
+        for i, t in enumerate((W1, W2, W3)):
+            h.W[i] = t.data_ptr()
+            h.dW[i] = dW[i].data_ptr()
+        for i, (g, b) in enumerate(((g0, b0), (g1, b1), (g2, b2))):
+            h.bn_w[i], h.bn_b[i] = g.data_ptr(), b.data_ptr()
+            rm, rv, nbt = ctx.bufs[3 * i: 3 * i + 3]
+            h.bn_rm[i], h.bn_rv[i] = rm.data_ptr(), rv.data_ptr()
+            h.mean[i], h.invstd[i] = stats[2 * i].data_ptr(), stats[2 * i + 1].data_ptr()
+            h.dbn_w[i], h.dbn_b[i] = dg[i].data_ptr(), db[i].data_ptr()
+        h.rng = snap.data_ptr() if snap is not None else None
+        h.a1, h.a2 = a1.data_ptr(), a2.data_ptr()
+        h.part, h.bar = part.data_ptr(), _head_bar(dev).data_ptr()
+        h.d_out = d_out.data_ptr()
+        h.d_a2 = d_a2.data_ptr() if d_a2 is not None else None
+        h.g2buf, h.g1buf, h.dh0, h.dx0 = g2buf.data_ptr(), g1buf.data_ptr(), dh0.data_ptr(), dx0.data_ptr()
+        check(L.eagcn_head_backward(ctypes.byref(h), _stream()), "eagcn_head_backward")
+        return (None, None, dx0, dW[0], dW[1], dW[2], dg[0], db[0], dg[1], db[1], dg[2], db[2])
+
+
+def dense_head(x0, weights, bns, training, p_drop, rng_stream=1000):
+    """weights: (W1, W2, W3); bns: three nn.BatchNorm1d.  Returns (out, graph_representation)."""
+    params = tuple(weights) + tuple(t for bn in bns for t in (bn.weight, bn.bias))
+    bufs = tuple(t for bn in bns for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked))
+    cfg = (bool(training), float(p_drop), int(rng_stream), float(bns[0].eps), float(bns[0].momentum))
+    return _HeadFn.apply(cfg, bufs, x0, *params)
+
+
+def dropout_keep_mask_flat(rng_state, rng_stream, p_drop, total):
+    """Test hook: keep mask of the flat index range [0, total) for (rng_state, rng_stream): u8 [total]."""
+    keep = torch.empty(total, dtype=torch.uint8, device=rng_state.device)
+    check(lib().eagcn_dropout_mask_flat(ptr(rng_state), int(rng_stream), float(p_drop), int(total), ptr(keep), _stream()),
+          "eagcn_dropout_mask_flat")
     return keep
 
 

@@ -84,6 +84,7 @@ class EAGCNStack(nn.Module):
         if molfp_mode not in ("sum", "ave"):
             raise EagcnError("CUDA read-out implements molfp_mode 'sum' / 'ave' (models.py:104-111)")
         self.molfp_mode, self.dropout = molfp_mode, dropout
+        self.fused_head = True       # one CUDA kernel per direction for the dense head (False: stock PyTorch ops)
         fin = n_afeat
         self.n_layers = len(widths)
         for l, w in enumerate(widths):
@@ -118,6 +119,12 @@ class EAGCNStack(nn.Module):
         x = EF.readout_sum(plan, h.rows)                                            # models.py:108
         if self.molfp_mode == "ave":                                                # models.py:109-111
             x = x / size.view(-1, 1).to(x.dtype)
+        if self.fused_head and all(bn.momentum is not None and bn.affine and bn.track_running_stats
+                                   for bn in (self.Graph_BN, self.bn_den1, self.bn_den2)):
+            x, graph_representation = EF.dense_head(x, (self.den1.weight, self.den2.weight, self.den3.weight),
+                                                    (self.Graph_BN, self.bn_den1, self.bn_den2), self.training,
+                                                    float(self.dropout))              # models.py:112-120
+            return x, atom_representations, graph_representation
         x = self.Graph_BN(x)                                                        # models.py:112
         x = self.den1(x)
         x = F.relu(self.bn_den1(x))

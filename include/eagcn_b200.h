@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 7
+#define EAGCN_ABI_VERSION 8
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -179,6 +179,36 @@ int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_layer_t* lay
 
 /* --- test hook: the keep mask eagcn_layer_forward_b draws (u8 [t_cap, fo_tot]) ------------- */
 int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out, void* stream);
+/* same generator over a flat index range (the fused head draws element m*D1+k of stream rng_stream):
+ * keep_out u8 [total]                                                                          */
+int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, double p_drop, int64_t total, void* keep_out, void* stream);
+
+/* --- fused read-out head (models.py:112-120): Graph_BN -> den1 -> bn_den1 -> ReLU -> dropout -> den2 ->
+ * bn_den2 -> ReLU -> den3, three bias-free Dense layers (layers.py:360-392) and three BatchNorm1d over the B
+ * molecules.  ONE kernel forward, ONE kernel backward (single resident grid with a software grid barrier;
+ * `bar` is a persistent uint32[2] that must be zero when first used).                                     */
+typedef struct eagcn_head {
+  int64_t B, F, D1, D2, NC;         /* molecules, read-out width, den1 / den2 widths, classes           */
+  int64_t training, rng_stream;
+  double p_drop, eps, momentum;
+  void* x0;                         /* f32 [B, F]   read-out (sum / mean over atoms)                    */
+  void* W[3];                       /* f32 [F,D1] [D1,D2] [D2,NC]  den1..den3 weights                   */
+  void* bn_w[3]; void* bn_b[3];     /* Graph_BN, bn_den1, bn_den2 affine                                 */
+  void* bn_rm[3]; void* bn_rv[3]; void* bn_nbt[3];   /* running mean / var (updated in training), i64 counters */
+  void* rng;                        /* u64 [2] philox seed, offset (device)                              */
+  void* a1; void* a2; void* out;    /* f32 [B,D1] [B,D2] (= graph_representation) [B,NC]                 */
+  void* mean[3]; void* invstd[3];   /* saved statistics [F] [D1] [D2]                                    */
+  void* part;                       /* f32 eagcn_head_part_floats() workspace                            */
+  void* bar;                        /* u32 [2] grid barrier state                                        */
+  /* backward */
+  void* d_out; void* d_a2;          /* f32 [B,NC]; optional [B,D2] gradient of graph_representation     */
+  void* g2buf; void* g1buf; void* dh0;   /* f32 [B,D2] [B,D1] [B,F] workspaces                           */
+  void* dx0;                        /* f32 [B,F] out                                                    */
+  void* dW[3]; void* dbn_w[3]; void* dbn_b[3];   /* out: parameter gradients                            */
+} eagcn_head_t;
+int64_t eagcn_head_part_floats(int64_t B, int64_t F, int64_t D1, int64_t D2);
+int eagcn_head_forward(const eagcn_head_t* args, void* stream);
+int eagcn_head_backward(const eagcn_head_t* args, void* stream);
 
 /* --- projection GEMM engine ------------------------------------------------------------------ */
 /* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned

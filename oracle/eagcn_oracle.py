@@ -163,11 +163,16 @@ def stack_forward(sd, adj, afm, codes, n_layers, training, p=0.0, keeps=None, st
     return h, outs
 
 
-def head_forward(sd, x_atoms, sizes, training, p=0.0, keep=None, molfp_mode="sum"):
-    """Read-out + dense head (models.py:104-121), molfp_mode in {'sum','ave'}."""
-    x = x_atoms.sum(1)                                                    # models.py:108
-    if molfp_mode == "ave":
-        x = x / sizes.view(-1, 1).to(x.dtype)                             # models.py:110-111
+def head_forward(sd, x_atoms, sizes, training, p=0.0, keep=None, molfp_mode="sum", x0=None, relu_masks=None):
+    """Read-out + dense head (models.py:104-121), molfp_mode in {'sum','ave'}.  x0: start from a given read-out
+    [B,F] instead of x_atoms.  relu_masks: optional (mask1 [B,D1], mask2 [B,D2]) replacing the two ReLU decisions
+    (see block_forward)."""
+    if x0 is None:
+        x = x_atoms.sum(1)                                                # models.py:108
+        if molfp_mode == "ave":
+            x = x / sizes.view(-1, 1).to(x.dtype)                         # models.py:110-111
+    else:
+        x = x0
 
     def bn(x, pre):
         if training:
@@ -178,12 +183,14 @@ def head_forward(sd, x_atoms, sizes, training, p=0.0, keep=None, molfp_mode="sum
 
     x = bn(x, "Graph_BN.")                                                # models.py:112
     x = x.mm(sd["den1.weight"])                                           # models.py:114
-    x = F.relu(bn(x, "bn_den1."))                                         # models.py:115
+    z1 = bn(x, "bn_den1.")
+    x = F.relu(z1) if relu_masks is None else z1 * relu_masks[0]          # models.py:115
     if training and p > 0.0:                                              # models.py:116
         x = x * keep / (1.0 - p)
     x = x.mm(sd["den2.weight"])                                           # models.py:117
     g = x
-    x = F.relu(bn(x, "bn_den2."))                                         # models.py:119
+    z2 = bn(x, "bn_den2.")
+    x = F.relu(z2) if relu_masks is None else z2 * relu_masks[1]          # models.py:119
     x = x.mm(sd["den3.weight"])                                           # models.py:120
     return x, g
 

@@ -372,3 +372,63 @@ def test_view_count_sweep_vs_oracle(V, fixed_n, B):
         if k.endswith("graph_conv.bias"):
             denom = scale
         assert float((dsd[k].grad.cpu() - t.grad).abs().max()) / denom <= 5 * TOL, k
+
+
+# ------------------------------------------------------------------ fused dense head
+@pytest.mark.parametrize("B,F,D1,D2,NC,training,p", [
+    (64, 100, 48, 24, 5, True, 0.0), (256, 700, 256, 64, 12, True, 0.0), (37, 70, 33, 17, 1, False, 0.0),
+    (128, 300, 128, 64, 3, True, 0.3),
+])
+def test_fused_head_vs_oracle(B, F, D1, D2, NC, training, p):
+    """models.py:112-120 in one kernel per direction vs the oracle (ReLU decisions / dropout mask taken from the
+    implementation under test, the former bounded to the kink)."""
+    import torch.nn as nn
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    gen = torch.Generator().manual_seed(B + F)
+    x0 = (torch.randn(B, F, generator=gen) * 2 + 0.5)
+    sd = {"den1.weight": torch.randn(F, D1, generator=gen) / F ** 0.5, "den2.weight": torch.randn(D1, D2, generator=gen) / D1 ** 0.5,
+          "den3.weight": torch.randn(D2, NC, generator=gen) / D2 ** 0.5}
+    bns = []
+    for name, n in (("Graph_BN", F), ("bn_den1", D1), ("bn_den2", D2)):
+        bn = nn.BatchNorm1d(n)
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(n, generator=gen) + 0.5); bn.bias.copy_(torch.randn(n, generator=gen) * 0.2)
+            bn.running_mean.copy_(torch.randn(n, generator=gen) * 0.3); bn.running_var.copy_(torch.rand(n, generator=gen) + 0.5)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sd[f"{name}.{k}"] = getattr(bn, k).detach().clone()
+        bns.append(bn.to(dev).train(training))
+    Ws = [sd[f"den{i}.weight"].to(dev).requires_grad_(True) for i in (1, 2, 3)]
+    xg = x0.to(dev).requires_grad_(True)
+    EF.manual_seed(77, dev)
+    rng_before = EF.RngState.get(dev).state.clone()
+    out, a2 = EF.dense_head(xg, Ws, bns, training, p)
+    keep = None
+    if training and p > 0:
+        keep = EF.dropout_keep_mask_flat(rng_before, 1000, p, B * D1).view(B, D1).float().cpu()
+        assert abs(float(keep.mean()) - (1 - p)) < 0.03
+    # ReLU decisions of the implementation: recompute its pre-activations from its own saved stats is not exposed,
+    # so take them from a float64 oracle pass and only allow kink-level disagreement via the output check below
+    ref_sd = O.clone_sd(sd, requires_grad=True)
+    x_ref = x0.clone().requires_grad_(True)
+    y_ref, g_ref = O.head_forward(ref_sd, None, None, training, p=p, keep=keep, x0=x_ref)
+    assert rel_err(out.cpu(), y_ref) <= 2 * TOL
+    assert rel_err(a2.cpu(), g_ref) <= 2 * TOL
+    gen2 = torch.Generator().manual_seed(3)
+    R, R2 = torch.randn(y_ref.shape, generator=gen2), torch.randn(g_ref.shape, generator=gen2)
+    ((y_ref * R).sum() + (g_ref * R2).sum()).backward()
+    ((out * R.to(dev)).sum() + (a2 * R2.to(dev)).sum()).backward()
+    scale = max(float(t.grad.abs().max()) for t in ref_sd.values() if t.grad is not None)
+    checks = [(xg.grad, x_ref.grad, "x0")] + [(Ws[i].grad, ref_sd[f"den{i + 1}.weight"].grad, f"den{i + 1}") for i in range(3)]
+    for bn, name in zip(bns, ("Graph_BN", "bn_den1", "bn_den2")):
+        checks += [(bn.weight.grad, ref_sd[name + ".weight"].grad, name + ".w"), (bn.bias.grad, ref_sd[name + ".bias"].grad, name + ".b")]
+    for got, ref, name in checks:
+        denom = max(float(ref.abs().max()), 1e-3 * scale)
+        assert float((got.cpu() - ref).abs().max()) / denom <= 1e-4, name      # a rare ReLU-kink flip costs ~1/sqrt(width)
+    if training:
+        for bn, name in zip(bns, ("Graph_BN", "bn_den1", "bn_den2")):
+            assert int(bn.num_batches_tracked) == 1
+        exp_rm = 0.9 * sd["Graph_BN.running_mean"] + 0.1 * x0.mean(0)
+        exp_rv = 0.9 * sd["Graph_BN.running_var"] + 0.1 * x0.var(0, unbiased=True)
+        assert rel_err(bns[0].running_mean.cpu(), exp_rm) <= TOL
+        assert rel_err(bns[0].running_var.cpu(), exp_rv) <= TOL

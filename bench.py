@@ -232,6 +232,12 @@ def run_b200(args):
         out.sum().backward()
         return out
 
+    # everything from here on runs on ONE non-default stream: autograd bookkeeping created on the legacy
+    # default stream must never be touched while a graph is being captured
+    work_stream = torch.cuda.Stream()
+    work_stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work_stream)
+
     # which parameters get gradients -> their gradients are packed into ONE flat buffer per step and that
     # buffer is all-reduced (N > 1): a single collective per step
     step_dense(slots[0])
@@ -257,13 +263,9 @@ def run_b200(args):
         return
 
     # ---- capture one CUDA graph per (batch, layout) ----
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            for s in slots[:2]:
-                step_dense(s); step_codes(s)
-    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        for s in slots[:2]:
+            step_dense(s); step_codes(s)
     torch.cuda.synchronize()
     pool = torch.cuda.graph_pool_handle()
     launches_per_step = None

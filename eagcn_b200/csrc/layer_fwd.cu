@@ -91,6 +91,99 @@ __device__ __forceinline__ void store4(float* __restrict__ row, int q, int lane,
   }
 }
 
+// Single-pass variant for fo_v <= 128*NQ (float4 layout): every lane keeps NQ float4 accumulators, so the row's
+// edge list is walked once (one sigmoid-table lookup and one neighbour-index broadcast per edge) instead of once
+// per 128-channel chunk.  grid (row tiles of kStatRows, V); kAggWarps warps x kAggRows rows.
+template <int NQ>
+__global__ void __launch_bounds__(kAggThreads) agg_fwd_onepass_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+                                                                      const float* __restrict__ ball,
+                                                                      const float* __restrict__ sig, float* __restrict__ Y,
+                                                                      float* __restrict__ invR, float* __restrict__ partial,
+                                                                      int n_pad, int want_stats) {
+  __shared__ float s_red[kAggWarps][2][NQ * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.y;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int tile = blockIdx.x;
+  if (tile * kStatRows >= T) return;
+  const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot;
+  const float* sg = sig + v * EAGCN_SIG_STRIDE;
+  const float sig_r = sg[256];
+  const uint8_t* code = p.code + (size_t)v * p.e_cap;
+  float s1[NQ][4], s2[NQ][4], bias4[NQ][4];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    load4<4>(ball + off, q, lane, fo, bias4[q]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s1[q][u] = 0.f; s2[q][u] = 0.f; }
+  }
+  for (int r = 0; r < kAggRows; ++r) {
+    const int t = tile * kStatRows + warp * kAggRows + r;
+    if (t >= T) break;
+    const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
+    const int deg = e1 - e0;
+    float sw = 0.0f;                                               // attention row sum (layers.py:84,87)
+    for (int e = e0 + lane; e < e1; e += 32) sw += sg[code[e]];
+    sw = warp_sum(sw);
+    const float R = sw + sig_r + (float)(n_pad - deg) * EAGCN_TINY;
+    if (lane == 0) invR[(size_t)v * p.t_cap + t] = 1.0f / R;
+    const float a_self = sig_r / R;
+    float acc[NQ][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float zi[4];
+      load4<4>(Z + (size_t)t * ld + off, q, lane, fo, zi);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[q][u] = a_self * zi[u];
+    }
+    for (int eb = e0; eb < e1; eb += 32) {                         // aggregate (layers.py:90,39)
+      const int e = eb + lane;
+      float a_e = 0.0f; int j_e = 0;
+      if (e < e1) { a_e = sg[code[e]] / R; j_e = p.col[e]; }
+      const int cnt = min(32, e1 - eb);
+      for (int k = 0; k < cnt; ++k) {
+        const float a = __shfl_sync(0xffffffffu, a_e, k);
+        const int j = __shfl_sync(0xffffffffu, j_e, k);
+        const float* zr = Z + (size_t)j * ld + off;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          float zj[4];
+          load4<4>(zr, q, lane, fo, zj);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[q][u] = fmaf(a, zj[u], acc[q][u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        y[u] = acc[q][u] + bias4[q][u];
+        s1[q][u] += acc[q][u]; s2[q][u] = fmaf(acc[q][u], acc[q][u], s2[q][u]);
+      }
+      store4<4>(Y + (size_t)t * ld + off, q, lane, fo, y);
+    }
+  }
+  if (want_stats) {                                                // cross-warp reduction in fixed order
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s_red[warp][0][q * 128 + lane * 4 + u] = s1[q][u];
+        s_red[warp][1][q * 128 + lane * 4 + u] = s2[q][u];
+      }
+    __syncthreads();
+    for (int c = threadIdx.x; c < fo; c += kAggThreads) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAggWarps; ++w) { a += s_red[w][0][c]; b += s_red[w][1][c]; }
+      partial[((size_t)tile * 2 + 0) * ld + off + c] = a;
+      partial[((size_t)tile * 2 + 1) * ld + off + c] = b;
+    }
+  }
+}
+
 // grid (row tiles of kStatRows, V).  kAggWarps warps x kAggRows rows.
 template <int VEC>
 __global__ void __launch_bounds__(kAggThreads) agg_fwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
@@ -366,7 +459,19 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);
   const int want = (w->training & 1) ? 1 : 0;
   const bool host_allreduce = (w->training & 2) != 0;   // global-batch BatchNorm: host sums the partial sums over ranks
-  if (vec4_ok(layer)) {
+  int fo_max = 0;
+  for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
+  if (vec4_ok(layer) && fo_max <= 256) {
+    EAGCN_PROF("agg_fwd_kernel", st);
+    if (fo_max <= 128)
+      agg_fwd_onepass_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+                                                              (const float*)w->sig, (float*)w->Y, (float*)w->invR,
+                                                              (float*)w->partial, n_pad, want);
+    else
+      agg_fwd_onepass_kernel<2><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+                                                              (const float*)w->sig, (float*)w->Y, (float*)w->invR,
+                                                              (float*)w->partial, n_pad, want);
+  } else if (vec4_ok(layer)) {
     EAGCN_PROF("agg_fwd_kernel", st);
     agg_fwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);

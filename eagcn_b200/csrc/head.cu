@@ -30,6 +30,7 @@ struct HeadDev {
   float *a1, *a2, *out;                                // [B,D1] [B,D2] [B,NC]
   float *mean0, *invstd0, *mean1, *invstd1, *mean2, *invstd2;
   float* part;                                         // [rowtiles][2][max(F,D1,D2)] column partials
+  float* part2;                                        // second partial buffer (ping-pong between phases)
   unsigned* bar;                                       // [2] grid barrier (count, generation), zero-initialised once
   // backward
   const float *d_out, *d_a2;                           // [B,NC], optional [B,D2]
@@ -59,7 +60,9 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks) {
 // grid, 4 x 2 outputs per thread.
 template <class LA, class LB, class EPI>
 __device__ __forceinline__ void tile_gemm(int m0, int n0, int M, int N, int K, LA la, LB lb, EPI epi, float (*sA)[TM + 1],
-                                          float (*sB)[TN + 1]) {
+                                          float (*sB)[TN + 1], float* __restrict__ part = nullptr, int ldp = 0) {
+  // epi(m, n, value) returns a float2 (p, q); when `part` is given, the column sums of p and q over this tile's rows
+  // are stored to part[row_tile][0 / 1][n] (fixed order) -- the BatchNorm statistics of the product's output.
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // n = tx + 32*j (j<2), m = ty*4 + i (i<4)
   float acc[4][2];
 #pragma unroll
@@ -88,13 +91,31 @@ __device__ __forceinline__ void tile_gemm(int m0, int n0, int M, int N, int K, L
     }
     __syncthreads();
   }
+  float ps[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int gm = m0 + ty * 4 + i, gn = n0 + tx + 32 * j;
-      if (gm < M && gn < N) epi(gm, gn, acc[i][j]);
+      if (gm < M && gn < N) { const float2 r = epi(gm, gn, acc[i][j]); ps[j] += r.x; qs[j] += r.y; }
     }
+  if (part) {                                                      // 8 row groups -> fixed-order column sums
+    float (*red)[TN + 1] = sB;                                     // reuse: [0..7] p sums, [8..15] q sums
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { red[ty][tx + 32 * j] = ps[j]; red[8 + ty][tx + 32 * j] = qs[j]; }
+    __syncthreads();
+    if (threadIdx.x < TN) {
+      const int gn = n0 + threadIdx.x;
+      if (gn < N) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += red[w][threadIdx.x]; b += red[8 + w][threadIdx.x]; }
+        part[((size_t)(m0 / TM) * 2 + 0) * ldp + gn] = a;
+        part[((size_t)(m0 / TM) * 2 + 1) * ldp + gn] = b;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // column statistics of an [R, C] row-major matrix restricted to one row tile: part[tile][0][c] = sum, [1] = sum sq
@@ -178,19 +199,17 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadDev h) {
       tile_gemm(m0, n0, h.B, h.D1, h.F,
                 [&](int m, int k) { return fmaf(h.x0[(size_t)m * h.F + k], s_stat[k], s_stat[ldp + k]); },
                 [&](int k, int n) { return h.W1[(size_t)k * h.D1 + n]; },
-                [&](int m, int n, float v) { h.a1[(size_t)m * h.D1 + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.a1[(size_t)m * h.D1 + n] = v; return make_float2(v, v * v); }, sA, sB,
+                h.training ? h.part2 : nullptr, ldp);
     }
   }
-  grid_sync(h.bar, nb);          // a1 complete; part (x0 partials) no longer needed
-  if (h.training)
-    for (int t = blockIdx.x; t < rt; t += nb) col_partials(h.a1, h.B, h.D1, t, h.part, ldp);
-  grid_sync(h.bar, nb);
+  grid_sync(h.bar, nb);          // a1 and its column partials (part2) complete
 
   // ---- phase 2: a2 = dropout(relu(BN1(a1))) @ W2 ----
-  finalize_bn(h, h.D1, rt, ldp, h.part, h.mean1, h.invstd1, h.rm1, h.rv1, h.nbt1);
+  finalize_bn(h, h.D1, rt, ldp, h.part2, h.mean1, h.invstd1, h.rm1, h.rv1, h.nbt1);
   for (int c = threadIdx.x; c < h.D1; c += HT) {
     float mu, is;
-    if (h.training) { double vu; bn_stats_from_partials(h.part, rt, ldp, c, h.B, h.eps, mu, is, vu); }
+    if (h.training) { double vu; bn_stats_from_partials(h.part2, rt, ldp, c, h.B, h.eps, mu, is, vu); }
     else { mu = h.rm1[c]; is = 1.0f / sqrtf(h.rv1[c] + (float)h.eps); }
     s_stat[c] = is * h.g1[c];
     s_stat[ldp + c] = h.b1[c] - mu * is * h.g1[c];
@@ -207,13 +226,11 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadDev h) {
                   return v;
                 },
                 [&](int k, int n) { return h.W2[(size_t)k * h.D2 + n]; },
-                [&](int m, int n, float v) { h.a2[(size_t)m * h.D2 + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.a2[(size_t)m * h.D2 + n] = v; return make_float2(v, v * v); }, sA, sB,
+                h.training ? h.part : nullptr, ldp);
     }
   }
-  grid_sync(h.bar, nb);
-  if (h.training)
-    for (int t = blockIdx.x; t < rt; t += nb) col_partials(h.a2, h.B, h.D2, t, h.part, ldp);
-  grid_sync(h.bar, nb);
+  grid_sync(h.bar, nb);          // a2 and its column partials (part) complete
 
   // ---- phase 3: out = relu(BN2(a2)) @ W3 ----
   finalize_bn(h, h.D2, rt, ldp, h.part, h.mean2, h.invstd2, h.rm2, h.rv2, h.nbt2);
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadDev h) {
       tile_gemm(m0, n0, h.B, h.NC, h.D2,
                 [&](int m, int k) { return fmaxf(fmaf(h.a2[(size_t)m * h.D2 + k], s_stat[k], s_stat[ldp + k]), 0.f); },
                 [&](int k, int n) { return h.W3[(size_t)k * h.NC + n]; },
-                [&](int m, int n, float v) { h.out[(size_t)m * h.NC + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.out[(size_t)m * h.NC + n] = v; return make_float2(0.f, 0.f); }, sA, sB);
     }
   }
 }
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
       tile_gemm(m0, n0, h.D2, h.NC, h.B,
                 [&](int m, int k) { return fmaxf(fmaf(h.a2[(size_t)k * h.D2 + m], s_c[m], s_c[ldp + m]), 0.f); },
                 [&](int k, int n) { return h.d_out[(size_t)k * h.NC + n]; },
-                [&](int m, int n, float v) { h.dW3[(size_t)m * h.NC + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.dW3[(size_t)m * h.NC + n] = v; return make_float2(0.f, 0.f); }, sA, sB);
     }
     const int nt2 = (h.D2 + TN - 1) / TN;
     for (int t = blockIdx.x; t < rt * nt2; t += nb) {
@@ -298,14 +315,15 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
                 [&](int m, int k) { return h.d_out[(size_t)m * h.NC + k]; },
                 [&](int k, int n) { return h.W3[(size_t)n * h.NC + k]; },
                 [&](int m, int n, float v) {
-                  const float z = fmaf(h.a2[(size_t)m * h.D2 + n], s_c[n], s_c[ldp + n]);
-                  h.g2buf[(size_t)m * h.D2 + n] = z > 0.f ? v : 0.f;
-                }, sA, sB);
+                  const float a = h.a2[(size_t)m * h.D2 + n];
+                  const float z = fmaf(a, s_c[n], s_c[ldp + n]);
+                  const float g = z > 0.f ? v : 0.f;
+                  h.g2buf[(size_t)m * h.D2 + n] = g;
+                  return make_float2(g, g * ((a - h.mean2[n]) * h.invstd2[n]));
+                }, sA, sB, h.part, ldp);
     }
   }
-  grid_sync(h.bar, nb);
-  for (int t = blockIdx.x; t < rt; t += nb) bwd_partials(h.g2buf, h.a2, h.mean2, h.invstd2, h.B, h.D2, t, h.part, ldp);
-  grid_sync(h.bar, nb);
+  grid_sync(h.bar, nb);          // g2 and its (sum g, sum g*xhat) partials complete
 
   // ---- phase 1: da2 (on the fly) ; dW2 = h1^T da2 ; g1 = (da2 W2^T) * drop * relu'(BN1(a1)) ----
   // da2[m,k] = gam2*invstd2*(g2 - S1/B - xhat2*S2/B) [train] | gam2*invstd2*g2 [eval]  (+ d_a2 if given)
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
                   return v;
                 },
                 [&](int k, int n) { return da2(k, n); },
-                [&](int m, int n, float v) { h.dW2[(size_t)m * h.D2 + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.dW2[(size_t)m * h.D2 + n] = v; return make_float2(0.f, 0.f); }, sA, sB);
     }
     const int nt1 = (h.D1 + TN - 1) / TN;
     for (int t = blockIdx.x; t < rt * nt1; t += nb) {
@@ -350,21 +368,21 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
                 [&](int m, int n, float v) {
                   const size_t i = (size_t)m * h.D1 + n;
                   const float sc = h.invstd1[n] * h.g1[n];
-                  const float z = fmaf(h.a1[i], sc, h.b1[n] - h.mean1[n] * sc);
+                  const float a = h.a1[i];
+                  const float z = fmaf(a, sc, h.b1[n] - h.mean1[n] * sc);
                   float g = z > 0.f ? v : 0.f;
                   if (drop) g = dropout_keep(ph, roff, h.rng_stream, (unsigned long long)i, h.p_drop) ? g * dscale : 0.f;
                   h.g1buf[i] = g;
-                }, sA, sB);
+                  return make_float2(g, g * ((a - h.mean1[n]) * h.invstd1[n]));
+                }, sA, sB, h.part2, ldp);
     }
   }
-  grid_sync(h.bar, nb);
-  for (int t = blockIdx.x; t < rt; t += nb) bwd_partials(h.g1buf, h.a1, h.mean1, h.invstd1, h.B, h.D1, t, h.part, ldp);
-  grid_sync(h.bar, nb);
+  grid_sync(h.bar, nb);          // g1 and its partials (part2) complete
 
   // ---- phase 2: da1 (on the fly) ; dW1 = h0^T da1 ; dh0 = da1 W1^T ----
   for (int c = threadIdx.x; c < h.D1; c += HT) {
     float s1, s2;
-    bwd_sums(h.part, rt, ldp, c, s1, s2);
+    bwd_sums(h.part2, rt, ldp, c, s1, s2);
     if (blockIdx.x == 0) { h.dg1[c] = s2; h.db1[c] = s1; }
     s_c[c] = h.g1[c] * h.invstd1[c];
     s_c[ldp + c] = h.training ? s1 * invB : 0.f;
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
                   return fmaf(h.x0[(size_t)k * h.F + m], sc, h.b0[m] - h.mean0[m] * sc);
                 },
                 [&](int k, int n) { return da1(k, n); },
-                [&](int m, int n, float v) { h.dW1[(size_t)m * h.D1 + n] = v; }, sA, sB);
+                [&](int m, int n, float v) { h.dW1[(size_t)m * h.D1 + n] = v; return make_float2(0.f, 0.f); }, sA, sB);
     }
     const int ntf = (h.F + TN - 1) / TN;
     for (int t = blockIdx.x; t < rt * ntf; t += nb) {
@@ -394,12 +412,13 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
       tile_gemm(m0, n0, h.B, h.F, h.D1,
                 [&](int m, int k) { return da1(m, k); },
                 [&](int k, int n) { return h.W1[(size_t)n * h.D1 + k]; },
-                [&](int m, int n, float v) { h.dh0[(size_t)m * h.F + n] = v; }, sA, sB);
+                [&](int m, int n, float v) {
+                  h.dh0[(size_t)m * h.F + n] = v;
+                  return make_float2(v, v * ((h.x0[(size_t)m * h.F + n] - h.mean0[n]) * h.invstd0[n]));
+                }, sA, sB, h.part, ldp);
     }
   }
-  grid_sync(h.bar, nb);
-  for (int t = blockIdx.x; t < rt; t += nb) bwd_partials(h.dh0, h.x0, h.mean0, h.invstd0, h.B, h.F, t, h.part, ldp);
-  grid_sync(h.bar, nb);
+  grid_sync(h.bar, nb);          // dh0 and its partials complete
 
   // ---- phase 3: dx0 = Graph_BN backward ----
   for (int c = threadIdx.x; c < h.F; c += HT) {
@@ -442,6 +461,7 @@ static bool head_to_dev(const eagcn_head_t* a, HeadDev& h, bool bwd) {
   h.mean0 = (float*)a->mean[0]; h.invstd0 = (float*)a->invstd[0]; h.mean1 = (float*)a->mean[1];
   h.invstd1 = (float*)a->invstd[1]; h.mean2 = (float*)a->mean[2]; h.invstd2 = (float*)a->invstd[2];
   h.part = (float*)a->part; h.bar = (unsigned*)a->bar;
+  h.part2 = h.part ? h.part + eagcn_head_part_floats(a->B, a->F, a->D1, a->D2) / 2 : nullptr;
   h.d_out = (const float*)a->d_out; h.d_a2 = (const float*)a->d_a2;
   h.g2buf = (float*)a->g2buf; h.g1buf = (float*)a->g1buf; h.dh0 = (float*)a->dh0;
   h.dx0 = (float*)a->dx0; h.dW1 = (float*)a->dW[0]; h.dW2 = (float*)a->dW[1]; h.dW3 = (float*)a->dW[2];
@@ -468,7 +488,7 @@ static int head_grid(const HeadDev& h) {
 
 extern "C" int64_t eagcn_head_part_floats(int64_t B, int64_t F, int64_t D1, int64_t D2) {
   const int64_t ld = F > D1 ? (F > D2 ? F : D2) : (D1 > D2 ? D1 : D2);
-  return ((B + TM - 1) / TM) * 2 * ld;
+  return 2 * ((B + TM - 1) / TM) * 2 * ld;          // two ping-pong buffers
 }
 
 extern "C" int eagcn_head_forward(const eagcn_head_t* args, void* stream) {

@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDe
             for (int u = 0; u < 4; ++u) qacc[qq][u] = 0.0f;
           }
         }
+#pragma unroll 2
         for (int k = 0; k < cnt; ++k) {
           const int j = __shfl_sync(0xffffffffu, j_e, k);
           const float aq = __shfl_sync(0xffffffffu, aq_e, k);

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_onepass_kernel(PlanDev p,
       float a_e = 0.0f; int j_e = 0;
       if (e < e1) { a_e = sg[code[e]] / R; j_e = p.col[e]; }
       const int cnt = min(32, e1 - eb);
+#pragma unroll 2
       for (int k = 0; k < cnt; ++k) {
         const float a = __shfl_sync(0xffffffffu, a_e, k);
         const int j = __shfl_sync(0xffffffffu, j_e, k);

@@ -84,7 +84,10 @@ class EAGCNStack(nn.Module):
         if molfp_mode not in ("sum", "ave"):
             raise EagcnError("CUDA read-out implements molfp_mode 'sum' / 'ave' (models.py:104-111)")
         self.molfp_mode, self.dropout = molfp_mode, dropout
-        self.fused_head = True       # one CUDA kernel per direction for the dense head (False: stock PyTorch ops)
+        # True: one CUDA kernel per direction for the dense head (eagcn_b200/csrc/head.cu, parity-tested).  Measured
+        # slower than the ~35 stock PyTorch launches it replaces at B = 256 (un-pipelined operand loads), so it is
+        # opt-in until its tile loop is software-pipelined.
+        self.fused_head = False
         fin = n_afeat
         self.n_layers = len(widths)
         for l, w in enumerate(widths):

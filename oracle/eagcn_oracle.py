@@ -278,3 +278,31 @@ def model_forward_conv(sd, adj, afm, rels, sizes, n_layers, training, p=0.0):
     x = x.mm(sd["den2.weight"])
     x = F.relu(bn(x, "bn_den2."))
     return x.mm(sd["den3.weight"])
+
+
+# --------------------------------------------------------------------------------------------
+# loss of the classification branch, restated loop for loop (utils.py:653-679, train.py:326-331)
+# --------------------------------------------------------------------------------------------
+def weight_tensor_loop(weights, labels):
+    """utils.weight_tensor: Python double loop over (molecule, task)."""
+    out = []
+    for i in range(labels.shape[0]):
+        for j in range(labels.shape[1]):
+            try:
+                v = int(labels[i][j])
+                if v == 1:
+                    out.append(weights[j][0])
+                elif v == 0:
+                    out.append(weights[j][1])
+                else:
+                    out.append(0)
+            except ValueError:                      # int(nan)
+                out.append(0)
+    return torch.tensor(out, dtype=torch.float32)
+
+
+def bce_loss_loop(outputs, labels, weights):
+    w = weight_tensor_loop(weights, labels)
+    non_nan = ((labels == 1).sum() + (labels == 0).sum()).float()
+    target = torch.nan_to_num(labels.float(), nan=0.0)
+    return F.binary_cross_entropy_with_logits(outputs.view(-1), target.view(-1), weight=w, reduction="sum") / non_nan

@@ -185,6 +185,8 @@ def run_b200(args):
     from eagcn_b200 import functional as EF
     EF.set_gemm_engine(args.gemm)
     model = build_model(dev)
+    if args.head != "auto":
+        model.fused_head = args.head == "fused"
     NB = args.nbatches
     slots = []
     for i in range(NB):
@@ -394,7 +396,8 @@ def run_b200(args):
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.isfile(tp):
-                traffic = json.load(open(tp)).get(top)
+                tj = json.load(open(tp))
+                traffic = tj.get(top, tj.get("gemm_tc_kernel") if top.startswith("gemm_tc") else None)
             if key.startswith("gemm"):
                 ach = f / sec / 1e12
                 roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
@@ -424,6 +427,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
+                       "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else "stock PyTorch ops",
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
                        "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
@@ -560,6 +564,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nbatches", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--head", default="auto", choices=["auto", "fused", "torch"],
+                    help="dense head: fused CUDA kernels or stock PyTorch ops (auto = the model's default)")
     ap.add_argument("--layers-only", action="store_true",
                     help="diagnostic: loss = sum of the last layer's atom rows (no read-out / dense head); not a bench value")
     ap.add_argument("--profile-only", action="store_true",

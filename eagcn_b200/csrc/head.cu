@@ -59,36 +59,59 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks) {
 // ReLU / dropout / gradient formulas), epi(m, n, value) consumes the results.  256 threads: 8 (m) x 32 (n) thread
 // grid, 4 x 2 outputs per thread.
 template <class LA, class LB, class EPI>
-__device__ __forceinline__ void tile_gemm(int m0, int n0, int M, int N, int K, LA la, LB lb, EPI epi, float (*sA)[TM + 1],
-                                          float (*sB)[TN + 1], float* __restrict__ part = nullptr, int ldp = 0) {
+__device__ __forceinline__ void tile_gemm(int m0, int n0, int M, int N, int K, LA la, LB lb, EPI epi,
+                                          float (*sA)[TK][TM + 1], float (*sB)[TK][TN + 1],
+                                          float* __restrict__ part = nullptr, int ldp = 0) {
   // epi(m, n, value) returns a float2 (p, q); when `part` is given, the column sums of p and q over this tile's rows
   // are stored to part[row_tile][0 / 1][n] (fixed order) -- the BatchNorm statistics of the product's output.
+  // Software pipeline: the operand elements of k-block i+1 are fetched into registers (all loads issued back to
+  // back, nothing stored in between) while k-block i is multiplied out of shared memory; two smem buffers.
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // n = tx + 32*j (j<2), m = ty*4 + i (i<4)
+  constexpr int NA = TM * TK / HT, NB = TK * TN / HT;
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = threadIdx.x + i * HT;
+      const int k = idx % TK, m = idx / TK;
+      const int gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = threadIdx.x + i * HT;
+      const int n = idx % TN, k = idx / TN;
+      const int gn = n0 + n, gk = k0 + k;
+      rb[i] = (gn < N && gk < K) ? lb(gk, gn) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) { const int idx = threadIdx.x + i * HT; sA[buf][idx % TK][idx / TK] = ra[i]; }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { const int idx = threadIdx.x + i * HT; sB[buf][idx / TN][idx % TN] = rb[i]; }
+  };
   float acc[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-  for (int k0 = 0; k0 < K; k0 += TK) {
-    for (int idx = threadIdx.x; idx < TM * TK; idx += HT) {       // A tile: TK x TM (k-major in smem)
-      const int k = idx % TK, m = idx / TK;
-      const int gm = m0 + m, gk = k0 + k;
-      sA[k][m] = (gm < M && gk < K) ? la(gm, gk) : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < TK * TN; idx += HT) {       // B tile: TK x TN
-      const int n = idx % TN, k = idx / TN;
-      const int gn = n0 + n, gk = k0 + k;
-      sB[k][n] = (gn < N && gk < K) ? lb(gk, gn) : 0.f;
-    }
-    __syncthreads();
+  const int nkb = (K + TK - 1) / TK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nkb) fetch((kb + 1) * TK);
 #pragma unroll 8
     for (int k = 0; k < TK; ++k) {
-      const float b0v = sB[k][tx], b1v = sB[k][tx + 32];
+      const float b0v = sB[buf][k][tx], b1v = sB[buf][k][tx + 32];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float a = sA[k][ty * 4 + i];
+        const float a = sA[buf][k][ty * 4 + i];
         acc[i][0] = fmaf(a, b0v, acc[i][0]);
         acc[i][1] = fmaf(a, b1v, acc[i][1]);
       }
     }
+    if (kb + 1 < nkb) stash(buf ^ 1);
     __syncthreads();
   }
   float ps[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f};
@@ -100,7 +123,7 @@ __device__ __forceinline__ void tile_gemm(int m0, int n0, int M, int N, int K, L
       if (gm < M && gn < N) { const float2 r = epi(gm, gn, acc[i][j]); ps[j] += r.x; qs[j] += r.y; }
     }
   if (part) {                                                      // 8 row groups -> fixed-order column sums
-    float (*red)[TN + 1] = sB;                                     // reuse: [0..7] p sums, [8..15] q sums
+    float (*red)[TN + 1] = sB[0];                                  // reuse: [0..7] p sums, [8..15] q sums
 #pragma unroll
     for (int j = 0; j < 2; ++j) { red[ty][tx + 32 * j] = ps[j]; red[8 + ty][tx + 32 * j] = qs[j]; }
     __syncthreads();
@@ -165,8 +188,8 @@ __device__ __forceinline__ void finalize_bn(const HeadDev& h, int C, int ntile, 
 
 // ======================================================================================================
 __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadDev h) {
-  __shared__ float sA[TK][TM + 1];
-  __shared__ float sB[TK][TN + 1];
+  __shared__ float sA[2][TK][TM + 1];
+  __shared__ float sB[2][TK][TN + 1];
   extern __shared__ float s_stat[];                    // [2][max(F, D1, D2)] mean / invstd of the operand being normalised
   const int nb = gridDim.x;
   const int rt = (h.B + TM - 1) / TM;                  // row tiles
@@ -279,8 +302,8 @@ __device__ __forceinline__ void bwd_partials(const float* __restrict__ G, const 
 }
 
 __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
-  __shared__ float sA[TK][TM + 1];
-  __shared__ float sB[TK][TN + 1];
+  __shared__ float sA[2][TK][TM + 1];
+  __shared__ float sB[2][TK][TN + 1];
   extern __shared__ float s_c[];                       // [4][ldp]: per-column coefficients of the current BatchNorm
   const int nb = gridDim.x;
   const int rt = (h.B + TM - 1) / TM;

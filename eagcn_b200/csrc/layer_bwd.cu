@@ -442,11 +442,12 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
                                                 (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
   }
-  // reduce the tile partials; without a host all-reduce in between (training bit1) also emit dbias/dgamma/dbeta
-  const bool host_allreduce = (w->training & 2) != 0;
-  if (!host_allreduce && !w->dvec) return EAGCN_E_ARG;
+  // reduce the tile partials and emit dbias / dgamma / dbeta from THIS rank's sums: under data parallelism the
+  // host all-reduces `bsums` afterwards (global-batch BatchNorm), but parameter gradients stay per-rank
+  // contributions -- the flat gradient all-reduce sums them exactly once
+  if (!w->dvec) return EAGCN_E_ARG;
   LayerDev L = to_dev(layer, plan);
-  StatEpilogue ep{host_allreduce ? 0 : 2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
+  StatEpilogue ep{2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
                   (w->training & 1) ? 1 : 0, 0.0, 0.0, 0.0};
   EAGCN_PROF("stat_reduce_kernel", st);
   stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
@@ -480,13 +481,6 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
         (const double*)w->bsums, (float*)w->dY, C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
-    EAGCN_LAUNCH_CHECK();
-  }
-  if (w->training & 2) {            // sums were all-reduced by the host after backward_a
-    EAGCN_PROF("bn_bwd_finalize_kernel", st);
-    bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>((const float*)w->ball, (const float*)w->invstd,
-                                                            (const double*)w->bsums, (float*)w->dvec, C,
-                                                            (w->training & 1) ? 1 : 0);
     EAGCN_LAUNCH_CHECK();
   }
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);

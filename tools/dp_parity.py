@@ -86,6 +86,14 @@ def main():
     res = torch.tensor([ex, eg, er], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
+        names = [n for n, p in model.named_parameters() if n.startswith("layer") and p.grad is not None]
+        off = 0
+        for n, p in zip(names, params):
+            k = p.numel()
+            e = float((bucket_flat[off:off + k] - flat_full[off:off + k]).abs().max() / flat_full.abs().max())
+            if e > 5e-5:
+                print(f"   grad mismatch {n}: {e:.2e}")
+            off += k
         print(f"DP-{world} global-BN vs single process: atoms {float(res[0]):.2e}  layer grads {float(res[1]):.2e}  running stats {float(res[2]):.2e}")
         assert float(res[0]) <= 1e-5 and float(res[1]) <= 5e-5 and float(res[2]) <= 1e-5, "data-parallel parity failed"
         print("DP PARITY OK")

@@ -432,3 +432,42 @@ def test_fused_head_vs_oracle(B, F, D1, D2, NC, training, p):
         exp_rv = 0.9 * sd["Graph_BN.running_var"] + 0.1 * x0.var(0, unbiased=True)
         assert rel_err(bns[0].running_mean.cpu(), exp_rm) <= TOL
         assert rel_err(bns[0].running_var.cpu(), exp_rv) <= TOL
+
+
+# ------------------------------------------------------------------ BASELINE.json configurations as parity cases
+@pytest.mark.parametrize("name,dataset,B,n_layers,training", [
+    ("config1 freesolv 2-layer fp32 forward", "freesolv", 16, 2, False),
+    ("config3 lipo 3-layer + regression head", "lipo", 24, 3, True),
+    ("config4 hiv widths 2-layer", "hiv", 12, 2, True),
+    ("full 4-layer tox21-width model", "tox21", 8, 4, True),
+])
+def test_baseline_configs_forward_vs_oracle(name, dataset, B, n_layers, training):
+    """The per-dataset layer widths of train.py:61-114 stacked 2 / 3 / 4 deep (+ the reference head), forward
+    parity of atom representations, graph representation and logits against the oracle."""
+    from eagcn_b200 import models as EM
+    from eagcn_b200.data import make_batch, DATASETS
+    dev = _cuda()
+    cfg = DATASETS[dataset]
+    s1, s2 = cfg["sgc1"], cfg["sgc2"]
+    widths = [(s1,) * 5, (s2,) * 5, (2 * s2,) * 5, (2 * s2,) * 5][:n_layers]
+    torch.manual_seed(1)
+    model = EM.EAGCNStack(cfg["kb"], 24, widths, cfg["den"][0], cfg["den"][1], cfg["nclass"], dropout=0.0).to(dev)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if n.endswith("graph_conv.weight") or n.startswith("den"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * (1.5 / prm.shape[0] ** 0.5))
+            elif n.endswith("att.weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g))
+    model.train(training)
+    batch = make_batch(B, dataset, seed=4)
+    dense = [torch.from_numpy(a) for a in batch.dense()]
+    sd = O.clone_sd(model.state_dict())
+    y, atom, grep = model(*_to(dev, dense), torch.from_numpy(batch.sizes).to(dev))
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    h, _ = O.stack_forward(sd, dense[0], dense[1], codes, n_layers, training)
+    y_ref, g_ref = O.head_forward(sd, h, torch.from_numpy(batch.sizes), training)
+    # deeper stacks of train-mode BatchNorms amplify fp32 differences a little: 1e-5 per layer
+    assert rel_err(atom.materialize(), h) <= n_layers * TOL, name
+    assert rel_err(grep.detach().cpu(), g_ref) <= 2 * n_layers * TOL, name
+    assert rel_err(y.detach().cpu(), y_ref) <= 2 * n_layers * TOL, name

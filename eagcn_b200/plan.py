@@ -86,7 +86,12 @@ class GraphPlan:
     # ------------------------------------------------------------------------------------
     @classmethod
     def build(cls, adj, rels, t_cap=None, e_cap=None):
-        """From the dense layout of the reference collate: adj [B,N,N] f32, rels: V x [B,C_v,N,N] f32."""
+        """From the dense layout of the reference collate: adj [B,N,N] f32, rels: V x [B,C_v,N,N] f32.
+
+        The relation tensors may also be PINNED HOST tensors (``tensor.pin_memory()``): the packer only reads them
+        at bonded pairs, so it gathers those ~E*sum(C_v) values straight out of page-locked host memory over PCIe
+        (zero-copy, unified addressing) instead of first copying the whole 4*(Kb+10)*N^2 bytes per molecule to the
+        device -- ~25x fewer bytes across the bus for a Tox21 batch.  ``adj`` must be on the device."""
         if not adj.is_cuda:
             raise _lib.EagcnError("eagcn_b200 is CUDA-only (no CPU fallback): adj is on %s" % adj.device)
         if adj.dim() != 3 or adj.shape[1] != adj.shape[2]:
@@ -94,8 +99,11 @@ class GraphPlan:
         B, N = adj.shape[0], adj.shape[1]
         rels = [r if r.dtype == torch.float32 else r.float() for r in rels]   # layers.py:82 '.float()'
         for r in rels:
-            if r.dim() != 4 or r.shape[0] != B or r.shape[2] != N or r.shape[3] != N or r.device != adj.device:
-                raise ValueError("relation tensors must be [B,C_v,N,N] on the adjacency's device")
+            on_dev = r.device == adj.device
+            zero_copy = r.device.type == "cpu" and r.is_pinned()
+            if r.dim() != 4 or r.shape[0] != B or r.shape[2] != N or r.shape[3] != N or not (on_dev or zero_copy):
+                raise ValueError("relation tensors must be [B,C_v,N,N] on the adjacency's device "
+                                 "(or pinned host tensors for the zero-copy gather)")
         adj = adj.contiguous() if adj.dtype == torch.float32 else adj.float().contiguous()
         rels = [r.contiguous() for r in rels]
         self = cls(B, N, [r.shape[1] for r in rels], adj.device)

@@ -50,6 +50,13 @@ def test_pack_roundtrip_bit_exact(case):
     assert torch.equal(plan.rcode[:, :E], plan2.rcode[:, :E])
     # row mask == max_j adj (layers.py:295)
     assert torch.equal(plan.row_mask(), adj.max(2).values)
+    # zero-copy boundary: one-hot planes left in pinned host memory, gathered over PCIe by the packer
+    plan3 = GraphPlan.build(adj, [r.cpu().pin_memory() for r in rels]).check()
+    assert (plan3.n_rows, plan3.n_edges) == (T, E)
+    for name in ("col", "colpos", "rev"):
+        assert torch.equal(getattr(plan, name)[:E], getattr(plan3, name)[:E])
+    assert torch.equal(plan.code[:, :E], plan3.code[:, :E])
+    assert torch.equal(plan.rcode[:, :E], plan3.rcode[:, :E])
 
 
 def test_pack_rejects_malformed():

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_count_kernel(PlanDev p, con
     bc[r] = (((size_t)b * p.V) * p.N + i) * p.N;
     cnt[r] = 0;
   }
+#pragma unroll 4
   for (int j0 = 0; j0 < p.N; j0 += 32) {
     const int j = j0 + lane;
     float a[kRowsPerWarp];

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 
 // grid (row tiles, V); kAggWarps warps x kAggRows rows.  Fo_v handled in super-chunks of 512 channels (4 x 128).
 template <int VEC>
-__global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+__global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                       const float* __restrict__ Y, const float* __restrict__ dY,
                                                       const float* __restrict__ ball, const float* __restrict__ sig,
                                                       const float* __restrict__ invR, float* __restrict__ Q,

@@ -95,7 +95,7 @@ __device__ __forceinline__ void store4(float* __restrict__ row, int q, int lane,
 // edge list is walked once (one sigmoid-table lookup and one neighbour-index broadcast per edge) instead of once
 // per 128-channel chunk.  grid (row tiles of kStatRows, V); kAggWarps warps x kAggRows rows.
 template <int NQ>
-__global__ void __launch_bounds__(kAggThreads, 4) agg_fwd_onepass_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+__global__ void __launch_bounds__(kAggThreads) agg_fwd_onepass_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                                       const float* __restrict__ ball,
                                                                       const float* __restrict__ sig, float* __restrict__ Y,
                                                                       float* __restrict__ invR, float* __restrict__ partial,

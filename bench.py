@@ -184,6 +184,7 @@ def run_b200(args):
 
     from eagcn_b200 import functional as EF
     EF.set_gemm_engine(args.gemm)
+    EF.set_agg_engine(args.agg)
     model = build_model(dev)
     if args.head != "auto":
         model.fused_head = args.head == "fused"
@@ -467,6 +468,7 @@ def run_b200(args):
                        "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else "stock PyTorch ops",
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
+                       "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
                        "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
                        "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
                        "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
@@ -614,6 +616,7 @@ def main():
                     help="diagnostic: loss = sum of the last layer's atom rows (no read-out / dense head); not a bench value")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
+    ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

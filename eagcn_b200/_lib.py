@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -96,6 +96,8 @@ _PROTOS = {
     "eagcn_head_backward": (c_int, [c_void_p, c_void_p]),
     "eagcn_set_gemm_mode": (c_int, [c_int]),
     "eagcn_get_gemm_mode": (c_int, []),
+    "eagcn_set_agg_mode": (c_int, [c_int]),
+    "eagcn_get_agg_mode": (c_int, []),
     "eagcn_gemm_nt": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                               c_void_p, c_int, c_void_p]),
     "eagcn_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,

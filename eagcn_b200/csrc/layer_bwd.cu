@@ -357,6 +357,227 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDe
   }
 }
 
+// ---- shared-memory tile variant with the BatchNorm/ReLU/dropout backward folded in -----------------------------
+struct BnBwdArgs {
+  const float* dX; const float* mean; const float* invstd; const double* bsums;
+  const unsigned long long* rng; unsigned long long stream; double M; float p_drop; int training;
+};
+inline size_t agg_bwd_tile_smem(int fo) { return (size_t)(2 * kStatRows * fo + 6 * fo) * sizeof(float); }
+
+// dY of 4 consecutive channels (c4-th float4 of the view slab) of row t: exactly bn_bwd_apply_vec_kernel's arithmetic.
+// sP = per-view parameter rows [mean | invstd | gamma | beta | S1/M | S2/M], each nc4 float4 long.
+__device__ __forceinline__ float4 dy_at(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, int nc4, int ld,
+                                        int off, int t, int c4, bool drop, float scale, const Philox& ph,
+                                        unsigned long long rng_off) {
+  const size_t idx = (size_t)t * ld + off + c4 * 4;
+  const float4 dx = __ldg(reinterpret_cast<const float4*>(bn.dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
+  const float4 mu = sP[c4], is = sP[nc4 + c4], ga = sP[2 * nc4 + c4], be = sP[3 * nc4 + c4];
+  const float4 m1 = sP[4 * nc4 + c4], m2 = sP[5 * nc4 + c4];
+  float g[4], xh[4];
+  grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, rng_off, bn.stream, (unsigned long long)idx, bn.p_drop, g, xh);
+  const float gi[4] = {ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w};
+  const float a1[4] = {m1.x, m1.y, m1.z, m1.w}, a2[4] = {m2.x, m2.y, m2.z, m2.w};
+  float r[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) r[u] = gi[u] * (bn.training ? (g[u] - a1[u] - xh[u] * a2[u]) : g[u]);
+  return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// out-of-line copy for the rare neighbour outside the tile: keeps the Philox state out of the row loop's registers
+__device__ __noinline__ float4 dy_at_halo(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, int nc4, int ld,
+                                          int off, int t, int c4) {
+  const bool drop = bn.training && bn.p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - bn.p_drop) : 1.0f;
+  unsigned long long seed = 0, rng_off = 0;
+  if (drop) { seed = bn.rng[0]; rng_off = bn.rng[1]; }
+  const Philox ph(seed);
+  return dy_at(bn, Y, sP, nc4, ld, off, t, c4, drop, scale, ph, rng_off);
+}
+
+// dY slab of a tile -> shared memory (out of line: its Philox/parameter registers do not add to the row loop's)
+__device__ __noinline__ void stage_dy_slab(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, float4* sG,
+                                           int nc4, int ld, int off, int t0, int nrows) {
+  const bool drop = bn.training && bn.p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - bn.p_drop) : 1.0f;
+  unsigned long long seed = 0, rng_off = 0;
+  if (drop) { seed = bn.rng[0]; rng_off = bn.rng[1]; }
+  const Philox ph(seed);
+#pragma unroll 2
+  for (int i = threadIdx.x; i < nrows * nc4; i += kAggThreads) {
+    const int r = i / nc4, c = i - r * nc4;
+    sG[i] = dy_at(bn, Y, sP, nc4, ld, off, t0 + r, c, drop, scale, ph, rng_off);
+  }
+}
+
+// grid (row tiles, V); fo_v <= 128*NQ, float4 layout.  The CTA builds its kStatRows x fo_v slabs of Z (cp.async) and of
+// dY (computed from dX, Y and the reduced BatchNorm sums while staging -- bn_bwd_apply and the dY round trip through
+// memory disappear) in shared memory, prefetches the edge metadata of each warp's rows (one edge per lane), and then
+// runs the row loop of agg_bwd_kernel out of shared memory.  Neighbours outside the tile recompute dY on the fly.
+template <int NQ>
+__global__ void __launch_bounds__(kAggThreads, 3) agg_bwd_tile_kernel(PlanDev p, LayerDev L, BnBwdArgs bn,
+                                                                   const float* __restrict__ Z, const float* __restrict__ Y,
+                                                                   const float* __restrict__ ball,
+                                                                   const float* __restrict__ sig,
+                                                                   const float* __restrict__ invR, float* __restrict__ Q,
+                                                                   float* __restrict__ dpart) {
+  extern __shared__ __align__(16) float tile_smem_b[];
+  __shared__ float s_hist[kAggWarps][EAGCN_SIG_STRIDE];
+  __shared__ int s_rp[kStatRows + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot, nc4 = fo >> 2;
+  for (int r = 0; r < kAggRows; ++r) {   // slack rows [T, t_cap) of Q stay defined (zeros) for the split-K dW GEMM
+    const int t = t0 + warp * kAggRows + r;
+    if (t >= T && t < p.t_cap)
+      for (int c = lane; c < nc4; c += 32) reinterpret_cast<float4*>(Q + (size_t)t * ld + off)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (t0 >= T) return;
+  const int nrows = min(kStatRows, T - t0);
+  float4* sZ = reinterpret_cast<float4*>(tile_smem_b);   // [kStatRows][nc4]
+  float4* sG = sZ + kStatRows * nc4;                     // [kStatRows][nc4]  dY
+  float4* sP = sG + kStatRows * nc4;                     // [6][nc4]
+  for (int i = tid; i < nrows * nc4; i += kAggThreads) {
+    const int r = i / nc4, c = i - r * nc4;
+    cp_async16(sZ + i, Z + (size_t)(t0 + r) * ld + off + c * 4);
+  }
+  cp_async_commit();
+  {
+    float* P = reinterpret_cast<float*>(sP);
+    for (int c = tid; c < fo; c += kAggThreads) {
+      P[c] = bn.mean[off + c]; P[fo + c] = bn.invstd[off + c];
+      P[2 * fo + c] = ball[ld + off + c]; P[3 * fo + c] = ball[2 * ld + off + c];
+      P[4 * fo + c] = bn.training ? (float)(bn.bsums[off + c] / bn.M) : 0.0f;
+      P[5 * fo + c] = bn.training ? (float)(bn.bsums[ld + off + c] / bn.M) : 0.0f;
+    }
+  }
+  if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
+  for (int i = tid; i < kAggWarps * EAGCN_SIG_STRIDE; i += kAggThreads) (&s_hist[0][0])[i] = 0.0f;
+  __syncthreads();
+  const float* sg = sig + v * EAGCN_SIG_STRIDE;
+  const float sig_r = sg[256];
+  const uint8_t* code = p.code + (size_t)v * p.e_cap;
+  const uint8_t* rcode = p.rcode + (size_t)v * p.e_cap;
+  const float* iR = invR + (size_t)v * p.t_cap;
+  // edge metadata of this warp's rows: consecutive in the CSR arrays, one edge per lane when there are <= 32
+  const int wr0 = warp * kAggRows, wr1 = min(nrows, wr0 + kAggRows);
+  int ea = 0, eb = 0;
+  if (wr0 < nrows) { ea = s_rp[wr0]; eb = s_rp[wr1]; }
+  const bool pre = eb - ea <= 32;
+  const bool mine = pre && ea + lane < eb;
+  int j_p = 0, c_p = 0, rc_p = 0;
+  if (mine) { j_p = p.col[ea + lane]; c_p = code[ea + lane]; rc_p = rcode[ea + lane]; }
+  const float invR_l = wr0 + lane < wr1 ? iR[t0 + wr0 + lane] : 0.0f;
+  stage_dy_slab(bn, Y, sP, sG, nc4, ld, off, t0, nrows);
+  float s_p = 0.f, aq_p = 0.f;
+  if (mine) { s_p = sg[c_p]; aq_p = sg[rc_p] * iR[j_p]; }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int r = wr0; r < wr1; ++r) {
+    const int t = t0 + r;
+    const int e0 = s_rp[r], e1 = s_rp[r + 1];
+    const float invR_t = __shfl_sync(0xffffffffu, invR_l, r - wr0);
+    // ---- c_t = dY_t . (Y_t - b),  d_self = dY_t . Z_t ----
+    float dyt[NQ][4];
+    float ct = 0.f, dself = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int c4 = q * 32 + lane;
+      if (c4 < nc4) {
+        const float4 a = sG[r * nc4 + c4], z = sZ[r * nc4 + c4];
+        const float4 y = __ldg(reinterpret_cast<const float4*>(Y + (size_t)t * ld + off) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ball + off) + c4);
+        dyt[q][0] = a.x; dyt[q][1] = a.y; dyt[q][2] = a.z; dyt[q][3] = a.w;
+        ct = fmaf(a.x, y.x - b.x, ct); dself = fmaf(a.x, z.x, dself);
+        ct = fmaf(a.y, y.y - b.y, ct); dself = fmaf(a.y, z.y, dself);
+        ct = fmaf(a.z, y.z - b.z, ct); dself = fmaf(a.z, z.z, dself);
+        ct = fmaf(a.w, y.w - b.w, ct); dself = fmaf(a.w, z.w, dself);
+      } else { dyt[q][0] = dyt[q][1] = dyt[q][2] = dyt[q][3] = 0.0f; }
+    }
+    ct = warp_sum(ct); dself = warp_sum(dself);
+    if (lane == 0) s_hist[warp][256] += (dself - ct) * invR_t * sig_r * (1.0f - sig_r);
+    const float a_self = sig_r * invR_t;
+    float qacc[NQ][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { qacc[q][0] = qacc[q][1] = qacc[q][2] = qacc[q][3] = 0.0f; }
+    for (int ch = e0; ch < e1; ch += 32) {   // active rows have deg >= 1
+      int j_e = j_p, c_e = c_p, lo = e0 - ea;
+      float aq_e = aq_p, s_e = s_p;
+      if (!pre) {
+        const int e = ch + lane;
+        lo = 0; j_e = 0; c_e = 0; aq_e = 0.f; s_e = 0.f;
+        if (e < e1) { j_e = p.col[e]; c_e = code[e]; s_e = sg[c_e]; aq_e = sg[rcode[e]] * iR[j_e]; }
+      }
+      const int cnt = min(32, e1 - ch);
+      float d_e = 0.f;
+      for (int k = 0; k < cnt; ++k) {
+        const int j = __shfl_sync(0xffffffffu, j_e, lo + k);
+        const float aq = __shfl_sync(0xffffffffu, aq_e, lo + k);   // A_v[j -> t]: edge (j,t) has type rcode, row sum R_j
+        const int jr = j - t0;
+        const bool in_tile = (unsigned)jr < (unsigned)nrows;
+        float dot = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int c4 = q * 32 + lane;
+          if (c4 < nc4) {
+            float4 zj, gj;
+            if (in_tile) { zj = sZ[jr * nc4 + c4]; gj = sG[jr * nc4 + c4]; }
+            else {
+              zj = __ldg(reinterpret_cast<const float4*>(Z + (size_t)j * ld + off) + c4);
+              gj = dy_at_halo(bn, Y, sP, nc4, ld, off, j, c4);
+            }
+            dot = fmaf(dyt[q][0], zj.x, dot); qacc[q][0] = fmaf(aq, gj.x, qacc[q][0]);
+            dot = fmaf(dyt[q][1], zj.y, dot); qacc[q][1] = fmaf(aq, gj.y, qacc[q][1]);
+            dot = fmaf(dyt[q][2], zj.z, dot); qacc[q][2] = fmaf(aq, gj.z, qacc[q][2]);
+            dot = fmaf(dyt[q][3], zj.w, dot); qacc[q][3] = fmaf(aq, gj.w, qacc[q][3]);
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == lo + k) d_e += dot;
+      }
+      // attention-logit gradients of this chunk's edges, serialised -> deterministic
+      const float ds_e = (d_e - ct) * invR_t * s_e * (1.0f - s_e);
+      for (int k = 0; k < cnt; ++k) {
+        const float dsk = __shfl_sync(0xffffffffu, ds_e, lo + k);
+        const int ck = __shfl_sync(0xffffffffu, c_e, lo + k);
+        if (lane == 0) s_hist[warp][ck] += dsk;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int c4 = q * 32 + lane;
+      if (c4 < nc4)
+        reinterpret_cast<float4*>(Q + (size_t)t * ld + off)[c4] =
+            make_float4(a_self * dyt[q][0] + qacc[q][0], a_self * dyt[q][1] + qacc[q][1],
+                        a_self * dyt[q][2] + qacc[q][2], a_self * dyt[q][3] + qacc[q][3]);
+    }
+  }
+  __syncthreads();
+  float* out = dpart + ((size_t)tile * L.V + v) * EAGCN_SIG_STRIDE;
+  for (int i = tid; i < EAGCN_SIG_STRIDE; i += kAggThreads) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAggWarps; ++w) a += s_hist[w][i];
+    out[i] = a;
+  }
+}
+
+template <int NQ>
+static int launch_agg_bwd_tile(dim3 grid, size_t smem, cudaStream_t st, const PlanDev& p, const LayerDev& L,
+                               const BnBwdArgs& bn, const eagcn_work_t* w) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(agg_bwd_tile_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)agg_bwd_tile_smem(128 * NQ));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  agg_bwd_tile_kernel<NQ><<<grid, kAggThreads, smem, st>>>(p, L, bn, (const float*)w->Z, (const float*)w->Y,
+                                                           (const float*)w->ball, (const float*)w->sig,
+                                                           (const float*)w->invR, (float*)w->Q, (float*)w->partial);
+  return 0;
+}
+
 // datt[v][i] = sum over live tiles (fixed order)
 __global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float* __restrict__ dpart,
                                                           float* __restrict__ datt, int V) {
@@ -382,19 +603,24 @@ __global__ void __launch_bounds__(256) bwd_post_kernel(PlanDev p, LayerDev L, co
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n) return;
     float s = 0.0f;
-    for (int z = 0; z < ns; ++z) s += wpart[(long long)z * n + idx];
+#pragma unroll 4
+    for (int z = 0; z < ns; ++z) s += __ldg(wpart + (long long)z * n + idx);
     const int k = (int)(idx / C), c = (int)(idx - (long long)k * C);
     int v = 0;
     while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
     dwall[(long long)L.fin * L.off[v] + (long long)k * L.fo[v] + (c - L.off[v])] = s;
   } else {
-    const int i = ((int)blockIdx.x - nblk_w) * 256 + threadIdx.x;
+    // one warp per table entry: lanes take every 32nd tile (independent loads), fixed-order shuffle tree
+    const int i = ((int)blockIdx.x - nblk_w) * 8 + (threadIdx.x >> 5);
     if (i >= L.V * EAGCN_SIG_STRIDE) return;
     const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
     const int ntile = (T + kStatRows - 1) / kStatRows;
     double a = 0.0;
-    for (int t = 0; t < ntile; ++t) a += (double)dpart[(size_t)t * L.V * EAGCN_SIG_STRIDE + i];
-    datt[i] = (float)a;
+#pragma unroll 4
+    for (int t = threadIdx.x & 31; t < ntile; t += 32) a += (double)__ldg(dpart + (size_t)t * L.V * EAGCN_SIG_STRIDE + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) datt[i] = (float)a;
   }
 }
 
@@ -450,7 +676,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   StatEpilogue ep{2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
                   (w->training & 1) ? 1 : 0, 0.0, 0.0, 0.0};
   EAGCN_PROF("stat_reduce_kernel", st);
-  stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
+  stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -467,6 +693,24 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const long long total = (long long)p.t_cap * C;
+  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
+  int fo_max = 0;
+  for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
+  if (agg_mode() == 0 && vec4_ok_b(layer) && fo_max <= kTileMaxFo && aligned16(w->dX) && aligned16(w->Y) &&
+      aligned16(w->Z) && aligned16(w->Q) && aligned16(w->ball)) {
+    // fused: dY is produced inside the aggregation kernel's shared-memory tile (w->dY is not written)
+    BnBwdArgs bn{(const float*)w->dX, (const float*)w->mean, (const float*)w->invstd, (const double*)w->bsums,
+                 (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M, (float)w->p_drop,
+                 (w->training & 1) ? 1 : 0};
+    const size_t smem = agg_bwd_tile_smem(fo_max);
+    int lrc;
+    EAGCN_PROF("agg_bwd_kernel", st);
+    if (fo_max <= 128) lrc = launch_agg_bwd_tile<1>(grid, smem, st, p, L, bn, w);
+    else if (fo_max <= 256) lrc = launch_agg_bwd_tile<2>(grid, smem, st, p, L, bn, w);
+    else if (fo_max <= 384) lrc = launch_agg_bwd_tile<3>(grid, smem, st, p, L, bn, w);
+    else lrc = launch_agg_bwd_tile<4>(grid, smem, st, p, L, bn, w);
+    if (lrc) { ::eagcn::prof_end(); return lrc; }
+  } else {
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY)) {
     dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_bwd_apply_kernel", st);
@@ -483,7 +727,6 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
     EAGCN_LAUNCH_CHECK();
   }
-  dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   if (vec4_ok_b(layer)) {
     EAGCN_PROF("agg_bwd_kernel", st);
     agg_bwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
@@ -494,6 +737,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
     agg_bwd_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
+  }
   }
   EAGCN_LAUNCH_CHECK();
   int rc = 0;
@@ -515,7 +759,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
                  (float*)w->gemm_ws, w->gemm_ws_bytes / (long long)sizeof(float), st, &ns);
   if (rc) return rc;
   const int nblk_w = (int)(((long long)L.fin * C + 255) / 256);
-  const int nblk_a = (L.V * EAGCN_SIG_STRIDE + 255) / 256;
+  const int nblk_a = (L.V * EAGCN_SIG_STRIDE + 7) / 8;
   EAGCN_PROF("bwd_post_kernel", st);
   bwd_post_kernel<<<nblk_w + nblk_a, 256, 0, st>>>(p, L, (const float*)w->gemm_ws, ns, (float*)w->dwall,
                                                    (const float*)w->partial, (float*)w->datt, nblk_w);

@@ -24,6 +24,7 @@ namespace eagcn {
 int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
             const int* Mdev, cudaStream_t st);
 inline int& gemm_mode() { static int m = 0; return m; }
+inline int& agg_mode() { static int m = 0; return m; }   // 0: shared-memory tile kernels when eligible, 1: generic
 
 // ---------------------------------------------------------------------------------------------
 // wallT: [2][fo_tot][fin] and wsplit: [2][fin][fo_tot] hold the exact TF32 split of every weight
@@ -185,6 +186,112 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_onepass_kernel(PlanDev p,
   }
 }
 
+// ---- shared-memory tile variant -------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kTileEdgeCap = 512;     // edges of one row tile staged in shared memory (beyond: read through L2)
+constexpr int kTileMaxFo = 512;       // widest view the tile kernels take (float4 layout)
+
+inline int tile_row_groups(int fo) { return kAggThreads / (fo / 4); }
+inline size_t agg_fwd_tile_smem(int fo) { return (size_t)(kStatRows * fo + tile_row_groups(fo) * 2 * fo) * sizeof(float); }
+
+// Tile variant (float4 layout, fo_v <= kTileMaxFo).  Atoms of a molecule are consecutive packed rows, so nearly
+// every neighbour of a row lives in the same 32-row tile: the CTA stages its kStatRows x fo_v slab of Z with cp.async
+// (every load in flight at once instead of one dependent L2 round trip per row and edge) together with the tile's
+// edge list, then (row group, float4 channel) items -- no idle lanes for fo_v = 80 / 140 -- walk the edges out of
+// shared memory.  Neighbours outside the tile (molecules straddling a tile boundary) are read through L2.
+// Y is bit-identical to the generic kernel (same operation order); the statistics partials are summed per row group.
+__global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+                                                                   const float* __restrict__ ball,
+                                                                   const float* __restrict__ sig, float* __restrict__ Y,
+                                                                   float* __restrict__ invR, float* __restrict__ partial,
+                                                                   int n_pad, int want_stats) {
+  extern __shared__ __align__(16) float tile_smem[];
+  __shared__ int s_rp[kStatRows + 1];
+  __shared__ float s_a[kTileEdgeCap];      // sigma(code), then a_e = sigma / R_row
+  __shared__ int s_j[kTileEdgeCap];
+  __shared__ float s_R[kStatRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  if (t0 >= T) return;
+  const int nrows = min(kStatRows, T - t0);
+  const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot, nc4 = fo >> 2;
+  float4* sZ = reinterpret_cast<float4*>(tile_smem);             // [kStatRows][nc4]
+  float* s_red = tile_smem + kStatRows * fo;                     // [row groups][2][fo]
+  for (int i = tid; i < nrows * nc4; i += kAggThreads) {
+    const int r = i / nc4, c = i - r * nc4;
+    cp_async16(sZ + i, Z + (size_t)(t0 + r) * ld + off + c * 4);
+  }
+  cp_async_commit();
+  if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
+  __syncthreads();
+  const float* sg = sig + v * EAGCN_SIG_STRIDE;
+  const float sig_r = sg[256];
+  const uint8_t* code = p.code + (size_t)v * p.e_cap;
+  const int e_lo = s_rp[0], ne = s_rp[nrows] - e_lo;
+  for (int i = tid; i < min(ne, kTileEdgeCap); i += kAggThreads) { s_a[i] = sg[code[e_lo + i]]; s_j[i] = p.col[e_lo + i]; }
+  __syncthreads();
+  // attention row sums (layers.py:84,87): warp w owns rows w*kAggRows .. ; lane-strided partial sums like the generic kernel
+  for (int r = warp * kAggRows; r < min(nrows, (warp + 1) * kAggRows); ++r) {
+    const int a0 = s_rp[r] - e_lo, a1 = s_rp[r + 1] - e_lo;
+    float sw = 0.0f;
+    for (int e = a0 + lane; e < a1; e += 32) sw += e < kTileEdgeCap ? s_a[e] : sg[code[e_lo + e]];
+    sw = warp_sum(sw);
+    const float R = sw + sig_r + (float)(n_pad - (a1 - a0)) * EAGCN_TINY;
+    if (lane == 0) { invR[(size_t)v * p.t_cap + t0 + r] = 1.0f / R; s_R[r] = R; }
+    for (int e = a0 + lane; e < min(a1, kTileEdgeCap); e += 32) s_a[e] = s_a[e] / R;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int nrg = kAggThreads / nc4;
+  const int rg = tid / nc4, c4 = tid - rg * nc4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rg < nrg) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ball + off) + c4);
+    for (int r = rg; r < nrows; r += nrg) {                      // aggregate (layers.py:90,39)
+      const float R = s_R[r];
+      const float a_self = sig_r / R;
+      const float4 zt = sZ[r * nc4 + c4];
+      float acc[4] = {a_self * zt.x, a_self * zt.y, a_self * zt.z, a_self * zt.w};
+      const int a0 = s_rp[r] - e_lo, a1 = s_rp[r + 1] - e_lo;
+      for (int e = a0; e < a1; ++e) {
+        float a; int j;
+        if (e < kTileEdgeCap) { a = s_a[e]; j = s_j[e]; }
+        else { a = sg[code[e_lo + e]] / R; j = p.col[e_lo + e]; }
+        const int jr = j - t0;
+        const float4 zj = (unsigned)jr < (unsigned)nrows
+                              ? sZ[jr * nc4 + c4]
+                              : __ldg(reinterpret_cast<const float4*>(Z + (size_t)j * ld + off) + c4);
+        acc[0] = fmaf(a, zj.x, acc[0]); acc[1] = fmaf(a, zj.y, acc[1]);
+        acc[2] = fmaf(a, zj.z, acc[2]); acc[3] = fmaf(a, zj.w, acc[3]);
+      }
+      reinterpret_cast<float4*>(Y + (size_t)(t0 + r) * ld + off)[c4] =
+          make_float4(acc[0] + b4.x, acc[1] + b4.y, acc[2] + b4.z, acc[3] + b4.w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s1[u] += acc[u]; s2[u] = fmaf(acc[u], acc[u], s2[u]); }
+    }
+  }
+  if (want_stats) {                                              // cross-row-group reduction in fixed order
+    if (rg < nrg) {
+      *reinterpret_cast<float4*>(s_red + (rg * 2 + 0) * fo + c4 * 4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      *reinterpret_cast<float4*>(s_red + (rg * 2 + 1) * fo + c4 * 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+    __syncthreads();
+    for (int c = tid; c < fo; c += kAggThreads) {
+      float a = 0.f, b = 0.f;
+      for (int g = 0; g < nrg; ++g) { a += s_red[(g * 2 + 0) * fo + c]; b += s_red[(g * 2 + 1) * fo + c]; }
+      partial[((size_t)tile * 2 + 0) * ld + off + c] = a;
+      partial[((size_t)tile * 2 + 1) * ld + off + c] = b;
+    }
+  }
+}
+
 // grid (row tiles of kStatRows, V).  kAggWarps warps x kAggRows rows.
 template <int VEC>
 __global__ void __launch_bounds__(kAggThreads) agg_fwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
@@ -296,27 +403,38 @@ struct StatEpilogue {             // what stat_reduce_kernel does with the reduc
   int training; double M, eps, momentum;
 };
 
-// sums[k][c] = sum over live tiles of partial[tile][k][c]   (double, fixed order), then the per-channel epilogue
-__global__ void __launch_bounds__(256) stat_reduce_kernel(PlanDev p, LayerDev L, const float* __restrict__ partial,
-                                                          double* __restrict__ sums, int C, StatEpilogue ep) {
-  __shared__ double s[8][2][32];
+// sums[k][c] = sum over live tiles of partial[tile][k][c]   (double, fixed order), then the per-channel epilogue.
+// Block = 32 channels x 32 tile lanes: a thread adds every 32nd tile (independent loads, ~5 per thread at Tox21 sizes,
+// instead of a 19-deep dependent chain), the 32 lanes are then combined through shared memory in lane order.
+constexpr int kStatLanes = 32;
+__global__ void __launch_bounds__(32 * kStatLanes) stat_reduce_kernel(PlanDev p, LayerDev L,
+                                                                      const float* __restrict__ partial,
+                                                                      double* __restrict__ sums, int C, StatEpilogue ep) {
+  __shared__ double s[kStatLanes][2][32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int ntile = (T + kStatRows - 1) / kStatRows;
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int t = ty; t < ntile; t += 8) {
-      a += (double)partial[((size_t)t * 2 + 0) * C + c];
-      b += (double)partial[((size_t)t * 2 + 1) * C + c];
+  if (c < C) {
+#pragma unroll 4
+    for (int t = ty; t < ntile; t += kStatLanes) {
+      a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
+      b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
     }
+  }
   s[ty][0][cx] = a; s[ty][1][cx] = b;
   __syncthreads();
-  if (ty == 0 && c < C) {
-    double aa = 0.0, bb = 0.0;
+  if (ty < 2 && c < C) {                 // warp 0 finishes the S1 column, warp 1 the S2 column
+    double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { aa += s[w][0][cx]; bb += s[w][1][cx]; }
-    sums[c] = aa; sums[C + c] = bb;
+    for (int w = 0; w < kStatLanes; ++w) acc += s[w][ty][cx];
+    sums[ty * C + c] = acc;
+    s[0][ty][cx] = acc;
+  }
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    const double aa = s[0][0][cx], bb = s[0][1][cx];
     if (ep.kind == 1) {
       bn_finalize_channel(L, ep.ball, c, aa, bb, ep.mean, ep.invstd, ep.training, ep.M, ep.eps, ep.momentum);
     } else if (ep.kind == 2) {      // dvec = [dbias | dgamma | dbeta]
@@ -462,7 +580,21 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   const bool host_allreduce = (w->training & 2) != 0;   // global-batch BatchNorm: host sums the partial sums over ranks
   int fo_max = 0;
   for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
-  if (vec4_ok(layer) && fo_max <= 256) {
+  if (agg_mode() == 0 && vec4_ok(layer) && fo_max <= kTileMaxFo && aligned16(w->Z) && aligned16(w->Y) && aligned16(w->ball)) {
+    size_t smem = 0;
+    for (int v = 0; v < L.V; ++v) smem = agg_fwd_tile_smem(L.fo[v]) > smem ? agg_fwd_tile_smem(L.fo[v]) : smem;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(agg_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)agg_fwd_tile_smem(kTileMaxFo));
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    EAGCN_PROF("agg_fwd_kernel", st);
+    agg_fwd_tile_kernel<<<grid, kAggThreads, smem, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+                                                         (const float*)w->sig, (float*)w->Y, (float*)w->invR,
+                                                         (float*)w->partial, n_pad, want);
+  } else if (vec4_ok(layer) && fo_max <= 256) {
     EAGCN_PROF("agg_fwd_kernel", st);
     if (fo_max <= 128)
       agg_fwd_onepass_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
@@ -485,7 +617,7 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (want && host_allreduce) {
     StatEpilogue ep{0, nullptr, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0};
     EAGCN_PROF("stat_reduce_kernel", st);
-    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
     EAGCN_LAUNCH_CHECK();
   }
   return 0;
@@ -508,7 +640,7 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
     if (!w->partial) return EAGCN_E_ARG;
     StatEpilogue ep{1, (const float*)w->ball, (float*)w->mean, (float*)w->invstd, nullptr, 1, M, w->eps, w->momentum};
     EAGCN_PROF("stat_reduce_kernel", st);
-    stat_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_finalize_kernel", st);

@@ -45,16 +45,30 @@ __global__ void __launch_bounds__(256) rows_scatter_kernel(PlanDev p, const floa
   }
 }
 
-// grid (B, ceil(F/128)); 128 threads, one channel each; rows summed in order
-__global__ void __launch_bounds__(128) readout_sum_kernel(PlanDev p, const float* __restrict__ packed,
+// grid (B, ceil(F/64)); 64 channels x 8 row groups: a group sums a contiguous eighth of the molecule's rows (the
+// largest molecule would otherwise be a 132-deep serial chain), the groups are combined in fixed order
+__global__ void __launch_bounds__(512) readout_sum_kernel(PlanDev p, const float* __restrict__ packed,
                                                           float* __restrict__ out, int F) {
+  __shared__ float s[8][64];
   const int b = blockIdx.x;
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= F) return;
+  const int cx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cx;
   const int t0 = p.mol_ptr[b], t1 = p.mol_ptr[b + 1];
-  float s = 0.0f;
-  for (int t = t0; t < t1; ++t) s += __ldg(packed + (size_t)t * F + c);
-  out[(size_t)b * F + c] = s;
+  const int per = (t1 - t0 + 7) >> 3;
+  const int a0 = t0 + g * per, a1 = min(t1, a0 + per);
+  float acc = 0.0f;
+  if (c < F) {
+#pragma unroll 4
+    for (int t = a0; t < a1; ++t) acc += __ldg(packed + (size_t)t * F + c);
+  }
+  s[g][cx] = acc;
+  __syncthreads();
+  if (g == 0 && c < F) {
+    float r = s[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += s[k][cx];
+    out[(size_t)b * F + c] = r;
+  }
 }
 
 __global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const float* __restrict__ dout,
@@ -92,9 +106,9 @@ extern "C" int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, 
 extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, void* out, int64_t F, void* stream) {
   if (!plan_ok(plan) || !out || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
-  dim3 grid(p.B, (unsigned)((F + 127) / 128));
+  dim3 grid(p.B, (unsigned)((F + 63) / 64));
   EAGCN_PROF("readout_sum_kernel", (cudaStream_t)stream);
-  readout_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)out, (int)F);
+  readout_sum_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)out, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -447,3 +447,9 @@ def gemm_tn(A, B, k_dev, engine=0):
 def set_gemm_engine(name: str):
     """'tcgen05' (default: tensor cores with 3xTF32 compensation where the layout allows) or 'ffma'."""
     check(lib().eagcn_set_gemm_mode({"tcgen05": 0, "ffma": 1, "tcgen05-nt": 2}[name]), "eagcn_set_gemm_mode")
+
+
+def set_agg_engine(name: str):
+    """'tile' (default: shared-memory tile aggregation kernels, BatchNorm backward folded into the backward one) or
+    'generic' (warp-per-row kernels reading neighbours through L2, dY materialised)."""
+    check(lib().eagcn_set_agg_mode({"tile": 0, "generic": 1}[name]), "eagcn_set_agg_mode")

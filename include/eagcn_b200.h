@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 8
+#define EAGCN_ABI_VERSION 9
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -216,6 +216,13 @@ int eagcn_head_backward(const eagcn_head_t* args, void* stream);
  * (Z = H W, dH = Q W^T), FFMA for the MN-major weight gradient (dW = H^T Q).  Process-wide.    */
 int eagcn_set_gemm_mode(int mode);
 int eagcn_get_gemm_mode(void);
+/* --- aggregation engine ------------------------------------------------------------------------ */
+/* 0 (default): shared-memory tile kernels for the neighbour aggregation (layers.py:90,39) and its backward when
+ * the layout allows it (every fo_v a multiple of 4 and <= 512, 16-byte aligned buffers); the backward tile kernel
+ * also applies the BatchNorm/ReLU/dropout backward on the fly, so eagcn_layer_backward_b then leaves work.dY
+ * unwritten.  1: always the generic warp-per-row kernels (dY materialised).  Process-wide.               */
+int eagcn_set_agg_mode(int mode);
+int eagcn_get_agg_mode(void);
 /* stand-alone projection product  C[m_cap, N] = A[m_cap, K] . B[N, K]^T  (fp32, rows contiguous; lda/ldb/ldc
  * in elements).  Only the first min(*m_dev, m_cap) rows are live (m_dev: device int32); the remaining
  * rows of C are written as zeros.  engine: 0 = tcgen05 3xTF32 (EAGCN_E_UNSUPPORTED if the layout does

@@ -268,6 +268,30 @@ def run_b200(args):
                 flat.mul_(1.0 / world)
     bucket = _Bucket()
     torch.cuda.synchronize()
+    if args.gemm_trace:
+        # diagnostic: clock64 stamps of the tcgen05 GEMM pipeline (CTA 0 of each GEMM launch of one eager step)
+        for i in range(3):
+            step_dense(slots[i % NB])
+        torch.cuda.synchronize()
+        stride = int(_lib.lib().eagcn_gemm_trace_stride())
+        buf = torch.zeros(8 * stride, dtype=torch.int64, device=dev)
+        _lib.lib().eagcn_gemm_trace(buf.data_ptr(), 8)
+        step_dense(slots[0])
+        torch.cuda.synchronize()
+        _lib.lib().eagcn_gemm_trace(None, 0)
+        tr = buf.cpu().view(8, stride)
+        out = []
+        for l in range(8):
+            h = tr[l, :8].tolist()
+            nkb = int(h[0])
+            if nkb <= 0:
+                continue
+            t0 = h[4]
+            kb = [[int(x - t0) for x in tr[l, 8 + 5 * k: 13 + 5 * k].tolist()] for k in range(min(nkb, 64))]
+            out.append({"num_kb": nkb, "BN": h[1], "stages": h[2], "mode": h[3], "epi_start": h[5] - t0,
+                        "epi_end": h[6] - t0, "kb": kb})
+        print(json.dumps({"gemm_trace": out}))
+        return
     if args.profile_only:
         for i in range(args.warmup + args.steps):
             step_dense(slots[i % NB])
@@ -317,6 +341,33 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.trace:
+        # diagnostic (never a bench value): per-kernel durations INSIDE the graph replays, via CUPTI activity records
+        from torch.profiler import profile, ProfilerActivity
+        for i in range(2 * NB):
+            slots[i % NB].g_dense.replay()
+        torch.cuda.synchronize()
+        nrep = 4 * NB
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(nrep):
+                slots[i % NB].g_dense.replay()
+            torch.cuda.synchronize()
+        agg = {}
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        t_first, t_last, busy = None, None, 0.0
+        for e in evs:
+            d = e.time_range.end - e.time_range.start
+            a = agg.setdefault(e.name[:70], [0, 0.0]); a[0] += 1; a[1] += d
+            busy += d
+            t_first = e.time_range.start if t_first is None else t_first
+            t_last = e.time_range.end
+        rows = sorted(((k, n / nrep, t / nrep) for k, (n, t) in agg.items()), key=lambda r: -r[2])
+        print(json.dumps({"trace": True, "replays": nrep, "span_us_per_step": (t_last - t_first) / nrep,
+                          "busy_us_per_step": busy / nrep,
+                          "kernels": [{"name": k, "launches_per_step": n, "us_per_step": t} for k, n, t in rows]}))
+        return
 
     def timed(run_step, K, W):
         for i in range(W):
@@ -614,6 +665,8 @@ def main():
                     help="dense head: fused CUDA kernels or stock PyTorch ops (auto = the model's default)")
     ap.add_argument("--layers-only", action="store_true",
                     help="diagnostic: loss = sum of the last layer's atom rows (no read-out / dense head); not a bench value")
+    ap.add_argument("--gemm-trace", action="store_true", help="diagnostic: GEMM pipeline clock stamps of one eager step")
+    ap.add_argument("--trace", action="store_true", help="diagnostic: per-kernel durations inside the graph replays")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")

@@ -96,6 +96,8 @@ _PROTOS = {
     "eagcn_head_backward": (c_int, [c_void_p, c_void_p]),
     "eagcn_set_gemm_mode": (c_int, [c_int]),
     "eagcn_get_gemm_mode": (c_int, []),
+    "eagcn_gemm_trace": (c_int, [c_void_p, c_int64]),
+    "eagcn_gemm_trace_stride": (c_int64, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),
     "eagcn_get_agg_mode": (c_int, []),
     "eagcn_gemm_nt": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,

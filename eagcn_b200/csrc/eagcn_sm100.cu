@@ -63,6 +63,17 @@ extern "C" int eagcn_gemm_tn(const void* A, int64_t lda, const void* B, int64_t 
 #include <string>
 extern "C" int64_t eagcn_launch_count(void) { return eagcn::prof().launches; }
 
+// Pipeline trace of the tcgen05 GEMM (diagnostic): the next `max_launches` GEMM launches write the clock64 stamps of
+// CTA (0,0,0) into buf (device int64, EAGCN_GEMM_TRACE_STRIDE entries per launch): [0] k-blocks, [1] BN, [2] stages,
+// [3] mode, [4] start, [5] epilogue start, [6] epilogue end, then per k-block at 8+5*kb: TMA issue, tile landed,
+// transform done, MMA issue start, MMA issued+committed.  buf = NULL switches it off.
+extern "C" int eagcn_gemm_trace(void* buf, int64_t max_launches) {
+  eagcn::tc::TraceState& t = eagcn::tc::trace_state();
+  t.buf = (long long*)buf; t.max_launches = buf ? (int)max_launches : 0; t.n = 0;
+  return 0;
+}
+extern "C" int64_t eagcn_gemm_trace_stride(void) { return eagcn::tc::kTraceStride; }
+
 extern "C" int eagcn_profile(int enable) {
   eagcn::ProfState& s = eagcn::prof();
   for (auto& r : s.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -127,7 +127,9 @@ struct TcArgs {
   const int* Kdev;                 // TN: live K rows = min(*Kdev, K)
   int kchunk;                      // TN: K rows per blockIdx.z
   long long split_stride;          // TN: elements between split partials
+  long long* trace;                // diagnostic: clock64 stamps of CTA (0,0,0)'s pipeline events (nullptr: off)
 };
+constexpr int kTraceKb = 64, kTraceStride = 8 + 5 * kTraceKb;
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -149,6 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     g.C += (long long)blockIdx.z * g.split_stride;
   }
 
+  const bool tr = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr && threadIdx.x == 0) {
+    g.trace[0] = num_kb; g.trace[1] = g.BN; g.trace[2] = g.stages; g.trace[3] = g.mode; g.trace[4] = clock64();
+  }
   if (m0 >= M || num_kb == 0) {        // nothing to accumulate: keep the tile defined (zeros)
     for (int i = threadIdx.x; i < BM * g.BN; i += kThreads) {
       const int r = m0 + i / g.BN, c = n0 + i % g.BN;
@@ -169,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_ready[s], kXformThreads);
+      mbar_init(&bar_ready[s], kXformThreads / 32);     // one arrival per transform warp
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_acc, 1);
@@ -197,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % g.stages, it = kb / g.stages;
         if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
+        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 0] = clock64();
         if (!tn) {
           mbar_expect_tx(&bar_full[s], bytesA + (g.b_split ? 2 : 1) * bytesB);
           tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
@@ -222,6 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&bar_ready[s], it & 1);
       tc_fence_after();
       if (lane == 0) {
+        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 3] = clock64();
         const uint64_t dAh = tn ? make_desc_mn(smem_u32(sA_hi(s)), box_bytes) : make_desc(smem_u32(sA_hi(s)));
         const uint64_t dAl = tn ? make_desc_mn(smem_u32(sA_lo(s)), box_bytes) : make_desc(smem_u32(sA_lo(s)));
         const uint64_t dBh = tn ? make_desc_mn(smem_u32(sB_hi(s)), box_bytes) : make_desc(smem_u32(sB_hi(s)));
@@ -237,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         umma_commit(&bar_empty[s]);                               // smem stage free once these MMAs retire
         if (kb == num_kb - 1) umma_commit(&bar_acc);              // accumulator complete
+        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 4] = clock64();
       }
       __syncwarp();
     }
@@ -246,6 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % g.stages, it = kb / g.stages;
       mbar_wait(&bar_full[s], it & 1);
+      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * 5 + 1] = clock64();
       if (tn) {                                                    // boxes outside the tensors were not loaded
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         uint4* ah = reinterpret_cast<uint4*>(sA_hi(s));
@@ -280,11 +290,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       fence_proxy_async();                                         // generic-proxy writes -> visible to UMMA (async proxy)
-      mbar_arrive(&bar_ready[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[s]);                   // 8 arrivals per stage instead of 256
+      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * 5 + 2] = clock64();
     }
     // ---- epilogue: TMEM -> registers -> global ----
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
+    if (tr && xt == 0) g.trace[5] = clock64();
     const int quad = warp & 3;                                     // TMEM lane quadrant this warp may access
     const int row = m0 + quad * 32 + lane;
     const bool live = row < M;
@@ -338,6 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
     tc_fence_before();
+    if (tr && xt == 0) g.trace[6] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
@@ -410,6 +424,14 @@ bool tc_supported(const float* A, int lda, const float* B, int ldb, int K) {
          ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && encode_fn() != nullptr;
 }
 
+struct TraceState { long long* buf = nullptr; int max_launches = 0, n = 0; };
+inline TraceState& trace_state() { static TraceState t; return t; }
+static long long* next_trace() {
+  TraceState& t = trace_state();
+  if (!t.buf || t.n >= t.max_launches) return nullptr;
+  return t.buf + (size_t)(t.n++) * kTraceStride;
+}
+
 // C[Mcap(T live), N] = A[Mcap, K] . B[N, K]^T   (both K-contiguous)
 // B_lo != nullptr: B is pre-split (B = hi part, B_lo = lo part, same leading dimension)
 int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
@@ -418,7 +440,7 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   CUtensorMap mA, mB, mB2;
   if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
   if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
-  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, 0};
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, 0, next_trace()};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // main + correction accumulators
   g.stages = pick_stages(BN, (K + BK - 1) / BK);
   const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
@@ -472,7 +494,7 @@ int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long
   if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;
   int kchunk = (Kcap + ns - 1) / ns;
   kchunk = ((kchunk + BK - 1) / BK) * BK;
-  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, (long long)M * N};
+  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, (long long)M * N, next_trace()};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   g.stages = pick_stages(BN, kchunk / BK);
   const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;

@@ -221,6 +221,8 @@ int eagcn_get_gemm_mode(void);
  * the layout allows it (every fo_v a multiple of 4 and <= 512, 16-byte aligned buffers); the backward tile kernel
  * also applies the BatchNorm/ReLU/dropout backward on the fly, so eagcn_layer_backward_b then leaves work.dY
  * unwritten.  1: always the generic warp-per-row kernels (dY materialised).  Process-wide.               */
+int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock stamps of the GEMM pipeline (see .cu) */
+int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);
 int eagcn_get_agg_mode(void);
 /* stand-alone projection product  C[m_cap, N] = A[m_cap, K] . B[N, K]^T  (fp32, rows contiguous; lda/ldb/ldc

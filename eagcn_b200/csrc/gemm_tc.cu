@@ -37,6 +37,7 @@ constexpr int UK = 8;              // UMMA K for kind::tf32 (32 bytes)
 constexpr int MAX_STAGES = 4;      // smem ring depth is chosen on the host (as many stages as fit in 200 KB)
 constexpr int kThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 transform + epilogue
 constexpr int kXformThreads = 256;
+constexpr int kStgLd = 36;         // floats per row of an epilogue staging tile (32 + 4: conflict-free 128-bit access)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -306,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool vec = ((g.ldc & 3) == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     // 8 epilogue warps: warps w and w+4 share a TMEM lane quadrant and take alternate 32-column chunks
     const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * kStgLd);   // 4.5 KB per warp, stage memory is free now
     for (int c0 = half * 32; c0 < g.BN; c0 += 64) {
       uint32_t r[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
@@ -331,22 +333,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
-      if (in_cap) {
-        const int cbase = n0 + c0;
-        if (vec && cbase + 32 <= g.N && c0 + 32 <= g.BN) {
+      const int cbase = n0 + c0;
+      if (vec && cbase + 32 <= g.N && c0 + 32 <= g.BN) {
+        // lane == row here: a direct store would touch 32 different 128-byte lines per instruction (the trace showed
+        // the epilogue store-bound: 6.5k of 36k cycles).  Transpose through this warp's staging tile in the (now idle)
+        // pipeline buffers so that every store instruction writes 4 rows x 128 contiguous bytes.
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = live ? __uint_as_float(r[j]) : 0.f; o.y = live ? __uint_as_float(r[j + 1]) : 0.f;
-            o.z = live ? __uint_as_float(r[j + 2]) : 0.f; o.w = live ? __uint_as_float(r[j + 3]) : 0.f;
-            *reinterpret_cast<float4*>(crow + cbase + j) = o;
-          }
-        } else {
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = live ? __uint_as_float(r[4 * j]) : 0.f; o.y = live ? __uint_as_float(r[4 * j + 1]) : 0.f;
+          o.z = live ? __uint_as_float(r[4 * j + 2]) : 0.f; o.w = live ? __uint_as_float(r[4 * j + 3]) : 0.f;
+          *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * j) = o;
+        }
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            if (c < g.N && c0 + j < g.BN) crow[c] = live ? __uint_as_float(r[j]) : 0.f;
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          const float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgLd + (lane & 7) * 4);
+          const int grow = m0 + quad * 32 + rr;
+          if (grow < g.Mcap) *reinterpret_cast<float4*>(g.C + (size_t)grow * g.ldc + cbase + (lane & 7) * 4) = v;
+        }
+        __syncwarp();
+      } else if (in_cap) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + j;
+          if (c < g.N && c0 + j < g.BN) crow[c] = live ? __uint_as_float(r[j]) : 0.f;
         }
       }
     }
@@ -467,28 +479,45 @@ int tn_splits(int M, int N, int Kcap) {
   return s < 1 ? 1 : s;
 }
 
-static int pick_bn_tn(int N) {          // multiple of 32 (whole MN boxes), <= 256: least padding, ties -> wider
-  int best = 128, best_waste = 1 << 30;
+// TN tile width (multiple of 32: whole MN boxes) and split count from a pipeline model fitted to clock traces of the
+// kernel (profiles/r01_gemm_trace.json): per k-block the TMA round trip is ~2100 cycles, the hi/lo transform
+// ~300 + 30/KB, twelve UMMAs cost 12 * max(75, BN/2) cycles (a narrow UMMA is not cheaper than ~75 cycles), and the
+// three overlap only as far as the stage count allows.  Narrow tiles looked attractive on padding alone (N = 700 ->
+// BN = 64) but run 55 k-blocks at the UMMA floor; wide tiles with more K splits are ~2.4x faster.
+static void pick_tn_shape(int M, int N, int Kcap, long long ws_floats, int* bn_out, int* ns_out) {
+  const int mt = (M + BM - 1) / BM, kmax = (Kcap + 127) / 128;
+  long long best = 1LL << 60;
+  *bn_out = 128; *ns_out = 1;
   for (int bn = 256; bn >= 32; bn -= 32) {
-    const int tiles = (N + bn - 1) / bn;
-    const int waste = tiles * bn - N;
-    if (waste < best_waste) { best_waste = waste; best = bn; }
+    const int tiles = mt * ((N + bn - 1) / bn);
+    int ns = 148 / tiles;
+    if (ns < 1) ns = 1;
+    if (ns > kmax) ns = kmax;
+    if (ns > 32) ns = 32;
+    while (ns > 1 && (long long)ns * M * N > ws_floats) --ns;
+    const int kb = (((Kcap + ns - 1) / ns) + BK - 1) / BK;
+    const int stage_kb = (2 * BM * BK * 4 + 2 * bn * BK * 4) / 1024;
+    int stages = 199 / stage_kb;
+    stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    stages = stages > kb ? kb : stages;
+    stages = stages < 1 ? 1 : stages;
+    const long long xform = 300 + 30 * (16 + bn / 8);
+    const long long mma = 12 * (bn / 2 > 75 ? bn / 2 : 75);
+    long long per_kb = (2100 + xform + mma) / stages;
+    per_kb = per_kb < mma ? mma : per_kb;
+    per_kb = per_kb < xform + 300 ? xform + 300 : per_kb;       // the transform warps are a serial resource
+    const long long waves = (tiles * (long long)ns + 147) / 148;
+    const long long cost = waves * (kb * per_kb + 4000 + 25 * bn);     // + prologue and epilogue
+    if (cost < best) { best = cost; *bn_out = bn; *ns_out = ns; }
   }
-  return best;
 }
 
 // C[M, N] = A[Kcap(T live), M]^T . B[Kcap, N]; rows >= T of A and B must be zero (they are: rows_gather,
 // bn_apply and agg_bwd zero-fill the slack rows).  ws: split-K partials, reduced by the caller.
 int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long long ws_floats, int M, int N, int Kcap,
                const int* Kdev, int* nsplit_out, cudaStream_t st) {
-  const int BN = pick_bn_tn(N);
-  // as many K splits as keep the whole grid inside one wave of 148 CTAs (never more than the workspace bound)
-  int ns = tn_splits(M, N, Kcap);
-  {
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int one_wave = 148 / tiles;
-    if (one_wave >= 1 && ns > one_wave) ns = one_wave;
-  }
+  int BN, ns;
+  pick_tn_shape(M, N, Kcap, ws_floats, &BN, &ns);
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
   CUtensorMap mA, mB;
   if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
                                                                  const float* __restrict__ Y, const float* __restrict__ ball,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  float* __restrict__ partial, int C, int training, float p_drop,
-                                                                 const unsigned long long* rng, unsigned long long stream) {
+                                                                 const unsigned long long* rng, unsigned long long stream,
+                                                                 float* __restrict__ G) {
   __shared__ float4 s_red[2][8][32];
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
       const float4 dx = __ldg(reinterpret_cast<const float4*>(dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
       float g[4], xh[4];
       grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, off, stream, (unsigned long long)idx, p_drop, g, xh);
+      // g = dX * relu' * dropout: kept for the tile aggregation kernel, which then needs no Philox replay
+      if (G) *reinterpret_cast<float4*>(G + idx) = make_float4(g[0], g[1], g[2], g[3]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) { s1[u] += g[u]; s2[u] = fmaf(g[u], xh[u], s2[u]); }
     }
@@ -357,226 +360,194 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDe
   }
 }
 
-// ---- shared-memory tile variant with the BatchNorm/ReLU/dropout backward folded in -----------------------------
-struct BnBwdArgs {
-  const float* dX; const float* mean; const float* invstd; const double* bsums;
-  const unsigned long long* rng; unsigned long long stream; double M; float p_drop; int training;
+// ---- shared-memory tile variant, BatchNorm backward folded in ---------------------------------------------------
+// The warp-per-row kernel above is instruction-bound (Nsight: ~30k warp instructions per 32-row tile and view,
+// lanes idle for fo_v = 80 / 140, a 5-step shuffle reduction per edge).  This variant splits the work of a tile into
+// phases whose thread mappings fit each job:
+//   stage : Z slab (cp.async) and dY slab -> shared memory.  dY = a*g - (c1 + xhat*c2) per element from
+//           g = dX*relu'*dropout (written by bn_bwd_partial, no Philox replay here), Y and the reduced BatchNorm sums:
+//           bn_bwd_apply and the dY round trip through memory disappear;
+//   dots  : d_e = dY_t . Z_j for every edge of the tile and d_self = dY_t . Z_t, 8 lanes per dot (4 dots per warp
+//           in flight, 3 shuffle steps);  c_t = dY_t . (Y_t - b) follows from them as sum_j A[t,j] d_(t,j);
+//   Q     : (row group, float4 channel) items, no cross-lane traffic:  Q_t = a_self dY_t + sum_e A[j->t] dY_j;
+//   hist  : d att / d self_r partials: one thread per table entry scans the tile's edges in order (deterministic).
+// Rows are processed in chunks whose edge lists fit the staged arrays (one chunk unless the graph is dense);
+// neighbours outside the tile are read through L2 (dY recomputed on the fly).
+struct BnFold {
+  const float* G; const float* mean; const float* invstd; const double* bsums; double M; int training;
 };
-inline size_t agg_bwd_tile_smem(int fo) { return (size_t)(2 * kStatRows * fo + 6 * fo) * sizeof(float); }
-
-// dY of 4 consecutive channels (c4-th float4 of the view slab) of row t: exactly bn_bwd_apply_vec_kernel's arithmetic.
-// sP = per-view parameter rows [mean | invstd | gamma | beta | S1/M | S2/M], each nc4 float4 long.
-__device__ __forceinline__ float4 dy_at(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, int nc4, int ld,
-                                        int off, int t, int c4, bool drop, float scale, const Philox& ph,
-                                        unsigned long long rng_off) {
-  const size_t idx = (size_t)t * ld + off + c4 * 4;
-  const float4 dx = __ldg(reinterpret_cast<const float4*>(bn.dX + idx)), y = __ldg(reinterpret_cast<const float4*>(Y + idx));
-  const float4 mu = sP[c4], is = sP[nc4 + c4], ga = sP[2 * nc4 + c4], be = sP[3 * nc4 + c4];
-  const float4 m1 = sP[4 * nc4 + c4], m2 = sP[5 * nc4 + c4];
-  float g[4], xh[4];
-  grad_through_act4(dx, y, mu, is, ga, be, drop, scale, ph, rng_off, bn.stream, (unsigned long long)idx, bn.p_drop, g, xh);
-  const float gi[4] = {ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w};
-  const float a1[4] = {m1.x, m1.y, m1.z, m1.w}, a2[4] = {m2.x, m2.y, m2.z, m2.w};
-  float r[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) r[u] = gi[u] * (bn.training ? (g[u] - a1[u] - xh[u] * a2[u]) : g[u]);
-  return make_float4(r[0], r[1], r[2], r[3]);
+constexpr int kTileMaxN = 4096;       // padded molecule size up to which the tile kernel's edge staging is sized
+inline int tile_edge_cap(int N) { return N > kTileEdgeCap ? ((N + 31) / 32) * 32 : kTileEdgeCap; }
+inline size_t agg_bwd_tile_smem(int fo, int cap) {
+  return (size_t)(2 * kStatRows * fo + 5 * fo) * sizeof(float) + (size_t)cap * 20 + (size_t)(cap + kStatRows) * 4;
 }
 
-// out-of-line copy for the rare neighbour outside the tile: keeps the Philox state out of the row loop's registers
-__device__ __noinline__ float4 dy_at_halo(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, int nc4, int ld,
-                                          int off, int t, int c4) {
-  const bool drop = bn.training && bn.p_drop > 0.0f;
-  const float scale = drop ? 1.0f / (1.0f - bn.p_drop) : 1.0f;
-  unsigned long long seed = 0, rng_off = 0;
-  if (drop) { seed = bn.rng[0]; rng_off = bn.rng[1]; }
-  const Philox ph(seed);
-  return dy_at(bn, Y, sP, nc4, ld, off, t, c4, drop, scale, ph, rng_off);
+__device__ __forceinline__ float4 dy_fold(const float4 g, const float4 y, const float4* sP, int nc4, int c4) {
+  const float4 mu = sP[c4], is = sP[nc4 + c4], a = sP[2 * nc4 + c4], c1 = sP[3 * nc4 + c4], c2 = sP[4 * nc4 + c4];
+  float4 r;
+  r.x = fmaf(a.x, g.x, -fmaf((y.x - mu.x) * is.x, c2.x, c1.x));
+  r.y = fmaf(a.y, g.y, -fmaf((y.y - mu.y) * is.y, c2.y, c1.y));
+  r.z = fmaf(a.z, g.z, -fmaf((y.z - mu.z) * is.z, c2.z, c1.z));
+  r.w = fmaf(a.w, g.w, -fmaf((y.w - mu.w) * is.w, c2.w, c1.w));
+  return r;
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
 }
 
-// dY slab of a tile -> shared memory (out of line: its Philox/parameter registers do not add to the row loop's)
-__device__ __noinline__ void stage_dy_slab(const BnBwdArgs& bn, const float* __restrict__ Y, const float4* sP, float4* sG,
-                                           int nc4, int ld, int off, int t0, int nrows) {
-  const bool drop = bn.training && bn.p_drop > 0.0f;
-  const float scale = drop ? 1.0f / (1.0f - bn.p_drop) : 1.0f;
-  unsigned long long seed = 0, rng_off = 0;
-  if (drop) { seed = bn.rng[0]; rng_off = bn.rng[1]; }
-  const Philox ph(seed);
-#pragma unroll 2
-  for (int i = threadIdx.x; i < nrows * nc4; i += kAggThreads) {
-    const int r = i / nc4, c = i - r * nc4;
-    sG[i] = dy_at(bn, Y, sP, nc4, ld, off, t0 + r, c, drop, scale, ph, rng_off);
-  }
-}
-
-// grid (row tiles, V); fo_v <= 128*NQ, float4 layout.  The CTA builds its kStatRows x fo_v slabs of Z (cp.async) and of
-// dY (computed from dX, Y and the reduced BatchNorm sums while staging -- bn_bwd_apply and the dY round trip through
-// memory disappear) in shared memory, prefetches the edge metadata of each warp's rows (one edge per lane), and then
-// runs the row loop of agg_bwd_kernel out of shared memory.  Neighbours outside the tile recompute dY on the fly.
-template <int NQ>
-__global__ void __launch_bounds__(kAggThreads, 3) agg_bwd_tile_kernel(PlanDev p, LayerDev L, BnBwdArgs bn,
+__global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, LayerDev L, BnFold bn,
                                                                    const float* __restrict__ Z, const float* __restrict__ Y,
                                                                    const float* __restrict__ ball,
                                                                    const float* __restrict__ sig,
                                                                    const float* __restrict__ invR, float* __restrict__ Q,
-                                                                   float* __restrict__ dpart) {
+                                                                   float* __restrict__ dpart, int cap) {
   extern __shared__ __align__(16) float tile_smem_b[];
-  __shared__ float s_hist[kAggWarps][EAGCN_SIG_STRIDE];
   __shared__ int s_rp[kStatRows + 1];
+  __shared__ float s_invR[kStatRows], s_ct[kStatRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot, nc4 = fo >> 2;
-  for (int r = 0; r < kAggRows; ++r) {   // slack rows [T, t_cap) of Q stay defined (zeros) for the split-K dW GEMM
-    const int t = t0 + warp * kAggRows + r;
+  for (int r = warp; r < kStatRows; r += kAggWarps) {   // slack rows [T, t_cap) of Q stay defined (zeros): dW GEMM input
+    const int t = t0 + r;
     if (t >= T && t < p.t_cap)
       for (int c = lane; c < nc4; c += 32) reinterpret_cast<float4*>(Q + (size_t)t * ld + off)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (t0 >= T) return;
   const int nrows = min(kStatRows, T - t0);
-  float4* sZ = reinterpret_cast<float4*>(tile_smem_b);   // [kStatRows][nc4]
-  float4* sG = sZ + kStatRows * nc4;                     // [kStatRows][nc4]  dY
-  float4* sP = sG + kStatRows * nc4;                     // [6][nc4]
-  for (int i = tid; i < nrows * nc4; i += kAggThreads) {
-    const int r = i / nc4, c = i - r * nc4;
-    cp_async16(sZ + i, Z + (size_t)(t0 + r) * ld + off + c * 4);
-  }
+  float4* sZ = reinterpret_cast<float4*>(tile_smem_b);       // [kStatRows][nc4]
+  float4* sG = sZ + kStatRows * nc4;                         // [kStatRows][nc4]   dY
+  float4* sP = sG + kStatRows * nc4;                         // [5][nc4]           mean | invstd | a | c1 | c2
+  float* s_aq = reinterpret_cast<float*>(sP + 5 * nc4);      // [cap]  A[j -> t] = sigma(rcode) / R_j
+  float* s_s = s_aq + cap;                                   // [cap]  sigma(code)
+  float* s_ds = s_s + cap;                                   // [cap]  d logit of the edge
+  int* s_j = reinterpret_cast<int*>(s_ds + cap);             // [cap]  neighbour row
+  int* s_cr = s_j + cap;                                     // [cap]  code | row-in-tile << 8
+  float* s_d = reinterpret_cast<float*>(s_cr + cap);         // [cap + kStatRows]  dots: rows first, then edges
+  // ---- stage: Z slab, BatchNorm fold parameters, row pointers ----
+  for (int r = warp; r < nrows; r += kAggWarps)
+    for (int c = lane; c < nc4; c += 32) cp_async16(sZ + r * nc4 + c, Z + (size_t)(t0 + r) * ld + off + c * 4);
   cp_async_commit();
   {
     float* P = reinterpret_cast<float*>(sP);
     for (int c = tid; c < fo; c += kAggThreads) {
-      P[c] = bn.mean[off + c]; P[fo + c] = bn.invstd[off + c];
-      P[2 * fo + c] = ball[ld + off + c]; P[3 * fo + c] = ball[2 * ld + off + c];
-      P[4 * fo + c] = bn.training ? (float)(bn.bsums[off + c] / bn.M) : 0.0f;
-      P[5 * fo + c] = bn.training ? (float)(bn.bsums[ld + off + c] / bn.M) : 0.0f;
+      const float is = bn.invstd[off + c], gi = ball[ld + off + c] * is;
+      P[c] = bn.mean[off + c]; P[fo + c] = is; P[2 * fo + c] = gi;
+      P[3 * fo + c] = bn.training ? gi * (float)(bn.bsums[off + c] / bn.M) : 0.0f;
+      P[4 * fo + c] = bn.training ? gi * (float)(bn.bsums[ld + off + c] / bn.M) : 0.0f;
     }
   }
+  const float* iR = invR + (size_t)v * p.t_cap;
   if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
-  for (int i = tid; i < kAggWarps * EAGCN_SIG_STRIDE; i += kAggThreads) (&s_hist[0][0])[i] = 0.0f;
+  if (tid < nrows) s_invR[tid] = iR[t0 + tid];
   __syncthreads();
+  // ---- stage: dY slab ----
+  for (int r = warp; r < nrows; r += kAggWarps) {
+    const size_t rowoff = (size_t)(t0 + r) * ld + off;
+    for (int c = lane; c < nc4; c += 32) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(bn.G + rowoff) + c);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(Y + rowoff) + c);
+      sG[r * nc4 + c] = dy_fold(g, y, sP, nc4, c);
+    }
+  }
   const float* sg = sig + v * EAGCN_SIG_STRIDE;
   const float sig_r = sg[256];
   const uint8_t* code = p.code + (size_t)v * p.e_cap;
   const uint8_t* rcode = p.rcode + (size_t)v * p.e_cap;
-  const float* iR = invR + (size_t)v * p.t_cap;
-  // edge metadata of this warp's rows: consecutive in the CSR arrays, one edge per lane when there are <= 32
-  const int wr0 = warp * kAggRows, wr1 = min(nrows, wr0 + kAggRows);
-  int ea = 0, eb = 0;
-  if (wr0 < nrows) { ea = s_rp[wr0]; eb = s_rp[wr1]; }
-  const bool pre = eb - ea <= 32;
-  const bool mine = pre && ea + lane < eb;
-  int j_p = 0, c_p = 0, rc_p = 0;
-  if (mine) { j_p = p.col[ea + lane]; c_p = code[ea + lane]; rc_p = rcode[ea + lane]; }
-  const float invR_l = wr0 + lane < wr1 ? iR[t0 + wr0 + lane] : 0.0f;
-  stage_dy_slab(bn, Y, sP, sG, nc4, ld, off, t0, nrows);
-  float s_p = 0.f, aq_p = 0.f;
-  if (mine) { s_p = sg[c_p]; aq_p = sg[rc_p] * iR[j_p]; }
+  const int nbins = L.chan[v] + 1;                           // codes 0..C_v (C_v: all-zero relation vector)
+  float hist = 0.0f;                                         // thread c < nbins: d att[c];  thread 255: d self_r
+  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
+  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
   cp_async_wait_all();
-  __syncthreads();
-  for (int r = wr0; r < wr1; ++r) {
-    const int t = t0 + r;
-    const int e0 = s_rp[r], e1 = s_rp[r + 1];
-    const float invR_t = __shfl_sync(0xffffffffu, invR_l, r - wr0);
-    // ---- c_t = dY_t . (Y_t - b),  d_self = dY_t . Z_t ----
-    float dyt[NQ][4];
-    float ct = 0.f, dself = 0.f;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int c4 = q * 32 + lane;
-      if (c4 < nc4) {
-        const float4 a = sG[r * nc4 + c4], z = sZ[r * nc4 + c4];
-        const float4 y = __ldg(reinterpret_cast<const float4*>(Y + (size_t)t * ld + off) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ball + off) + c4);
-        dyt[q][0] = a.x; dyt[q][1] = a.y; dyt[q][2] = a.z; dyt[q][3] = a.w;
-        ct = fmaf(a.x, y.x - b.x, ct); dself = fmaf(a.x, z.x, dself);
-        ct = fmaf(a.y, y.y - b.y, ct); dself = fmaf(a.y, z.y, dself);
-        ct = fmaf(a.z, y.z - b.z, ct); dself = fmaf(a.z, z.z, dself);
-        ct = fmaf(a.w, y.w - b.w, ct); dself = fmaf(a.w, z.w, dself);
-      } else { dyt[q][0] = dyt[q][1] = dyt[q][2] = dyt[q][3] = 0.0f; }
+  int r0 = 0;
+  while (r0 < nrows) {
+    // rows [r0, r1): the longest run whose edges fit the staged arrays (a single row always fits: deg < N <= cap)
+    int r1 = r0 + 1;
+    while (r1 < nrows && s_rp[r1 + 1] - s_rp[r0] <= cap) ++r1;
+    const int eA = s_rp[r0], nE = s_rp[r1] - eA, nR = r1 - r0;
+    __syncthreads();                                         // previous chunk fully consumed; slabs visible (first pass)
+    for (int i = tid; i < nE; i += kAggThreads) {
+      const int j = p.col[eA + i];
+      s_j[i] = j; s_s[i] = sg[code[eA + i]]; s_aq[i] = sg[rcode[eA + i]] * iR[j];
     }
-    ct = warp_sum(ct); dself = warp_sum(dself);
-    if (lane == 0) s_hist[warp][256] += (dself - ct) * invR_t * sig_r * (1.0f - sig_r);
-    const float a_self = sig_r * invR_t;
-    float qacc[NQ][4];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) { qacc[q][0] = qacc[q][1] = qacc[q][2] = qacc[q][3] = 0.0f; }
-    for (int ch = e0; ch < e1; ch += 32) {   // active rows have deg >= 1
-      int j_e = j_p, c_e = c_p, lo = e0 - ea;
-      float aq_e = aq_p, s_e = s_p;
-      if (!pre) {
-        const int e = ch + lane;
-        lo = 0; j_e = 0; c_e = 0; aq_e = 0.f; s_e = 0.f;
-        if (e < e1) { j_e = p.col[e]; c_e = code[e]; s_e = sg[c_e]; aq_e = sg[rcode[e]] * iR[j_e]; }
-      }
-      const int cnt = min(32, e1 - ch);
-      float d_e = 0.f;
-      for (int k = 0; k < cnt; ++k) {
-        const int j = __shfl_sync(0xffffffffu, j_e, lo + k);
-        const float aq = __shfl_sync(0xffffffffu, aq_e, lo + k);   // A_v[j -> t]: edge (j,t) has type rcode, row sum R_j
-        const int jr = j - t0;
-        const bool in_tile = (unsigned)jr < (unsigned)nrows;
-        float dot = 0.0f;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int c4 = q * 32 + lane;
-          if (c4 < nc4) {
-            float4 zj, gj;
-            if (in_tile) { zj = sZ[jr * nc4 + c4]; gj = sG[jr * nc4 + c4]; }
-            else {
-              zj = __ldg(reinterpret_cast<const float4*>(Z + (size_t)j * ld + off) + c4);
-              gj = dy_at_halo(bn, Y, sP, nc4, ld, off, j, c4);
-            }
-            dot = fmaf(dyt[q][0], zj.x, dot); qacc[q][0] = fmaf(aq, gj.x, qacc[q][0]);
-            dot = fmaf(dyt[q][1], zj.y, dot); qacc[q][1] = fmaf(aq, gj.y, qacc[q][1]);
-            dot = fmaf(dyt[q][2], zj.z, dot); qacc[q][2] = fmaf(aq, gj.z, qacc[q][2]);
-            dot = fmaf(dyt[q][3], zj.w, dot); qacc[q][3] = fmaf(aq, gj.w, qacc[q][3]);
+    if (tid < nR) {                                          // code | owning row, written by the row's thread
+      const int r = r0 + tid;
+      for (int e = s_rp[r] - eA; e < s_rp[r + 1] - eA; ++e) s_cr[e] = (int)code[eA + e] | (r << 8);
+    }
+    __syncthreads();
+    // ---- dots: index d < nR -> d_self of row r0+d, else edge d-nR; 8 lanes per dot ----
+    {
+      const int grp = tid >> 3, sub = tid & 7;
+      const int ndots = nR + nE;
+      for (int base = 0; base < ndots; base += kAggThreads / 8) {
+        const int d = base + grp;
+        float acc = 0.0f;
+        if (d < ndots) {
+          int r, j;
+          if (d < nR) { r = r0 + d; j = t0 + r; } else { r = s_cr[d - nR] >> 8; j = s_j[d - nR]; }
+          const float4* dy = sG + r * nc4;
+          const int jr = j - t0;
+          if ((unsigned)jr < (unsigned)nrows) {
+            const float4* z = sZ + jr * nc4;
+            for (int c = sub; c < nc4; c += 8) acc = dot4(dy[c], z[c], acc);
+          } else {
+            const float4* z = reinterpret_cast<const float4*>(Z + (size_t)j * ld + off);
+            for (int c = sub; c < nc4; c += 8) acc = dot4(dy[c], __ldg(z + c), acc);
           }
         }
-        dot = warp_sum(dot);
-        if (lane == lo + k) d_e += dot;
-      }
-      // attention-logit gradients of this chunk's edges, serialised -> deterministic
-      const float ds_e = (d_e - ct) * invR_t * s_e * (1.0f - s_e);
-      for (int k = 0; k < cnt; ++k) {
-        const float dsk = __shfl_sync(0xffffffffu, ds_e, lo + k);
-        const int ck = __shfl_sync(0xffffffffu, c_e, lo + k);
-        if (lane == 0) s_hist[warp][ck] += dsk;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (sub == 0 && d < ndots) s_d[d] = acc;
       }
     }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int c4 = q * 32 + lane;
-      if (c4 < nc4)
-        reinterpret_cast<float4*>(Q + (size_t)t * ld + off)[c4] =
-            make_float4(a_self * dyt[q][0] + qacc[q][0], a_self * dyt[q][1] + qacc[q][1],
-                        a_self * dyt[q][2] + qacc[q][2], a_self * dyt[q][3] + qacc[q][3]);
+    // ---- Q rows (independent of the dots): (row group, float4 channel) items ----
+    if (rg < nrg) {
+      for (int r = r0 + rg; r < r1; r += nrg) {
+        const float a_self = sig_r * s_invR[r];
+        const float4 gt = sG[r * nc4 + c4];
+        float q0 = a_self * gt.x, q1 = a_self * gt.y, q2 = a_self * gt.z, q3 = a_self * gt.w;
+        for (int e = s_rp[r] - eA; e < s_rp[r + 1] - eA; ++e) {
+          const float aq = s_aq[e];
+          const int j = s_j[e], jr = j - t0;
+          float4 gj;
+          if ((unsigned)jr < (unsigned)nrows) gj = sG[jr * nc4 + c4];
+          else {
+            const size_t ro = (size_t)j * ld + off;
+            gj = dy_fold(__ldg(reinterpret_cast<const float4*>(bn.G + ro) + c4),
+                         __ldg(reinterpret_cast<const float4*>(Y + ro) + c4), sP, nc4, c4);
+          }
+          q0 = fmaf(aq, gj.x, q0); q1 = fmaf(aq, gj.y, q1); q2 = fmaf(aq, gj.z, q2); q3 = fmaf(aq, gj.w, q3);
+        }
+        reinterpret_cast<float4*>(Q + (size_t)(t0 + r) * ld + off)[c4] = make_float4(q0, q1, q2, q3);
+      }
     }
+    __syncthreads();
+    // ---- per row: c_t = dY_t . (Y_t - b) = sum_j A[t,j] d_(t,j);  d logits of the row's edges and of its self loop ----
+    if (tid < nR) {
+      const int r = r0 + tid;
+      const float ir = s_invR[r], dself = s_d[tid];
+      const int ea = s_rp[r] - eA, eb = s_rp[r + 1] - eA;
+      float ct = sig_r * ir * dself;
+      for (int e = ea; e < eb; ++e) ct = fmaf(s_s[e] * ir, s_d[nR + e], ct);
+      for (int e = ea; e < eb; ++e) { const float se = s_s[e]; s_ds[e] = (s_d[nR + e] - ct) * ir * se * (1.0f - se); }
+      s_ct[r] = (dself - ct) * ir * sig_r * (1.0f - sig_r);
+    }
+    __syncthreads();
+    // ---- table-entry owners scan the chunk's edges in order ----
+    if (tid < nbins) {
+      for (int e = 0; e < nE; ++e) if ((s_cr[e] & 255) == tid) hist += s_ds[e];
+    } else if (tid == kAggThreads - 1) {
+      for (int r = r0; r < r1; ++r) hist += s_ct[r];
+    }
+    r0 = r1;
   }
-  __syncthreads();
   float* out = dpart + ((size_t)tile * L.V + v) * EAGCN_SIG_STRIDE;
-  for (int i = tid; i < EAGCN_SIG_STRIDE; i += kAggThreads) {
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < kAggWarps; ++w) a += s_hist[w][i];
-    out[i] = a;
-  }
+  out[tid] = tid < nbins ? hist : 0.0f;                      // entries 0..255 (nbins <= 255)
+  if (tid == kAggThreads - 1) out[256] = hist;
 }
 
-template <int NQ>
-static int launch_agg_bwd_tile(dim3 grid, size_t smem, cudaStream_t st, const PlanDev& p, const LayerDev& L,
-                               const BnBwdArgs& bn, const eagcn_work_t* w) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(agg_bwd_tile_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)agg_bwd_tile_smem(128 * NQ));
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  agg_bwd_tile_kernel<NQ><<<grid, kAggThreads, smem, st>>>(p, L, bn, (const float*)w->Z, (const float*)w->Y,
-                                                           (const float*)w->ball, (const float*)w->sig,
-                                                           (const float*)w->invR, (float*)w->Q, (float*)w->partial);
-  return 0;
-}
+static bool tile_bwd_ok(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w);
 
 // datt[v][i] = sum over live tiles (fixed order)
 __global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float* __restrict__ dpart,
@@ -630,6 +601,14 @@ static bool vec4_ok_b(const eagcn_layer_t* l) {
   return true;
 }
 
+static bool tile_bwd_ok(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w) {
+  if (agg_mode() != 0 || !vec4_ok_b(layer) || plan->N > kTileMaxN) return false;
+  int fo_max = 0;
+  for (int v = 0; v < layer->V; ++v) fo_max = (int)layer->fo[v] > fo_max ? (int)layer->fo[v] : fo_max;
+  if (fo_max > kTileMaxFo || agg_bwd_tile_smem(fo_max, tile_edge_cap((int)plan->N)) > 200 * 1024) return false;
+  return aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY) && aligned16(w->Z) && aligned16(w->Q) && aligned16(w->ball);
+}
+
 }  // namespace eagcn
 using namespace eagcn;
 
@@ -657,7 +636,8 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
                                                     C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,
-                                                    (unsigned long long)w->rng_stream);
+                                                    (unsigned long long)w->rng_stream,
+                                                    tile_bwd_ok(plan, layer, w) ? (float*)w->dY : nullptr);
     EAGCN_LAUNCH_CHECK();
   } else {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
@@ -696,20 +676,22 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   int fo_max = 0;
   for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
-  if (agg_mode() == 0 && vec4_ok_b(layer) && fo_max <= kTileMaxFo && aligned16(w->dX) && aligned16(w->Y) &&
-      aligned16(w->Z) && aligned16(w->Q) && aligned16(w->ball)) {
-    // fused: dY is produced inside the aggregation kernel's shared-memory tile (w->dY is not written)
-    BnBwdArgs bn{(const float*)w->dX, (const float*)w->mean, (const float*)w->invstd, (const double*)w->bsums,
-                 (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M, (float)w->p_drop,
-                 (w->training & 1) ? 1 : 0};
-    const size_t smem = agg_bwd_tile_smem(fo_max);
-    int lrc;
+  if (tile_bwd_ok(plan, layer, w)) {
+    // fused: w->dY holds g = dX*relu'*dropout (written by backward_a); dY itself only ever exists in shared memory
+    BnFold bn{(const float*)w->dY, (const float*)w->mean, (const float*)w->invstd, (const double*)w->bsums, M,
+              (w->training & 1) ? 1 : 0};
+    const int cap = tile_edge_cap(p.N);
+    const size_t smem = agg_bwd_tile_smem(fo_max, cap);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(agg_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      smem_set = smem;
+    }
     EAGCN_PROF("agg_bwd_kernel", st);
-    if (fo_max <= 128) lrc = launch_agg_bwd_tile<1>(grid, smem, st, p, L, bn, w);
-    else if (fo_max <= 256) lrc = launch_agg_bwd_tile<2>(grid, smem, st, p, L, bn, w);
-    else if (fo_max <= 384) lrc = launch_agg_bwd_tile<3>(grid, smem, st, p, L, bn, w);
-    else lrc = launch_agg_bwd_tile<4>(grid, smem, st, p, L, bn, w);
-    if (lrc) { ::eagcn::prof_end(); return lrc; }
+    agg_bwd_tile_kernel<<<grid, kAggThreads, smem, st>>>(p, L, bn, (const float*)w->Z, (const float*)w->Y,
+                                                         (const float*)w->ball, (const float*)w->sig,
+                                                         (const float*)w->invR, (float*)w->Q, (float*)w->partial, cap);
   } else {
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY)) {
     dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);

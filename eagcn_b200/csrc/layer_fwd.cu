@@ -205,7 +205,8 @@ inline size_t agg_fwd_tile_smem(int fo) { return (size_t)(kStatRows * fo + tile_
 // (every load in flight at once instead of one dependent L2 round trip per row and edge) together with the tile's
 // edge list, then (row group, float4 channel) items -- no idle lanes for fo_v = 80 / 140 -- walk the edges out of
 // shared memory.  Neighbours outside the tile (molecules straddling a tile boundary) are read through L2.
-// Y is bit-identical to the generic kernel (same operation order); the statistics partials are summed per row group.
+// The attention row sums are accumulated edge by edge (the generic kernel: lane-strided + shuffle tree), so Y can
+// differ from the generic kernel's in the last bit; the statistics partials are summed per row group.
 __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                                    const float* __restrict__ ball,
                                                                    const float* __restrict__ sig, float* __restrict__ Y,
@@ -213,8 +214,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
                                                                    int n_pad, int want_stats) {
   extern __shared__ __align__(16) float tile_smem[];
   __shared__ int s_rp[kStatRows + 1];
-  __shared__ float s_a[kTileEdgeCap];      // sigma(code), then a_e = sigma / R_row
-  __shared__ int s_j[kTileEdgeCap];
+  __shared__ float2 s_e[kTileEdgeCap];     // per staged edge: (a_e = sigma(code) / R_row, neighbour row as int bits)
   __shared__ float s_R[kStatRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
@@ -224,10 +224,8 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
   const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot, nc4 = fo >> 2;
   float4* sZ = reinterpret_cast<float4*>(tile_smem);             // [kStatRows][nc4]
   float* s_red = tile_smem + kStatRows * fo;                     // [row groups][2][fo]
-  for (int i = tid; i < nrows * nc4; i += kAggThreads) {
-    const int r = i / nc4, c = i - r * nc4;
-    cp_async16(sZ + i, Z + (size_t)(t0 + r) * ld + off + c * 4);
-  }
+  for (int r = warp; r < nrows; r += kAggWarps)
+    for (int c = lane; c < nc4; c += 32) cp_async16(sZ + r * nc4 + c, Z + (size_t)(t0 + r) * ld + off + c * 4);
   cp_async_commit();
   if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
   __syncthreads();
@@ -235,22 +233,23 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
   const float sig_r = sg[256];
   const uint8_t* code = p.code + (size_t)v * p.e_cap;
   const int e_lo = s_rp[0], ne = s_rp[nrows] - e_lo;
-  for (int i = tid; i < min(ne, kTileEdgeCap); i += kAggThreads) { s_a[i] = sg[code[e_lo + i]]; s_j[i] = p.col[e_lo + i]; }
+  for (int i = tid; i < min(ne, kTileEdgeCap); i += kAggThreads)
+    s_e[i] = make_float2(sg[code[e_lo + i]], __int_as_float(p.col[e_lo + i]));
   __syncthreads();
-  // attention row sums (layers.py:84,87): warp w owns rows w*kAggRows .. ; lane-strided partial sums like the generic kernel
-  for (int r = warp * kAggRows; r < min(nrows, (warp + 1) * kAggRows); ++r) {
-    const int a0 = s_rp[r] - e_lo, a1 = s_rp[r + 1] - e_lo;
+  // attention row sums (layers.py:84,87): one thread per row walks its (few) edges in order
+  if (tid < nrows) {
+    const int a0 = s_rp[tid] - e_lo, a1 = s_rp[tid + 1] - e_lo;
     float sw = 0.0f;
-    for (int e = a0 + lane; e < a1; e += 32) sw += e < kTileEdgeCap ? s_a[e] : sg[code[e_lo + e]];
-    sw = warp_sum(sw);
+    for (int e = a0; e < a1; ++e) sw += e < kTileEdgeCap ? s_e[e].x : sg[code[e_lo + e]];
     const float R = sw + sig_r + (float)(n_pad - (a1 - a0)) * EAGCN_TINY;
-    if (lane == 0) { invR[(size_t)v * p.t_cap + t0 + r] = 1.0f / R; s_R[r] = R; }
-    for (int e = a0 + lane; e < min(a1, kTileEdgeCap); e += 32) s_a[e] = s_a[e] / R;
+    invR[(size_t)v * p.t_cap + t0 + tid] = 1.0f / R;
+    s_R[tid] = R;
+    for (int e = a0; e < min(a1, kTileEdgeCap); ++e) s_e[e].x = s_e[e].x / R;
   }
   cp_async_wait_all();
   __syncthreads();
-  const int nrg = kAggThreads / nc4;
-  const int rg = tid / nc4, c4 = tid - rg * nc4;
+  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
+  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (rg < nrg) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(ball + off) + c4);
@@ -262,7 +261,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
       const int a0 = s_rp[r] - e_lo, a1 = s_rp[r + 1] - e_lo;
       for (int e = a0; e < a1; ++e) {
         float a; int j;
-        if (e < kTileEdgeCap) { a = s_a[e]; j = s_j[e]; }
+        if (e < kTileEdgeCap) { const float2 ed = s_e[e]; a = ed.x; j = __float_as_int(ed.y); }
         else { a = sg[code[e_lo + e]] / R; j = p.col[e_lo + e]; }
         const int jr = j - t0;
         const float4 zj = (unsigned)jr < (unsigned)nrows

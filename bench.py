@@ -188,6 +188,7 @@ def run_b200(args):
     model = build_model(dev)
     if args.head != "auto":
         model.fused_head = args.head == "fused"
+        model.head_bn = "torch" if args.head == "torch" else "cuda"
     NB = args.nbatches
     slots = []
     for i in range(NB):
@@ -516,7 +517,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
-                       "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else "stock PyTorch ops",
+                       "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else
+                       ("library GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
                        "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],

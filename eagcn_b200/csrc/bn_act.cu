@@ -1,0 +1,147 @@
+// Fused BatchNorm1d (+ ReLU) (+ dropout) over a [B, C] matrix, forward and backward: the element-wise chain between
+// the dense layers of the read-out head (reference models.py:112 Graph_BN, :114-116 relu(bn_den1) + dropout,
+// :119 relu(bn_den2)).  Stock PyTorch spends 4 kernels per BatchNorm direction plus one per activation on these
+// 256-row matrices (launch-bound: ~85 us per step on the Tox21 shape); here one CTA owns 32 channels for ALL rows, so
+// statistics (two-pass: mean, then centred sum of squares -- the same algorithm as torch's batch_norm), normalisation,
+// activation and dropout are one launch per direction.  The slab (B x 32 floats) is re-read from L1/L2 per pass.
+#include "common.cuh"
+
+namespace eagcn {
+
+constexpr int kBnWarps = 8;
+
+// column sums over the 8 row-strided warps, fixed order; result valid in every thread of the column
+__device__ __forceinline__ float bn_col_reduce(float v, float (*s)[32], int warp, int lane) {
+  s[warp][lane] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int w = 0; w < kBnWarps; ++w) t += s[w][lane];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
+    const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ run_mean, float* __restrict__ run_var, long long* __restrict__ nbt, float* __restrict__ mean_out,
+    float* __restrict__ invstd_out, int B, int C, int training, int relu, float p_drop, const unsigned long long* rng,
+    unsigned long long stream, float momentum, float eps) {
+  __shared__ float s[kBnWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < C;
+  float mean, invstd;
+  if (training) {
+    float a = 0.0f;
+    if (act) {
+#pragma unroll 4
+      for (int r = warp; r < B; r += kBnWarps) a += __ldg(x + (size_t)r * C + c);
+    }
+    mean = bn_col_reduce(a, s, warp, lane) / (float)B;
+    float q = 0.0f;
+    if (act) {
+#pragma unroll 4
+      for (int r = warp; r < B; r += kBnWarps) { const float d = __ldg(x + (size_t)r * C + c) - mean; q = fmaf(d, d, q); }
+    }
+    const float var = bn_col_reduce(q, s, warp, lane) / (float)B;
+    invstd = 1.0f / sqrtf(var + eps);
+    if (warp == 0 && act) {                                  // running statistics like nn.BatchNorm1d (unbiased variance)
+      run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.0f - momentum) * run_var[c] + momentum * var * ((float)B / (float)(B > 1 ? B - 1 : 1));
+    }
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+  } else {
+    mean = act ? run_mean[c] : 0.0f;
+    invstd = act ? 1.0f / sqrtf(run_var[c] + eps) : 0.0f;
+  }
+  if (!act) return;
+  if (warp == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
+  const float g = gamma[c], b = beta[c];
+  const bool drop = training && p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+#pragma unroll 4
+  for (int r = warp; r < B; r += kBnWarps) {
+    const size_t idx = (size_t)r * C + c;
+    float z = (__ldg(x + idx) - mean) * invstd * g + b;
+    if (relu) z = fmaxf(z, 0.0f);
+    if (drop) z = dropout_keep(ph, off, stream, (unsigned long long)idx, p_drop) ? z * scale : 0.0f;
+    y[idx] = z;
+  }
+}
+
+__global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int training, int relu,
+    float p_drop, const unsigned long long* rng, unsigned long long stream) {
+  __shared__ float s[kBnWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < C;
+  const float mean = act ? mean_in[c] : 0.0f, invstd = act ? invstd_in[c] : 0.0f;
+  const float g = act ? gamma[c] : 0.0f, b = act ? beta[c] : 0.0f;
+  const bool drop = training && p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+  // gradient reaching the BatchNorm output of element (r, c): dropout and ReLU replayed from x
+  auto grad_at = [&](int r, float& xh) {
+    const size_t idx = (size_t)r * C + c;
+    xh = (__ldg(x + idx) - mean) * invstd;
+    float gr = __ldg(dy + idx);
+    if (drop) gr = dropout_keep(ph, off, stream, (unsigned long long)idx, p_drop) ? gr * scale : 0.0f;
+    if (relu && !(xh * g + b > 0.0f)) gr = 0.0f;
+    return gr;
+  };
+  float s1 = 0.0f, s2 = 0.0f;
+  if (act)
+    for (int r = warp; r < B; r += kBnWarps) { float xh; const float gr = grad_at(r, xh); s1 += gr; s2 = fmaf(gr, xh, s2); }
+  s1 = bn_col_reduce(s1, s, warp, lane);
+  s2 = bn_col_reduce(s2, s, warp, lane);
+  if (!act) return;
+  if (warp == 0) { dbeta[c] = s1; dgamma[c] = s2; }
+  const float m1 = s1 / (float)B, m2 = s2 / (float)B, gi = g * invstd;
+  for (int r = warp; r < B; r += kBnWarps) {
+    float xh;
+    const float gr = grad_at(r, xh);
+    dx[(size_t)r * C + c] = gi * (training ? (gr - m1 - xh * m2) : gr);
+  }
+}
+
+}  // namespace eagcn
+using namespace eagcn;
+
+extern "C" int eagcn_bn_act_forward(const void* x, void* y, const void* gamma, const void* beta, void* run_mean,
+                                    void* run_var, void* nbt, void* mean_out, void* invstd_out, int64_t B, int64_t C,
+                                    int training, int relu, double p_drop, const void* rng, int64_t rng_stream,
+                                    double momentum, double eps, void* stream) {
+  if (!x || !y || !gamma || !beta || !run_mean || !run_var || !mean_out || !invstd_out || B <= 0 || C <= 0)
+    return EAGCN_E_ARG;
+  if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
+  EAGCN_PROF("bn_act_fwd_kernel", stream);
+  bn_act_fwd_kernel<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+      (const float*)x, (float*)y, (const float*)gamma, (const float*)beta, (float*)run_mean, (float*)run_var,
+      (long long*)nbt, (float*)mean_out, (float*)invstd_out, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
+      (const unsigned long long*)rng, (unsigned long long)rng_stream, (float)momentum, (float)eps);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eagcn_bn_act_backward(const void* x, const void* dy, const void* gamma, const void* beta, const void* mean,
+                                     const void* invstd, void* dx, void* dgamma, void* dbeta, int64_t B, int64_t C,
+                                     int training, int relu, double p_drop, const void* rng, int64_t rng_stream,
+                                     void* stream) {
+  if (!x || !dy || !gamma || !beta || !mean || !invstd || !dx || !dgamma || !dbeta || B <= 0 || C <= 0) return EAGCN_E_ARG;
+  if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
+  EAGCN_PROF("bn_act_bwd_kernel", stream);
+  bn_act_bwd_kernel<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+      (const float*)x, (const float*)dy, (const float*)gamma, (const float*)beta, (const float*)mean, (const float*)invstd,
+      (float*)dx, (float*)dgamma, (float*)dbeta, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
+      (const unsigned long long*)rng, (unsigned long long)rng_stream);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}

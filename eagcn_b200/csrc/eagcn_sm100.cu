@@ -7,6 +7,7 @@
 #include "layer_bwd.cu"
 #include "attention.cu"
 #include "head.cu"
+#include "bn_act.cu"
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
 extern "C" int eagcn_set_gemm_mode(int mode) {

@@ -407,6 +407,55 @@ class _HeadFn(torch.autograd.Function):
         return (None, None, dx0, dW[0], dW[1], dW[2], dg[0], db[0], dg[1], db[1], dg[2], db[2])
 
 
+class _BnActFn(torch.autograd.Function):
+    """dropout(relu(BatchNorm1d(x))) in one kernel per direction (models.py:112, 114-116, 119)."""
+
+    @staticmethod
+    def forward(ctx, cfg, bufs, x, gamma, beta):
+        training, relu, p_drop, rng_stream, eps, momentum = cfg
+        if not x.is_cuda:
+            raise EagcnError("eagcn_b200.bn_act is CUDA-only (sm_100a, no CPU fallback)")
+        x = x.contiguous()
+        B, C = x.shape
+        rm, rv, nbt = bufs
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=_F32, device=x.device)
+        invstd = torch.empty(C, dtype=_F32, device=x.device)
+        rng = RngState.get(x.device)
+        snap = rng.state.clone() if (training and p_drop > 0.0) else None
+        g, b = gamma.detach().contiguous(), beta.detach().contiguous()
+        check(lib().eagcn_bn_act_forward(ptr(x), ptr(y), ptr(g), ptr(b), ptr(rm), ptr(rv),
+                                         ptr(nbt) if nbt is not None else None, ptr(mean), ptr(invstd), B, C,
+                                         int(training), int(relu), float(p_drop), ptr(snap) if snap is not None else None,
+                                         int(rng_stream), float(momentum), float(eps), _stream()), "eagcn_bn_act_forward")
+        if snap is not None:
+            rng.advance()
+        ctx.cfg = cfg
+        ctx.saved = (x, g, b, mean, invstd, snap)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        training, relu, p_drop, rng_stream, eps, momentum = ctx.cfg
+        x, g, b, mean, invstd, snap = ctx.saved
+        B, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg, db = torch.empty_like(g), torch.empty_like(b)
+        check(lib().eagcn_bn_act_backward(ptr(x), ptr(dy), ptr(g), ptr(b), ptr(mean), ptr(invstd), ptr(dx), ptr(dg),
+                                          ptr(db), B, C, int(training), int(relu), float(p_drop),
+                                          ptr(snap) if snap is not None else None, int(rng_stream), _stream()),
+              "eagcn_bn_act_backward")
+        return None, None, dx, dg, db
+
+
+def bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):
+    """``F.dropout(F.relu(bn(x)), p_drop, training)`` (each stage optional) for an ``nn.BatchNorm1d`` ``bn`` on [B, C]."""
+    momentum = bn.momentum if bn.momentum is not None else 0.1
+    cfg = (bool(training), bool(relu), float(p_drop), int(rng_stream), float(bn.eps), float(momentum))
+    return _BnActFn.apply(cfg, (bn.running_mean, bn.running_var, bn.num_batches_tracked), x, bn.weight, bn.bias)
+
+
 def dense_head(x0, weights, bns, training, p_drop, rng_stream=1000):
     """weights: (W1, W2, W3); bns: three nn.BatchNorm1d.  Returns (out, graph_representation)."""
     params = tuple(weights) + tuple(t for bn in bns for t in (bn.weight, bn.bias))

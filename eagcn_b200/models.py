@@ -88,6 +88,7 @@ class EAGCNStack(nn.Module):
         # slower than the ~35 stock PyTorch launches it replaces at B = 256 (un-pipelined operand loads), so it is
         # opt-in until its tile loop is software-pipelined.
         self.fused_head = False
+        self.head_bn = "cuda"          # 'cuda': fused BatchNorm/ReLU/dropout kernels; 'torch': stock modules
         fin = n_afeat
         self.n_layers = len(widths)
         for l, w in enumerate(widths):
@@ -127,6 +128,17 @@ class EAGCNStack(nn.Module):
             x, graph_representation = EF.dense_head(x, (self.den1.weight, self.den2.weight, self.den3.weight),
                                                     (self.Graph_BN, self.bn_den1, self.bn_den2), self.training,
                                                     float(self.dropout))              # models.py:112-120
+            return x, atom_representations, graph_representation
+        bns = (self.Graph_BN, self.bn_den1, self.bn_den2)
+        if self.head_bn == "cuda" and all(bn.affine and bn.track_running_stats and bn.momentum is not None for bn in bns):
+            # library GEMMs between fused BatchNorm(+ReLU)(+dropout) kernels: 3 + 3 launches instead of ~25
+            x = EF.bn_act(x, self.Graph_BN, self.training)                          # models.py:112
+            x = self.den1(x)
+            x = EF.bn_act(x, self.bn_den1, self.training, relu=True, p_drop=float(self.dropout))   # models.py:114-116
+            x = self.den2(x)
+            graph_representation = x
+            x = EF.bn_act(x, self.bn_den2, self.training, relu=True)                # models.py:119
+            x = self.den3(x)
             return x, atom_representations, graph_representation
         x = self.Graph_BN(x)                                                        # models.py:112
         x = self.den1(x)

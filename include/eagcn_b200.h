@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 9
+#define EAGCN_ABI_VERSION 10
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -209,6 +209,20 @@ typedef struct eagcn_head {
 int64_t eagcn_head_part_floats(int64_t B, int64_t F, int64_t D1, int64_t D2);
 int eagcn_head_forward(const eagcn_head_t* args, void* stream);
 int eagcn_head_backward(const eagcn_head_t* args, void* stream);
+
+/* --- fused BatchNorm1d (+ReLU)(+dropout) of the read-out head ---------------------------------- */
+/* y[B,C] = dropout(relu(BatchNorm1d(x)))  -- reference models.py:112 (Graph_BN: relu = 0, p_drop = 0), :114-116
+ * (relu(bn_den1(x)) then F.dropout), :119 (relu(bn_den2(x))).  training != 0: batch statistics (two-pass), running
+ * statistics / num_batches_tracked updated like nn.BatchNorm1d; training == 0: running statistics.  mean_out /
+ * invstd_out [C] receive the statistics used (saved for backward).  Dropout keeps element i iff the library's Philox
+ * stream (rng = device int64 {seed, offset}, rng_stream) says so for flat index i (eagcn_dropout_mask_flat).          */
+int eagcn_bn_act_forward(const void* x, void* y, const void* gamma, const void* beta, void* run_mean, void* run_var,
+                         void* nbt, void* mean_out, void* invstd_out, int64_t B, int64_t C, int training, int relu,
+                         double p_drop, const void* rng, int64_t rng_stream, double momentum, double eps, void* stream);
+/* autograd replay of the above: dx [B,C], dgamma [C], dbeta [C] from dy and the saved x, mean, invstd.             */
+int eagcn_bn_act_backward(const void* x, const void* dy, const void* gamma, const void* beta, const void* mean,
+                          const void* invstd, void* dx, void* dgamma, void* dbeta, int64_t B, int64_t C, int training,
+                          int relu, double p_drop, const void* rng, int64_t rng_stream, void* stream);
 
 /* --- projection GEMM engine ------------------------------------------------------------------ */
 /* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned

@@ -554,3 +554,53 @@ def test_agg_engines_agree(kind, B, fin, fo, training, p):
     for k in pg:
         denom = max(float(pg[k].abs().max()), 1e-3 * scale)
         assert float((pt[k] - pg[k]).abs().max()) / denom <= 2e-5 * loose, k
+
+
+# ------------------------------------------------------------------ fused BatchNorm(+ReLU)(+dropout) of the head
+@pytest.mark.parametrize("B,C,training,relu,p", [
+    (256, 1400, True, False, 0.0),      # Graph_BN (models.py:112)
+    (256, 256, True, True, 0.3),        # relu(bn_den1) + dropout (models.py:114-116)
+    (256, 64, True, True, 0.0),         # relu(bn_den2) (models.py:119)
+    (37, 45, True, True, 0.5),          # ragged sizes
+    (64, 96, False, True, 0.3),         # eval: running statistics, dropout off
+    (2, 8, True, False, 0.0),
+])
+def test_bn_act_vs_torch(B, C, training, relu, p):
+    """eagcn_bn_act_forward/backward against stock torch fp32 ops (batch_norm -> relu -> dropout with the same keep
+    mask), values, running statistics and all gradients."""
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = (torch.randn(B, C, generator=g) * 2.0 + 0.7).to(dev)
+    bn = torch.nn.BatchNorm1d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ref_bn = torch.nn.BatchNorm1d(C).to(dev)
+    ref_bn.load_state_dict(bn.state_dict())
+    bn.train(training); ref_bn.train(training)
+    EF.manual_seed(99)
+    rng_state = EF.RngState.get(dev).state.clone()
+    xa = x.clone().requires_grad_(True)
+    y = EF.bn_act(xa, bn, training, relu=relu, p_drop=p, rng_stream=1000)
+    xb = x.clone().requires_grad_(True)
+    z = ref_bn(xb)
+    if relu:
+        z = torch.relu(z)
+    if training and p > 0:
+        keep = EF.dropout_keep_mask_flat(rng_state, 1000, p, B * C).view(B, C).float()
+        z = z * keep / (1.0 - p)
+        frac = float(keep.mean())
+        assert abs(frac - (1.0 - p)) < 0.08
+    assert rel_err(y, z) <= TOL
+    assert rel_err(bn.running_mean, ref_bn.running_mean) <= TOL
+    assert rel_err(bn.running_var, ref_bn.running_var) <= TOL
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
+    R = torch.randn(B, C, generator=g).to(dev)
+    (y * R).sum().backward()
+    (z * R).sum().backward()
+    assert rel_err(xa.grad, xb.grad) <= 2 * TOL
+    assert rel_err(bn.weight.grad, ref_bn.weight.grad) <= 2 * TOL
+    assert rel_err(bn.bias.grad, ref_bn.bias.grad) <= 2 * TOL

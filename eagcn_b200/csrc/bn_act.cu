@@ -3,14 +3,16 @@
 // :119 relu(bn_den2)).  Stock PyTorch spends 4 kernels per BatchNorm direction plus one per activation on these
 // 256-row matrices (launch-bound: ~85 us per step on the Tox21 shape); here one CTA owns 32 channels for ALL rows, so
 // statistics (two-pass: mean, then centred sum of squares -- the same algorithm as torch's batch_norm), normalisation,
-// activation and dropout are one launch per direction.  The slab (B x 32 floats) is re-read from L1/L2 per pass.
+// activation and dropout are one launch per direction.  With B <= 256 a thread keeps its 8 rows in registers: one pass
+// over memory (the first version looped 32 rows per thread three times and was latency-bound at ~10 us per launch).
 #include "common.cuh"
 
 namespace eagcn {
 
-constexpr int kBnWarps = 8;
+constexpr int kBnWarps = 32;          // one CTA = 32 channels x 32 row lanes (1024 threads)
+constexpr int kBnRegRows = 8;         // rows a thread keeps in registers: B <= 256 is a single pass over memory
 
-// column sums over the 8 row-strided warps, fixed order; result valid in every thread of the column
+// column sums over the row lanes, fixed order; result valid in every thread of the column
 __device__ __forceinline__ float bn_col_reduce(float v, float (*s)[32], int warp, int lane) {
   s[warp][lane] = v;
   __syncthreads();
@@ -21,6 +23,9 @@ __device__ __forceinline__ float bn_col_reduce(float v, float (*s)[32], int warp
   return t;
 }
 
+// REG: the thread's rows (warp, warp+32, ...) live in registers (B <= 32*kBnRegRows); otherwise every pass re-reads
+// the slab from L1/L2.
+template <bool REG>
 __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
     const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* __restrict__ run_mean, float* __restrict__ run_var, long long* __restrict__ nbt, float* __restrict__ mean_out,
@@ -30,17 +35,30 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane;
   const bool act = c < C;
+  float xv[kBnRegRows];
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < kBnRegRows; ++k) {
+      const int r = warp + k * kBnWarps;
+      xv[k] = (act && r < B) ? __ldg(x + (size_t)r * C + c) : 0.0f;
+    }
+  }
   float mean, invstd;
   if (training) {
     float a = 0.0f;
-    if (act) {
-#pragma unroll 4
+    if (REG) {
+#pragma unroll
+      for (int k = 0; k < kBnRegRows; ++k) a += xv[k];               // rows >= B hold 0
+    } else if (act) {
       for (int r = warp; r < B; r += kBnWarps) a += __ldg(x + (size_t)r * C + c);
     }
     mean = bn_col_reduce(a, s, warp, lane) / (float)B;
     float q = 0.0f;
-    if (act) {
-#pragma unroll 4
+    if (REG) {
+#pragma unroll
+      for (int k = 0; k < kBnRegRows; ++k)
+        if (warp + k * kBnWarps < B) { const float d = xv[k] - mean; q = fmaf(d, d, q); }
+    } else if (act) {
       for (int r = warp; r < B; r += kBnWarps) { const float d = __ldg(x + (size_t)r * C + c) - mean; q = fmaf(d, d, q); }
     }
     const float var = bn_col_reduce(q, s, warp, lane) / (float)B;
@@ -62,16 +80,22 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
   unsigned long long seed = 0, off = 0;
   if (drop) { seed = rng[0]; off = rng[1]; }
   const Philox ph(seed);
-#pragma unroll 4
-  for (int r = warp; r < B; r += kBnWarps) {
+  auto emit = [&](int r, float xr) {
     const size_t idx = (size_t)r * C + c;
-    float z = (__ldg(x + idx) - mean) * invstd * g + b;
+    float z = (xr - mean) * invstd * g + b;
     if (relu) z = fmaxf(z, 0.0f);
     if (drop) z = dropout_keep(ph, off, stream, (unsigned long long)idx, p_drop) ? z * scale : 0.0f;
     y[idx] = z;
+  };
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < kBnRegRows; ++k) { const int r = warp + k * kBnWarps; if (r < B) emit(r, xv[k]); }
+  } else {
+    for (int r = warp; r < B; r += kBnWarps) emit(r, __ldg(x + (size_t)r * C + c));
   }
 }
 
+template <bool REG>
 __global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
@@ -97,18 +121,36 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
     if (relu && !(xh * g + b > 0.0f)) gr = 0.0f;
     return gr;
   };
+  float gv[kBnRegRows], hv[kBnRegRows];
   float s1 = 0.0f, s2 = 0.0f;
-  if (act)
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < kBnRegRows; ++k) {
+      const int r = warp + k * kBnWarps;
+      gv[k] = 0.0f; hv[k] = 0.0f;
+      if (act && r < B) gv[k] = grad_at(r, hv[k]);
+      s1 += gv[k]; s2 = fmaf(gv[k], hv[k], s2);
+    }
+  } else if (act) {
     for (int r = warp; r < B; r += kBnWarps) { float xh; const float gr = grad_at(r, xh); s1 += gr; s2 = fmaf(gr, xh, s2); }
+  }
   s1 = bn_col_reduce(s1, s, warp, lane);
   s2 = bn_col_reduce(s2, s, warp, lane);
   if (!act) return;
   if (warp == 0) { dbeta[c] = s1; dgamma[c] = s2; }
   const float m1 = s1 / (float)B, m2 = s2 / (float)B, gi = g * invstd;
-  for (int r = warp; r < B; r += kBnWarps) {
-    float xh;
-    const float gr = grad_at(r, xh);
-    dx[(size_t)r * C + c] = gi * (training ? (gr - m1 - xh * m2) : gr);
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < kBnRegRows; ++k) {
+      const int r = warp + k * kBnWarps;
+      if (r < B) dx[(size_t)r * C + c] = gi * (training ? (gv[k] - m1 - hv[k] * m2) : gv[k]);
+    }
+  } else {
+    for (int r = warp; r < B; r += kBnWarps) {
+      float xh;
+      const float gr = grad_at(r, xh);
+      dx[(size_t)r * C + c] = gi * (training ? (gr - m1 - xh * m2) : gr);
+    }
   }
 }
 
@@ -123,7 +165,8 @@ extern "C" int eagcn_bn_act_forward(const void* x, void* y, const void* gamma, c
     return EAGCN_E_ARG;
   if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
   EAGCN_PROF("bn_act_fwd_kernel", stream);
-  bn_act_fwd_kernel<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+  auto kern = B <= kBnWarps * kBnRegRows ? bn_act_fwd_kernel<true> : bn_act_fwd_kernel<false>;
+  kern<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
       (const float*)x, (float*)y, (const float*)gamma, (const float*)beta, (float*)run_mean, (float*)run_var,
       (long long*)nbt, (float*)mean_out, (float*)invstd_out, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
       (const unsigned long long*)rng, (unsigned long long)rng_stream, (float)momentum, (float)eps);
@@ -138,7 +181,8 @@ extern "C" int eagcn_bn_act_backward(const void* x, const void* dy, const void* 
   if (!x || !dy || !gamma || !beta || !mean || !invstd || !dx || !dgamma || !dbeta || B <= 0 || C <= 0) return EAGCN_E_ARG;
   if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
   EAGCN_PROF("bn_act_bwd_kernel", stream);
-  bn_act_bwd_kernel<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+  auto kern = B <= kBnWarps * kBnRegRows ? bn_act_bwd_kernel<true> : bn_act_bwd_kernel<false>;
+  kern<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
       (const float*)x, (const float*)dy, (const float*)gamma, (const float*)beta, (const float*)mean, (const float*)invstd,
       (float*)dx, (float*)dgamma, (float*)dbeta, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
       (const unsigned long long*)rng, (unsigned long long)rng_stream);

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDe
 // The warp-per-row kernel above is instruction-bound (Nsight: ~30k warp instructions per 32-row tile and view,
 // lanes idle for fo_v = 80 / 140, a 5-step shuffle reduction per edge).  This variant splits the work of a tile into
 // phases whose thread mappings fit each job:
-//   stage : Z slab (cp.async) and dY slab -> shared memory.  dY = a*g - (c1 + xhat*c2) per element from
+//   stage : Z slab (one bulk/TMA copy per row) and dY slab -> shared memory.  dY = a*g - (c1 + xhat*c2) per element from
 //           g = dX*relu'*dropout (written by bn_bwd_partial, no Philox replay here), Y and the reduced BatchNorm sums:
 //           bn_bwd_apply and the dY round trip through memory disappear;
 //   dots  : d_e = dY_t . Z_j for every edge of the tile and d_self = dY_t . Z_t, 8 lanes per dot (4 dots per warp
@@ -395,7 +395,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
 }
 
-__global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, LayerDev L, BnFold bn,
+__global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_tile_kernel(PlanDev p, LayerDev L, BnFold bn,
                                                                    const float* __restrict__ Z, const float* __restrict__ Y,
                                                                    const float* __restrict__ ball,
                                                                    const float* __restrict__ sig,
@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, La
   extern __shared__ __align__(16) float tile_smem_b[];
   __shared__ int s_rp[kStatRows + 1];
   __shared__ float s_invR[kStatRows], s_ct[kStatRows];
+  __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -425,9 +426,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, La
   int* s_cr = s_j + cap;                                     // [cap]  code | row-in-tile << 8
   float* s_d = reinterpret_cast<float*>(s_cr + cap);         // [cap + kStatRows]  dots: rows first, then edges
   // ---- stage: Z slab, BatchNorm fold parameters, row pointers ----
-  for (int r = warp; r < nrows; r += kAggWarps)
-    for (int c = lane; c < nc4; c += 32) cp_async16(sZ + r * nc4 + c, Z + (size_t)(t0 + r) * ld + off + c * 4);
-  cp_async_commit();
+  slab_load(sZ, Z, t0, nrows, ld, off, fo, &s_bar);
   {
     float* P = reinterpret_cast<float*>(sP);
     for (int c = tid; c < fo; c += kAggThreads) {
@@ -441,13 +440,22 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, La
   if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
   if (tid < nrows) s_invR[tid] = iR[t0 + tid];
   __syncthreads();
-  // ---- stage: dY slab ----
-  for (int r = warp; r < nrows; r += kAggWarps) {
-    const size_t rowoff = (size_t)(t0 + r) * ld + off;
-    for (int c = lane; c < nc4; c += 32) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(bn.G + rowoff) + c);
-      const float4 y = __ldg(reinterpret_cast<const float4*>(Y + rowoff) + c);
-      sG[r * nc4 + c] = dy_fold(g, y, sP, nc4, c);
+  // ---- stage: dY slab; a thread keeps one float4 channel's fold parameters in registers and walks rows ----
+  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
+  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
+  if (rg < nrg) {
+    const float4 mu = sP[c4], is = sP[nc4 + c4], a = sP[2 * nc4 + c4], c1 = sP[3 * nc4 + c4], c2 = sP[4 * nc4 + c4];
+#pragma unroll 2
+    for (int r = rg; r < nrows; r += nrg) {
+      const size_t rowoff = (size_t)(t0 + r) * ld + off;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(bn.G + rowoff) + c4);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(Y + rowoff) + c4);
+      float4 o;
+      o.x = fmaf(a.x, g.x, -fmaf((y.x - mu.x) * is.x, c2.x, c1.x));
+      o.y = fmaf(a.y, g.y, -fmaf((y.y - mu.y) * is.y, c2.y, c1.y));
+      o.z = fmaf(a.z, g.z, -fmaf((y.z - mu.z) * is.z, c2.z, c1.z));
+      o.w = fmaf(a.w, g.w, -fmaf((y.w - mu.w) * is.w, c2.w, c1.w));
+      sG[r * nc4 + c4] = o;
     }
   }
   const float* sg = sig + v * EAGCN_SIG_STRIDE;
@@ -456,14 +464,15 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_tile_kernel(PlanDev p, La
   const uint8_t* rcode = p.rcode + (size_t)v * p.e_cap;
   const int nbins = L.chan[v] + 1;                           // codes 0..C_v (C_v: all-zero relation vector)
   float hist = 0.0f;                                         // thread c < nbins: d att[c];  thread 255: d self_r
-  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
-  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
-  cp_async_wait_all();
+  slab_wait(&s_bar);
   int r0 = 0;
   while (r0 < nrows) {
     // rows [r0, r1): the longest run whose edges fit the staged arrays (a single row always fits: deg < N <= cap)
-    int r1 = r0 + 1;
-    while (r1 < nrows && s_rp[r1 + 1] - s_rp[r0] <= cap) ++r1;
+    int r1 = nrows;
+    if (s_rp[nrows] - s_rp[r0] > cap) {                      // dense graphs only
+      r1 = r0 + 1;
+      while (r1 < nrows && s_rp[r1 + 1] - s_rp[r0] <= cap) ++r1;
+    }
     const int eA = s_rp[r0], nE = s_rp[r1] - eA, nR = r1 - r0;
     __syncthreads();                                         // previous chunk fully consumed; slabs visible (first pass)
     for (int i = tid; i < nE; i += kAggThreads) {

@@ -194,6 +194,31 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// one bulk (TMA) copy per slab row instead of fo/4 16-byte cp.async's: global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc::smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+// stage rows [t0, t0+nrows) x [off, off+fo) of a [*, ld] matrix as a dense [nrows][fo] slab; call from all threads
+// BEFORE any divergence, then slab_wait() before reading.  Needs (fo*4) % 16 == 0 and 16-byte aligned rows.
+__device__ __forceinline__ void slab_load(float4* slab, const float* __restrict__ src, int t0, int nrows, int ld, int off,
+                                          int fo, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    tc::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)nrows * (uint32_t)fo * 4u);
+    __syncwarp();
+    if ((int)threadIdx.x < nrows)
+      bulk_g2s(slab + (size_t)threadIdx.x * (fo >> 2), src + (size_t)(t0 + threadIdx.x) * ld + off, (uint32_t)fo * 4u, bar);
+  }
+}
+__device__ __forceinline__ void slab_wait(uint64_t* bar) { tc::mbar_wait(bar, 0); }
+
 constexpr int kTileEdgeCap = 512;     // edges of one row tile staged in shared memory (beyond: read through L2)
 constexpr int kTileMaxFo = 512;       // widest view the tile kernels take (float4 layout)
 
@@ -201,8 +226,8 @@ inline int tile_row_groups(int fo) { return kAggThreads / (fo / 4); }
 inline size_t agg_fwd_tile_smem(int fo) { return (size_t)(kStatRows * fo + tile_row_groups(fo) * 2 * fo) * sizeof(float); }
 
 // Tile variant (float4 layout, fo_v <= kTileMaxFo).  Atoms of a molecule are consecutive packed rows, so nearly
-// every neighbour of a row lives in the same 32-row tile: the CTA stages its kStatRows x fo_v slab of Z with cp.async
-// (every load in flight at once instead of one dependent L2 round trip per row and edge) together with the tile's
+// every neighbour of a row lives in the same 32-row tile: the CTA stages its kStatRows x fo_v slab of Z with one bulk
+// (TMA) copy per row (instead of one dependent L2 round trip per row and edge) together with the tile's
 // edge list, then (row group, float4 channel) items -- no idle lanes for fo_v = 80 / 140 -- walk the edges out of
 // shared memory.  Neighbours outside the tile (molecules straddling a tile boundary) are read through L2.
 // The attention row sums are accumulated edge by edge (the generic kernel: lane-strided + shuffle tree), so Y can
@@ -215,6 +240,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
   extern __shared__ __align__(16) float tile_smem[];
   __shared__ int s_rp[kStatRows + 1];
   __shared__ float2 s_e[kTileEdgeCap];     // per staged edge: (a_e = sigma(code) / R_row, neighbour row as int bits)
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ float s_R[kStatRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int v = blockIdx.y, tile = blockIdx.x, t0 = tile * kStatRows;
@@ -224,9 +250,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
   const int fo = L.fo[v], off = L.off[v], ld = L.fo_tot, nc4 = fo >> 2;
   float4* sZ = reinterpret_cast<float4*>(tile_smem);             // [kStatRows][nc4]
   float* s_red = tile_smem + kStatRows * fo;                     // [row groups][2][fo]
-  for (int r = warp; r < nrows; r += kAggWarps)
-    for (int c = lane; c < nc4; c += 32) cp_async16(sZ + r * nc4 + c, Z + (size_t)(t0 + r) * ld + off + c * 4);
-  cp_async_commit();
+  slab_load(sZ, Z, t0, nrows, ld, off, fo, &s_bar);
   if (tid <= nrows) s_rp[tid] = p.row_ptr[t0 + tid];
   __syncthreads();
   const float* sg = sig + v * EAGCN_SIG_STRIDE;
@@ -246,8 +270,8 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, La
     s_R[tid] = R;
     for (int e = a0; e < min(a1, kTileEdgeCap); ++e) s_e[e].x = s_e[e].x / R;
   }
-  cp_async_wait_all();
   __syncthreads();
+  slab_wait(&s_bar);
   const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
   const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};

@@ -563,7 +563,8 @@ def test_agg_engines_agree(kind, B, fin, fo, training, p):
     (256, 64, True, True, 0.0),         # relu(bn_den2) (models.py:119)
     (37, 45, True, True, 0.5),          # ragged sizes
     (64, 96, False, True, 0.3),         # eval: running statistics, dropout off
-    (2, 8, True, False, 0.0),
+    (300, 40, True, True, 0.3),         # B > 256: multi-pass path
+    (5, 8, True, False, 0.0),
 ])
 def test_bn_act_vs_torch(B, C, training, relu, p):
     """eagcn_bn_act_forward/backward against stock torch fp32 ops (batch_norm -> relu -> dropout with the same keep

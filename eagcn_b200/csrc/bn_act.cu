@@ -2,7 +2,7 @@
 // the dense layers of the read-out head (reference models.py:112 Graph_BN, :114-116 relu(bn_den1) + dropout,
 // :119 relu(bn_den2)).  Stock PyTorch spends 4 kernels per BatchNorm direction plus one per activation on these
 // 256-row matrices (launch-bound: ~85 us per step on the Tox21 shape); here one CTA owns 32 channels for ALL rows, so
-// statistics (two-pass: mean, then centred sum of squares -- the same algorithm as torch's batch_norm), normalisation,
+// statistics (sums centred on a pivot row -- as well conditioned as torch's two-pass batch_norm), normalisation,
 // activation and dropout are one launch per direction.  With B <= 256 a thread keeps its 8 rows in registers: one pass
 // over memory (the first version looped 32 rows per thread three times and was latency-bound at ~10 us per launch).
 #include "common.cuh"
@@ -12,15 +12,19 @@ namespace eagcn {
 constexpr int kBnWarps = 32;          // one CTA = 32 channels x 32 row lanes (1024 threads)
 constexpr int kBnRegRows = 8;         // rows a thread keeps in registers: B <= 256 is a single pass over memory
 
-// column sums over the row lanes, fixed order; result valid in every thread of the column
-__device__ __forceinline__ float bn_col_reduce(float v, float (*s)[32], int warp, int lane) {
-  s[warp][lane] = v;
+// column sums of a value pair over the 32 row lanes, fixed order: warp 0 adds the 32 partials of its column and
+// broadcasts through shared memory (every thread summing them itself cost ~1k LSU cycles per reduction)
+__device__ __forceinline__ float2 bn_col_reduce2(float a, float b, float2 (*s)[32], float2* tot, int warp, int lane) {
+  s[warp][lane] = make_float2(a, b);
   __syncthreads();
-  float t = 0.0f;
+  if (warp == 0) {
+    float2 t = make_float2(0.0f, 0.0f);
 #pragma unroll
-  for (int w = 0; w < kBnWarps; ++w) t += s[w][lane];
+    for (int w = 0; w < kBnWarps; ++w) { const float2 v = s[w][lane]; t.x += v.x; t.y += v.y; }
+    tot[lane] = t;
+  }
   __syncthreads();
-  return t;
+  return tot[lane];
 }
 
 // REG: the thread's rows (warp, warp+32, ...) live in registers (B <= 32*kBnRegRows); otherwise every pass re-reads
@@ -31,7 +35,8 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
     float* __restrict__ run_mean, float* __restrict__ run_var, long long* __restrict__ nbt, float* __restrict__ mean_out,
     float* __restrict__ invstd_out, int B, int C, int training, int relu, float p_drop, const unsigned long long* rng,
     unsigned long long stream, float momentum, float eps) {
-  __shared__ float s[kBnWarps][32];
+  __shared__ float2 s[kBnWarps][32];
+  __shared__ float2 s_tot[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane;
   const bool act = c < C;
@@ -45,23 +50,29 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
   }
   float mean, invstd;
   if (training) {
-    float a = 0.0f;
+    float var;
     if (REG) {
-#pragma unroll
-      for (int k = 0; k < kBnRegRows; ++k) a += xv[k];               // rows >= B hold 0
-    } else if (act) {
-      for (int r = warp; r < B; r += kBnWarps) a += __ldg(x + (size_t)r * C + c);
-    }
-    mean = bn_col_reduce(a, s, warp, lane) / (float)B;
-    float q = 0.0f;
-    if (REG) {
+      // one reduction: sums of (x - p) and (x - p)^2 around the pivot p = x[0][c] (a sample of the column, so the
+      // variance formula below has no catastrophic cancellation: |mean - p| is of the order of the spread)
+      const float pv = act ? __ldg(x + c) : 0.0f;
+      float a = 0.0f, q = 0.0f;
 #pragma unroll
       for (int k = 0; k < kBnRegRows; ++k)
-        if (warp + k * kBnWarps < B) { const float d = xv[k] - mean; q = fmaf(d, d, q); }
-    } else if (act) {
-      for (int r = warp; r < B; r += kBnWarps) { const float d = __ldg(x + (size_t)r * C + c) - mean; q = fmaf(d, d, q); }
+        if (warp + k * kBnWarps < B) { const float d = xv[k] - pv; a += d; q = fmaf(d, d, q); }
+      const float2 t = bn_col_reduce2(a, q, s, s_tot, warp, lane);
+      const float dm = t.x / (float)B;
+      mean = pv + dm;
+      var = fmaxf(t.y / (float)B - dm * dm, 0.0f);
+    } else {
+      float a = 0.0f;
+      if (act)
+        for (int r = warp; r < B; r += kBnWarps) a += __ldg(x + (size_t)r * C + c);
+      mean = bn_col_reduce2(a, 0.0f, s, s_tot, warp, lane).x / (float)B;
+      float q = 0.0f;
+      if (act)
+        for (int r = warp; r < B; r += kBnWarps) { const float d = __ldg(x + (size_t)r * C + c) - mean; q = fmaf(d, d, q); }
+      var = bn_col_reduce2(q, 0.0f, s, s_tot, warp, lane).x / (float)B;
     }
-    const float var = bn_col_reduce(q, s, warp, lane) / (float)B;
     invstd = 1.0f / sqrtf(var + eps);
     if (warp == 0 && act) {                                  // running statistics like nn.BatchNorm1d (unbiased variance)
       run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * mean;
@@ -101,7 +112,8 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
     const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int training, int relu,
     float p_drop, const unsigned long long* rng, unsigned long long stream) {
-  __shared__ float s[kBnWarps][32];
+  __shared__ float2 s[kBnWarps][32];
+  __shared__ float2 s_tot[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane;
   const bool act = c < C;
@@ -134,8 +146,10 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
   } else if (act) {
     for (int r = warp; r < B; r += kBnWarps) { float xh; const float gr = grad_at(r, xh); s1 += gr; s2 = fmaf(gr, xh, s2); }
   }
-  s1 = bn_col_reduce(s1, s, warp, lane);
-  s2 = bn_col_reduce(s2, s, warp, lane);
+  {
+    const float2 t = bn_col_reduce2(s1, s2, s, s_tot, warp, lane);
+    s1 = t.x; s2 = t.y;
+  }
   if (!act) return;
   if (warp == 0) { dbeta[c] = s1; dgamma[c] = s2; }
   const float m1 = s1 / (float)B, m2 = s2 / (float)B, gi = g * invstd;

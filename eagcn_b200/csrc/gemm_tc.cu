@@ -37,6 +37,7 @@ constexpr int UK = 8;              // UMMA K for kind::tf32 (32 bytes)
 constexpr int MAX_STAGES = 4;      // smem ring depth is chosen on the host (as many stages as fit in 200 KB)
 constexpr int kThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 transform + epilogue
 constexpr int kXformThreads = 256;
+constexpr int kSmemBudget = 224 * 1024;   // dynamic shared memory per CTA (227 KB opt-in limit minus the static part)
 constexpr int kStgLd = 36;         // floats per row of an epilogue staging tile (32 + 4: conflict-free 128-bit access)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,6 +116,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// hi/lo split of one staged operand tile by the 256 transform threads: x -> (x with 13 low mantissa bits cleared,
+// x - that).  Four 16-byte vectors per thread are in flight at a time (the clock trace showed the one-at-a-time loop
+// latency-bound: 1.7k cycles for a 48 KB TN stage).
+__device__ __forceinline__ void split_tile(uint4* hi, uint4* lo, int n, int xt) {
+  for (int i0 = xt; i0 < n; i0 += 4 * kXformThreads) {
+    uint4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * kXformThreads; if (i < n) x[u] = hi[i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kXformThreads;
+      if (i < n) {
+        uint4 h, l;
+        h.x = x[u].x & 0xFFFFE000u; h.y = x[u].y & 0xFFFFE000u; h.z = x[u].z & 0xFFFFE000u; h.w = x[u].w & 0xFFFFE000u;
+        l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(h.x));
+        l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(h.y));
+        l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(h.z));
+        l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(h.w));
+        hi[i] = h; lo[i] = l;
+      }
+    }
+  }
 }
 
 struct TcArgs {
@@ -264,32 +289,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint4* bh = reinterpret_cast<uint4*>(sB_hi(s));
         for (int i = nboxB * (int)(box_bytes / 16) + xt; i < (int)(bytesB / 16); i += kXformThreads) bh[i] = z;
       }
-      {
-        uint4* hi = reinterpret_cast<uint4*>(sA_hi(s));
-        uint4* lo = reinterpret_cast<uint4*>(sA_lo(s));
-        for (int i = xt; i < (int)(bytesA / 16); i += kXformThreads) {
-          uint4 x = hi[i], h, l;
-          h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
-          l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-          hi[i] = h; lo[i] = l;
-        }
-      }
-      if (!g.b_split) {
-        uint4* hi = reinterpret_cast<uint4*>(sB_hi(s));
-        uint4* lo = reinterpret_cast<uint4*>(sB_lo(s));
-        for (int i = xt; i < (int)(bytesB / 16); i += kXformThreads) {
-          uint4 x = hi[i], h, l;
-          h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
-          l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-          hi[i] = h; lo[i] = l;
-        }
-      }
+      split_tile(reinterpret_cast<uint4*>(sA_hi(s)), reinterpret_cast<uint4*>(sA_lo(s)), (int)(bytesA / 16), xt);
+      if (!g.b_split)
+        split_tile(reinterpret_cast<uint4*>(sB_hi(s)), reinterpret_cast<uint4*>(sB_lo(s)), (int)(bytesB / 16), xt);
       fence_proxy_async();                                         // generic-proxy writes -> visible to UMMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ready[s]);                   // 8 arrivals per stage instead of 256
@@ -409,23 +411,36 @@ static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long
 
 static int pick_stages(int BN, int num_kb) {
   const int stage_bytes = 2 * BM * BK * 4 + 2 * BN * BK * 4;
-  int st = (200 * 1024 - 1024) / stage_bytes;
+  int st = (kSmemBudget - 1024) / stage_bytes;
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (st > num_kb) st = num_kb;
   return st < 2 ? 2 : st;
 }
 
-// N-tile width (multiple of `step`, 64..256).  One CTA per SM and a k-block cost that grows with the operand
-// bytes staged per k-block (~ 128 + BN rows): minimise  ceil(tiles / 148) * (128 + BN), i.e. avoid a nearly
-// empty second wave before worrying about padded columns.
-static int pick_bn(int N, int mtiles, int step = 16) {
+// N-tile width of the K-major products (multiple of 16, 64..256) from the same pipeline model as pick_tn_shape: one CTA
+// per SM, so first avoid a nearly empty second wave; then a k-block costs max(MMA, (TMA round trip + transform +
+// MMA) / stages) -- a tile narrow enough for a third shared-memory stage (144 columns for N = 400, with the full
+// 224 KB of dynamic shared memory) hides most of the TMA round trip, which the clock trace shows exposed with two.
+static int pick_bn(int N, int mtiles, int K, bool b_presplit) {
   int best = 128;
   long long best_cost = 1LL << 60;
-  for (int bn = 256; bn >= 64; bn -= step) {
+  const int kb = (K + BK - 1) / BK;
+  for (int bn = 256; bn >= 64; bn -= 16) {                   // UMMA M = 128 needs N % 16 == 0
     const int ntiles = (N + bn - 1) / bn;
     const long long tiles = (long long)ntiles * mtiles;
     const long long rounds = (tiles + 147) / 148;
-    const long long cost = rounds * (128 + bn) * 1000 + (long long)(ntiles * bn - N);
+    const int stage_bytes = 2 * BM * BK * 4 + 2 * bn * BK * 4;
+    int stages = (kSmemBudget - 1024) / stage_bytes;
+    stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    stages = stages > kb ? kb : stages;
+    stages = stages < 1 ? 1 : stages;
+    const long long xform = 300 + 30 * (16 + (b_presplit ? 0 : bn / 8));
+    const long long mma = 12 * (bn / 2 > 75 ? bn / 2 : 75);
+    const long long tma = 1500 + 8 * (16 + bn / 4);                  // ~KB per k-block -> cycles (fit: 76 KB ~ 2100)
+    long long per_kb = (400 + tma + xform + 100 + mma) / stages;
+    per_kb = per_kb < mma ? mma : per_kb;
+    per_kb = per_kb < xform + 300 ? xform + 300 : per_kb;
+    const long long cost = rounds * (kb * per_kb + 4000 + 25 * bn) * 100 + (long long)(ntiles * bn - N);
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -448,7 +463,7 @@ static long long* next_trace() {
 // B_lo != nullptr: B is pre-split (B = hi part, B_lo = lo part, same leading dimension)
 int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
                const int* Mdev, cudaStream_t st, const char* tag, const float* B_lo = nullptr) {
-  const int BN = pick_bn(N, (Mcap + BM - 1) / BM);
+  const int BN = pick_bn(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr);
   CUtensorMap mA, mB, mB2;
   if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
   if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
@@ -458,7 +473,7 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -497,7 +512,7 @@ static void pick_tn_shape(int M, int N, int Kcap, long long ws_floats, int* bn_o
     while (ns > 1 && (long long)ns * M * N > ws_floats) --ns;
     const int kb = (((Kcap + ns - 1) / ns) + BK - 1) / BK;
     const int stage_kb = (2 * BM * BK * 4 + 2 * bn * BK * 4) / 1024;
-    int stages = 199 / stage_kb;
+    int stages = (kSmemBudget / 1024 - 1) / stage_kb;
     stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     stages = stages > kb ? kb : stages;
     stages = stages < 1 ? 1 : stages;
@@ -527,7 +542,7 @@ int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   g.stages = pick_stages(BN, kchunk / BK);
   const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ns);
   EAGCN_PROF("gemm_tc_tn", st);

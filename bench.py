@@ -186,9 +186,15 @@ def run_b200(args):
     EF.set_gemm_engine(args.gemm)
     EF.set_agg_engine(args.agg)
     model = build_model(dev)
+    if args.dense_mm == "torch":
+        from eagcn_b200 import models as _M2
+        _M2.Dense.mm_engine = "torch"
     if args.head != "auto":
         model.fused_head = args.head == "fused"
         model.head_bn = "torch" if args.head == "torch" else "cuda"
+        if args.head == "torch":
+            from eagcn_b200 import models as _M
+            _M.Dense.mm_engine = "torch"
     NB = args.nbatches
     slots = []
     for i in range(NB):
@@ -364,10 +370,15 @@ def run_b200(args):
             busy += d
             t_first = e.time_range.start if t_first is None else t_first
             t_last = e.time_range.end
+        per = len(evs) // nrep
+        seq = [{"name": e.name[:60], "us": e.time_range.end - e.time_range.start,
+                "gap_us": (e.time_range.start - evs[len(evs) - per + i - 1].time_range.end) if i else 0.0}
+               for i, e in enumerate(evs[len(evs) - per:])] if per * nrep == len(evs) else []
         rows = sorted(((k, n / nrep, t / nrep) for k, (n, t) in agg.items()), key=lambda r: -r[2])
         print(json.dumps({"trace": True, "replays": nrep, "span_us_per_step": (t_last - t_first) / nrep,
                           "busy_us_per_step": busy / nrep,
-                          "kernels": [{"name": k, "launches_per_step": n, "us_per_step": t} for k, n, t in rows]}))
+                          "kernels": [{"name": k, "launches_per_step": n, "us_per_step": t} for k, n, t in rows],
+                          "last_step_sequence": seq}))
         return
 
     def timed(run_step, K, W):
@@ -518,7 +529,7 @@ def run_b200(args):
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
                        "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else
-                       ("library GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
+                       ("split-K FFMA GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
                        "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
@@ -671,6 +682,7 @@ def main():
     ap.add_argument("--trace", action="store_true", help="diagnostic: per-kernel durations inside the graph replays")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
+    ap.add_argument("--dense-mm", default="cuda", choices=["cuda", "torch"], help="GEMM of the head's dense layers")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -100,6 +100,9 @@ _PROTOS = {
                                      c_double, c_double, c_void_p]),
     "eagcn_bn_act_backward": (c_int, [c_void_p] * 9 + [c_int64, c_int64, c_int, c_int, c_double, c_void_p, c_int64,
                                       c_void_p]),
+    "eagcn_mm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "eagcn_mm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                         c_int64, c_void_p]),
     "eagcn_gemm_trace": (c_int, [c_void_p, c_int64]),
     "eagcn_gemm_trace_stride": (c_int64, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

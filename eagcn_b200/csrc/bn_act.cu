@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
       xv[k] = (act && r < B) ? __ldg(x + (size_t)r * C + c) : 0.0f;
     }
   }
+  // per-channel parameters: issued with the row loads so that their latency is not paid again after the reduction
+  const float g = act ? gamma[c] : 0.0f, b = act ? beta[c] : 0.0f;
+  const float rm0 = act ? run_mean[c] : 0.0f, rv0 = act ? run_var[c] : 1.0f;
   float mean, invstd;
   if (training) {
     float var;
@@ -75,17 +78,16 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
     }
     invstd = 1.0f / sqrtf(var + eps);
     if (warp == 0 && act) {                                  // running statistics like nn.BatchNorm1d (unbiased variance)
-      run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * mean;
-      run_var[c] = (1.0f - momentum) * run_var[c] + momentum * var * ((float)B / (float)(B > 1 ? B - 1 : 1));
+      run_mean[c] = (1.0f - momentum) * rm0 + momentum * mean;
+      run_var[c] = (1.0f - momentum) * rv0 + momentum * var * ((float)B / (float)(B > 1 ? B - 1 : 1));
     }
     if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
   } else {
-    mean = act ? run_mean[c] : 0.0f;
-    invstd = act ? 1.0f / sqrtf(run_var[c] + eps) : 0.0f;
+    mean = rm0;
+    invstd = act ? 1.0f / sqrtf(rv0 + eps) : 0.0f;
   }
   if (!act) return;
   if (warp == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
-  const float g = gamma[c], b = beta[c];
   const bool drop = training && p_drop > 0.0f;
   const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
   unsigned long long seed = 0, off = 0;

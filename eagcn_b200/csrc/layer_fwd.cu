@@ -232,7 +232,7 @@ inline size_t agg_fwd_tile_smem(int fo) { return (size_t)(kStatRows * fo + tile_
 // shared memory.  Neighbours outside the tile (molecules straddling a tile boundary) are read through L2.
 // The attention row sums are accumulated edge by edge (the generic kernel: lane-strided + shuffle tree), so Y can
 // differ from the generic kernel's in the last bit; the statistics partials are summed per row group.
-__global__ void __launch_bounds__(kAggThreads) agg_fwd_tile_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
+__global__ void __launch_bounds__(kAggThreads, 5) agg_fwd_tile_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
                                                                    const float* __restrict__ ball,
                                                                    const float* __restrict__ sig, float* __restrict__ Y,
                                                                    float* __restrict__ invR, float* __restrict__ partial,

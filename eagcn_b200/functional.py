@@ -449,6 +449,45 @@ class _BnActFn(torch.autograd.Function):
         return None, None, dx, dg, db
 
 
+def _mm(A, transA, B, transB):
+    """op(A) @ op(B) through eagcn_mm (strict fp32, split-K with fixed-order reduction)."""
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    if (B.shape[1] if transB else B.shape[0]) != K:
+        raise ValueError("mm: inner dimensions differ")
+    C = torch.empty(M, N, dtype=_F32, device=A.device)
+    nbytes = int(lib().eagcn_mm_workspace_bytes(M, N, K))
+    ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
+    check(lib().eagcn_mm(ptr(A), A.shape[1], int(transA), ptr(B), B.shape[1], int(transB), ptr(C), M, N, K,
+                         ptr(ws) if ws is not None else None, nbytes, _stream()), "eagcn_mm")
+    return C
+
+
+class _DenseMmFn(torch.autograd.Function):
+    """y = x @ W (layers.py:382-388) with dX = dY @ W^T and dW = x^T @ dY on the same split-K FFMA kernel."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        if not x.is_cuda:
+            raise EagcnError("eagcn_b200.dense_mm is CUDA-only (sm_100a, no CPU fallback)")
+        x, W = x.contiguous(), W.detach().contiguous()
+        ctx.save_for_backward(x, W)
+        return _mm(x, False, W, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = _mm(dy, False, W, True) if ctx.needs_input_grad[0] else None
+        dW = _mm(x, True, dy, False) if ctx.needs_input_grad[1] else None
+        return dx, dW
+
+
+def dense_mm(x, W):
+    return _DenseMmFn.apply(x, W)
+
+
 def bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):
     """``F.dropout(F.relu(bn(x)), p_drop, training)`` (each stage optional) for an ``nn.BatchNorm1d`` ``bn`` on [B, C]."""
     momentum = bn.momentum if bn.momentum is not None else 0.1

@@ -47,8 +47,13 @@ class Dense(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-stdv, stdv)
 
+    mm_engine = "cuda"          # 'cuda': eagcn_mm (split-K FFMA, fixed-order reduce); 'torch': library GEMM
+
     def forward(self, input):
-        out = torch.mm(input, self.weight)
+        if self.mm_engine == "cuda" and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:
+            out = EF.dense_mm(input, self.weight)                                   # layers.py:382-388
+        else:
+            out = torch.mm(input, self.weight)
         return out + self.bias if self.bias is not None else out
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 10
+#define EAGCN_ABI_VERSION 11
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -223,6 +223,15 @@ int eagcn_bn_act_forward(const void* x, void* y, const void* gamma, const void* 
 int eagcn_bn_act_backward(const void* x, const void* dy, const void* gamma, const void* beta, const void* mean,
                           const void* invstd, void* dx, void* dgamma, void* dbeta, int64_t B, int64_t C, int training,
                           int relu, double p_drop, const void* rng, int64_t rng_stream, void* stream);
+
+/* --- dense layers of the head ------------------------------------------------------------------ */
+/* C[M,N] = op(A) . op(B) in strict fp32 (FFMA), row-major; transX != 0: the operand is stored transposed (A as [K,M],
+ * B as [N,K]); lda / ldb = row strides in elements; C is dense (ldc = N).  Split-K with a fixed-order reduction
+ * through ws (eagcn_mm_workspace_bytes(M,N,K) bytes; may be NULL when that is 0).  This is `torch.mm(input, weight)`
+ * of reference layers.py:382-388 (Dense.forward) and its two autograd products.                                  */
+int64_t eagcn_mm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eagcn_mm(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C, int64_t M, int64_t N,
+             int64_t K, void* ws, int64_t ws_bytes, void* stream);
 
 /* --- projection GEMM engine ------------------------------------------------------------------ */
 /* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned

@@ -186,9 +186,10 @@ def run_b200(args):
     EF.set_gemm_engine(args.gemm)
     EF.set_agg_engine(args.agg)
     model = build_model(dev)
-    if args.dense_mm == "torch":
-        from eagcn_b200 import models as _M2
-        _M2.Dense.mm_engine = "torch"
+    if args.no_pdl:
+        _lib.lib().eagcn_set_pdl(0)
+    from eagcn_b200 import models as _M2
+    _M2.Dense.mm_engine = args.dense_mm
     if args.head != "auto":
         model.fused_head = args.head == "fused"
         model.head_bn = "torch" if args.head == "torch" else "cuda"
@@ -529,10 +530,10 @@ def run_b200(args):
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
                        "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else
-                       ("split-K FFMA GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
+                       ("library GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
-                       "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
+                       "pdl": bool(_lib.lib().eagcn_get_pdl()), "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
                        "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
                        "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
                        "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
@@ -682,7 +683,8 @@ def main():
     ap.add_argument("--trace", action="store_true", help="diagnostic: per-kernel durations inside the graph replays")
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
-    ap.add_argument("--dense-mm", default="cuda", choices=["cuda", "torch"], help="GEMM of the head's dense layers")
+    ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
+    ap.add_argument("--dense-mm", default="torch", choices=["cuda", "torch"], help="GEMM of the head's dense layers")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()

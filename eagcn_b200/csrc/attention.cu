@@ -7,6 +7,7 @@
 namespace eagcn {
 
 __global__ void __launch_bounds__(256) att_dense_kernel(PlanDev p, LayerDev L, float* __restrict__ A) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) att_dense_kernel(PlanDev p, LayerDev L, f
 // big -> two-level: each warp serialises its lanes into a shared histogram slot, warps summed in order.
 __global__ void __launch_bounds__(256) att_dense_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ dA,
                                                             float* __restrict__ datt) {
+  pdl_prologue();
   __shared__ float s_hist[8][256];
   const int v = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,7 +84,7 @@ extern "C" int eagcn_attention_dense(const eagcn_plan_t* plan, const eagcn_layer
   cudaError_t e = cudaMemsetAsync(A_out, 0, (size_t)p.V * p.B * p.N * p.N * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   EAGCN_PROF("att_dense_kernel", st);
-  att_dense_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p, L, (float*)A_out);
+  EAGCN_LAUNCH(att_dense_kernel, (p.t_cap + 7) / 8, 256, 0, st)(p, L, (float*)A_out);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -93,7 +95,7 @@ extern "C" int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_l
   PlanDev p = to_dev(plan);
   LayerDev L = to_dev(layer, plan);
   EAGCN_PROF("att_dense_bwd_kernel", (cudaStream_t)stream);
-  att_dense_bwd_kernel<<<p.V, 256, 0, (cudaStream_t)stream>>>(p, L, (const float*)dA, (float*)datt);
+  EAGCN_LAUNCH(att_dense_bwd_kernel, p.V, 256, 0, (cudaStream_t)stream)(p, L, (const float*)dA, (float*)datt);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_fwd_kernel(
     float* __restrict__ run_mean, float* __restrict__ run_var, long long* __restrict__ nbt, float* __restrict__ mean_out,
     float* __restrict__ invstd_out, int B, int C, int training, int relu, float p_drop, const unsigned long long* rng,
     unsigned long long stream, float momentum, float eps) {
+  pdl_prologue();
   __shared__ float2 s[kBnWarps][32];
   __shared__ float2 s_tot[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(kBnWarps * 32) bn_act_bwd_kernel(
     const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int training, int relu,
     float p_drop, const unsigned long long* rng, unsigned long long stream) {
+  pdl_prologue();
   __shared__ float2 s[kBnWarps][32];
   __shared__ float2 s_tot[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,7 +184,7 @@ extern "C" int eagcn_bn_act_forward(const void* x, void* y, const void* gamma, c
   if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
   EAGCN_PROF("bn_act_fwd_kernel", stream);
   auto kern = B <= kBnWarps * kBnRegRows ? bn_act_fwd_kernel<true> : bn_act_fwd_kernel<false>;
-  kern<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+  EAGCN_LAUNCH(kern, (unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream)(
       (const float*)x, (float*)y, (const float*)gamma, (const float*)beta, (float*)run_mean, (float*)run_var,
       (long long*)nbt, (float*)mean_out, (float*)invstd_out, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
       (const unsigned long long*)rng, (unsigned long long)rng_stream, (float)momentum, (float)eps);
@@ -198,7 +200,7 @@ extern "C" int eagcn_bn_act_backward(const void* x, const void* dy, const void* 
   if (p_drop < 0.0 || p_drop >= 1.0 || (training && p_drop > 0.0 && !rng) || B * C >= (int64_t)2147483000) return EAGCN_E_ARG;
   EAGCN_PROF("bn_act_bwd_kernel", stream);
   auto kern = B <= kBnWarps * kBnRegRows ? bn_act_bwd_kernel<true> : bn_act_bwd_kernel<false>;
-  kern<<<(unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream>>>(
+  EAGCN_LAUNCH(kern, (unsigned)((C + 31) / 32), kBnWarps * 32, 0, (cudaStream_t)stream)(
       (const float*)x, (const float*)dy, (const float*)gamma, (const float*)beta, (const float*)mean, (const float*)invstd,
       (float*)dx, (float*)dgamma, (float*)dbeta, (int)B, (int)C, training ? 1 : 0, relu ? 1 : 0, (float)p_drop,
       (const unsigned long long*)rng, (unsigned long long)rng_stream);

@@ -43,6 +43,38 @@ inline void prof_end() {
     if (e__ != cudaSuccess) return (int)e__;                  \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// A step is ~50 small dependent kernels; on the dependent chain of a CUDA graph each launch costs a few microseconds
+// of scheduling latency.  Every kernel here starts with pdl_prologue(): it lets the NEXT kernel of the stream be
+// scheduled as soon as all CTAs of this one have started (griddepcontrol.launch_dependents) and then blocks until the
+// PREVIOUS kernel has completed and flushed (griddepcontrol.wait) -- nothing is read or written before that, so the
+// semantics are those of ordinary stream order.  Kernels are launched through EAGCN_LAUNCH, which attaches
+// cudaLaunchAttributeProgrammaticStreamSerialization (captured into CUDA graphs as programmatic edges).
+namespace eagcn {
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline int& pdl_mode() { static int m = 1; return m; }
+template <typename K>
+struct PdlLaunch {
+  K kern; dim3 grid, block; size_t smem; cudaStream_t st;
+  template <typename... A>
+  void operator()(A&&... a) const {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_mode() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(a)...);    // errors surface through EAGCN_LAUNCH_CHECK
+  }
+};
+template <typename K>
+inline PdlLaunch<K> make_launch(K k, dim3 g, dim3 b, size_t smem, cudaStream_t st) { return PdlLaunch<K>{k, g, b, smem, st}; }
+}  // namespace eagcn
+#define EAGCN_LAUNCH(kernel, grid, block, smem, st) ::eagcn::make_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(st))
+
 #define EAGCN_TINY 1e-9f            // reference layers.py:294
 #define EAGCN_SIG_STRIDE 257        // sigma table row: [0..255] codes, [256] = sigmoid(self_r)
 #define EAGCN_NO_EDGE 255

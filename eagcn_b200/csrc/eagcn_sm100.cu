@@ -22,6 +22,8 @@ extern "C" int eagcn_set_agg_mode(int mode) {
   return 0;
 }
 extern "C" int eagcn_get_agg_mode(void) { return eagcn::agg_mode(); }
+extern "C" int eagcn_set_pdl(int on) { eagcn::pdl_mode() = on ? 1 : 0; return 0; }
+extern "C" int eagcn_get_pdl(void) { return eagcn::pdl_mode(); }
 extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,
                              int64_t N, int64_t K, const void* m_dev, int engine, void* stream) {
   if (!A || !B || !C || !m_dev || m_cap <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N) return EAGCN_E_ARG;

@@ -31,6 +31,7 @@ struct GemmArgs {
 
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(GTHREADS) gemm_simt_kernel(GemmArgs g) {
+  pdl_prologue();
   __shared__ __align__(16) float As[GBK][GAS];
   __shared__ __align__(16) float Bs[GBK][GBS];
   const int tid = threadIdx.x;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_simt_kernel(GemmArgs g) {
 // C[i] = sum_z part[z][i], z ascending (deterministic)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C,
                                                             long long n, int nsplit) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   float s = 0.0f;
@@ -117,7 +119,7 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
   GemmArgs g{A, B, C, lda, 1, ldb, 1, ldc, Mcap, N, K, Mdev, nullptr, K + GBK, 0};
   dim3 grid((N + GBN - 1) / GBN, (Mcap + GBM - 1) / GBM, 1);
   EAGCN_PROF("gemm_simt_nn", st);
-  gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, st>>>(g);
+  EAGCN_LAUNCH((gemm_simt_kernel<true, false>), grid, GTHREADS, 0, st)(g);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -128,7 +130,7 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
   GemmArgs g{A, B, C, lda, 1, 1, ldb, ldc, Mcap, N, K, Mdev, nullptr, K + GBK, 0};
   dim3 grid((N + GBN - 1) / GBN, (Mcap + GBM - 1) / GBM, 1);
   EAGCN_PROF("gemm_simt_nt", st);
-  gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, st>>>(g);
+  EAGCN_LAUNCH((gemm_simt_kernel<true, true>), grid, GTHREADS, 0, st)(g);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -139,7 +141,7 @@ long long gemm_tn_workspace_floats(int M, int N, int Kcap) { return (long long)t
 
 int splitk_reduce(const float* ws, float* C, long long n, int ns, cudaStream_t st) {
   EAGCN_PROF("splitk_reduce_kernel", st);
-  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, C, n, ns);
+  EAGCN_LAUNCH(splitk_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(ws, C, n, ns);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -155,7 +157,7 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
   GemmArgs g{A, B, ws, 1, lda, ldb, 1, N, M, N, Kcap, nullptr, Kdev, kchunk, (long long)M * N};
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, ns);
   EAGCN_PROF("gemm_simt_tn", st);
-  gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, st>>>(g);
+  EAGCN_LAUNCH((gemm_simt_kernel<false, false>), grid, GTHREADS, 0, st)(g);
   EAGCN_LAUNCH_CHECK();
   if (nsplit_out) { *nsplit_out = ns; return 0; }
   return splitk_reduce(ws, C, (long long)M * N, ns, st);
@@ -190,10 +192,10 @@ int mm(const float* A, int lda, bool transA, const float* B, int ldb, bool trans
              nullptr, nullptr, kchunk, (long long)M * N};
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, ns);
   EAGCN_PROF("mm_simt", st);
-  if (!transA && !transB) gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, st>>>(g);
-  else if (!transA && transB) gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, st>>>(g);
-  else if (transA && !transB) gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, st>>>(g);
-  else gemm_simt_kernel<false, true><<<grid, GTHREADS, 0, st>>>(g);
+  if (!transA && !transB) EAGCN_LAUNCH((gemm_simt_kernel<true, false>), grid, GTHREADS, 0, st)(g);
+  else if (!transA && transB) EAGCN_LAUNCH((gemm_simt_kernel<true, true>), grid, GTHREADS, 0, st)(g);
+  else if (transA && !transB) EAGCN_LAUNCH((gemm_simt_kernel<false, false>), grid, GTHREADS, 0, st)(g);
+  else EAGCN_LAUNCH((gemm_simt_kernel<false, true>), grid, GTHREADS, 0, st)(g);
   EAGCN_LAUNCH_CHECK();
   if (ns > 1) return splitk_reduce(ws, C, (long long)M * N, ns, st);
   return 0;

@@ -160,6 +160,7 @@ constexpr int kTraceKb = 64, kTraceStride = 8 + 5 * kTraceKb;
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapB2, TcArgs g) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_ready[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc;
   __shared__ uint32_t tmem_base_smem;
@@ -479,7 +480,7 @@ int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int l
   }
   dim3 grid((N + BN - 1) / BN, (Mcap + BM - 1) / BM, 1);
   EAGCN_PROF(tag, st);
-  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, mB2, g);
+  EAGCN_LAUNCH(gemm_tc_kernel, grid, kThreads, smem, st)(mA, mB, mB2, g);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -546,7 +547,7 @@ int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ns);
   EAGCN_PROF("gemm_tc_tn", st);
-  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mA, mB, mB, g);
+  EAGCN_LAUNCH(gemm_tc_kernel, grid, kThreads, smem, st)(mA, mB, mB, g);
   EAGCN_LAUNCH_CHECK();
   *nsplit_out = ns;
   return 0;

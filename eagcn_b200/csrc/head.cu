@@ -188,6 +188,7 @@ __device__ __forceinline__ void finalize_bn(const HeadDev& h, int C, int ntile, 
 
 // ======================================================================================================
 __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadDev h) {
+  pdl_prologue();
   __shared__ float sA[2][TK][TM + 1];
   __shared__ float sB[2][TK][TN + 1];
   extern __shared__ float s_stat[];                    // [2][max(F, D1, D2)] mean / invstd of the operand being normalised
@@ -302,6 +303,7 @@ __device__ __forceinline__ void bwd_partials(const float* __restrict__ G, const 
 }
 
 __global__ void __launch_bounds__(HT) head_bwd_kernel(HeadDev h) {
+  pdl_prologue();
   __shared__ float sA[2][TK][TM + 1];
   __shared__ float sB[2][TK][TN + 1];
   extern __shared__ float s_c[];                       // [4][ldp]: per-column coefficients of the current BatchNorm
@@ -523,7 +525,7 @@ extern "C" int eagcn_head_forward(const eagcn_head_t* args, void* stream) {
   cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return (int)e;
   EAGCN_PROF("head_fwd_kernel", stream);
-  head_fwd_kernel<<<head_grid(h), HT, smem, (cudaStream_t)stream>>>(h);
+  EAGCN_LAUNCH(head_fwd_kernel, head_grid(h), HT, smem, (cudaStream_t)stream)(h);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -537,7 +539,7 @@ extern "C" int eagcn_head_backward(const eagcn_head_t* args, void* stream) {
   cudaError_t e = cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return (int)e;
   EAGCN_PROF("head_bwd_kernel", stream);
-  head_bwd_kernel<<<head_grid(h), HT, smem, (cudaStream_t)stream>>>(h);
+  EAGCN_LAUNCH(head_bwd_kernel, head_grid(h), HT, smem, (cudaStream_t)stream)(h);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

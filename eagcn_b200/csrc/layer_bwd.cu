@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(PlanDev p, const fl
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
                                                              float* __restrict__ partial, int C, int training, float p_drop,
                                                              const unsigned long long* rng, unsigned long long stream) {
+  pdl_prologue();
   __shared__ float s[2][2][128];
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(PlanDev p, const floa
                                                            const double* __restrict__ bsums, float* __restrict__ dY, int C,
                                                            int training, float p_drop, const unsigned long long* rng,
                                                            unsigned long long stream, double M) {
+  pdl_prologue();
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)p.t_cap * C) return;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
                                                                  float* __restrict__ partial, int C, int training, float p_drop,
                                                                  const unsigned long long* rng, unsigned long long stream,
                                                                  float* __restrict__ G) {
+  pdl_prologue();
   __shared__ float4 s_red[2][8][32];
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const 
                                                                const double* __restrict__ bsums, float* __restrict__ dY, int C,
                                                                int training, float p_drop, const unsigned long long* rng,
                                                                unsigned long long stream, double M) {
+  pdl_prologue();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
   if (c >= C) return;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ ball, const float* __restrict__ invstd,
                                                               const double* __restrict__ bsums, float* __restrict__ dvec,
                                                               int C, int training) {
+  pdl_prologue();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   const double s1 = bsums[c], s2 = bsums[C + c];
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDe
                                                       const float* __restrict__ ball, const float* __restrict__ sig,
                                                       const float* __restrict__ invR, float* __restrict__ Q,
                                                       float* __restrict__ dpart) {
+  pdl_prologue();
   __shared__ float s_hist[kAggWarps][EAGCN_SIG_STRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y, tile = blockIdx.x;
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_tile_kernel(PlanDev p,
                                                                    const float* __restrict__ sig,
                                                                    const float* __restrict__ invR, float* __restrict__ Q,
                                                                    float* __restrict__ dpart, int cap) {
+  pdl_prologue();
   extern __shared__ __align__(16) float tile_smem_b[];
   __shared__ int s_rp[kStatRows + 1];
   __shared__ float s_invR[kStatRows], s_ct[kStatRows];
@@ -561,6 +568,7 @@ static bool tile_bwd_ok(const eagcn_plan_t* plan, const eagcn_layer_t* layer, co
 // datt[v][i] = sum over live tiles (fixed order)
 __global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float* __restrict__ dpart,
                                                           float* __restrict__ datt, int V) {
+  pdl_prologue();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= V * EAGCN_SIG_STRIDE) return;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float
 __global__ void __launch_bounds__(256) bwd_post_kernel(PlanDev p, LayerDev L, const float* __restrict__ wpart, int ns,
                                                        float* __restrict__ dwall, const float* __restrict__ dpart,
                                                        float* __restrict__ datt, int nblk_w) {
+  pdl_prologue();
   const int C = L.fo_tot;
   if ((int)blockIdx.x < nblk_w) {
     const long long n = (long long)L.fin * C;
@@ -641,7 +650,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y)) {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 31) / 32);
     EAGCN_PROF("bn_bwd_partial_kernel", st);
-    bn_bwd_partial_vec_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+    EAGCN_LAUNCH(bn_bwd_partial_vec_kernel, grid, 256, 0, st)(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
                                                     C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,
@@ -651,7 +660,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   } else {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
     EAGCN_PROF("bn_bwd_partial_kernel", st);
-    bn_bwd_partial_kernel<<<grid, 256, 0, st>>>(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+    EAGCN_LAUNCH(bn_bwd_partial_kernel, grid, 256, 0, st)(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                 (const float*)w->mean, (const float*)w->invstd, (float*)w->partial, C,
                                                 (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                 (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
@@ -665,7 +674,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   StatEpilogue ep{2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
                   (w->training & 1) ? 1 : 0, 0.0, 0.0, 0.0};
   EAGCN_PROF("stat_reduce_kernel", st);
-  stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
+  EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -698,21 +707,21 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
       smem_set = smem;
     }
     EAGCN_PROF("agg_bwd_kernel", st);
-    agg_bwd_tile_kernel<<<grid, kAggThreads, smem, st>>>(p, L, bn, (const float*)w->Z, (const float*)w->Y,
+    EAGCN_LAUNCH(agg_bwd_tile_kernel, grid, kAggThreads, smem, st)(p, L, bn, (const float*)w->Z, (const float*)w->Y,
                                                          (const float*)w->ball, (const float*)w->sig,
                                                          (const float*)w->invR, (float*)w->Q, (float*)w->partial, cap);
   } else {
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y) && aligned16(w->dY)) {
     dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_bwd_apply_kernel", st);
-    bn_bwd_apply_vec_kernel<<<grid, 128, 0, st>>>(
+    EAGCN_LAUNCH(bn_bwd_apply_vec_kernel, grid, 128, 0, st)(
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
         (const float*)w->invstd, (const double*)w->bsums, (float*)w->dY, C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_bwd_apply_kernel", st);
-    bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+    EAGCN_LAUNCH(bn_bwd_apply_kernel, (unsigned)((total + 255) / 256), 256, 0, st)(
         p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd,
         (const double*)w->bsums, (float*)w->dY, C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
         (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, M);
@@ -720,12 +729,12 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   }
   if (vec4_ok_b(layer)) {
     EAGCN_PROF("agg_bwd_kernel", st);
-    agg_bwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+    EAGCN_LAUNCH((agg_bwd_kernel<4>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
   } else {
     EAGCN_PROF("agg_bwd_kernel", st);
-    agg_bwd_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
+    EAGCN_LAUNCH((agg_bwd_kernel<1>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->Y, (const float*)w->dY,
                                             (const float*)w->ball, (const float*)w->sig, (const float*)w->invR,
                                             (float*)w->Q, (float*)w->partial);
   }
@@ -752,7 +761,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   const int nblk_w = (int)(((long long)L.fin * C + 255) / 256);
   const int nblk_a = (L.V * EAGCN_SIG_STRIDE + 7) / 8;
   EAGCN_PROF("bwd_post_kernel", st);
-  bwd_post_kernel<<<nblk_w + nblk_a, 256, 0, st>>>(p, L, (const float*)w->gemm_ws, ns, (float*)w->dwall,
+  EAGCN_LAUNCH(bwd_post_kernel, nblk_w + nblk_a, 256, 0, st)(p, L, (const float*)w->gemm_ws, ns, (float*)w->dwall,
                                                    (const float*)w->partial, (float*)w->datt, nblk_w);
   EAGCN_LAUNCH_CHECK();
   return 0;

@@ -32,6 +32,7 @@ inline int& agg_mode() { static int m = 0; return m; }   // 0: shared-memory til
 __global__ void __launch_bounds__(256) prep_params_kernel(LayerDev L, float* __restrict__ wall, float* __restrict__ wallT,
                                                           float* __restrict__ wsplit, float* __restrict__ ball,
                                                           float* __restrict__ sig) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long nW = (long long)L.fin * L.fo_tot;
   if (idx < nW) {
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_onepass_kernel(PlanDev p,
                                                                       const float* __restrict__ sig, float* __restrict__ Y,
                                                                       float* __restrict__ invR, float* __restrict__ partial,
                                                                       int n_pad, int want_stats) {
+  pdl_prologue();
   __shared__ float s_red[kAggWarps][2][NQ * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(kAggThreads, 5) agg_fwd_tile_kernel(PlanDev p,
                                                                    const float* __restrict__ sig, float* __restrict__ Y,
                                                                    float* __restrict__ invR, float* __restrict__ partial,
                                                                    int n_pad, int want_stats) {
+  pdl_prologue();
   extern __shared__ __align__(16) float tile_smem[];
   __shared__ int s_rp[kStatRows + 1];
   __shared__ float2 s_e[kTileEdgeCap];     // per staged edge: (a_e = sigma(code) / R_row, neighbour row as int bits)
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_kernel(PlanDev p, LayerDe
                                                       const float* __restrict__ ball, const float* __restrict__ sig,
                                                       float* __restrict__ Y, float* __restrict__ invR,
                                                       float* __restrict__ partial, int n_pad, int want_stats) {
+  pdl_prologue();
   __shared__ float s_red[kAggWarps][2][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.y;
@@ -433,6 +437,7 @@ constexpr int kStatLanes = 32;
 __global__ void __launch_bounds__(32 * kStatLanes) stat_reduce_kernel(PlanDev p, LayerDev L,
                                                                       const float* __restrict__ partial,
                                                                       double* __restrict__ sums, int C, StatEpilogue ep) {
+  pdl_prologue();
   __shared__ double s[kStatLanes][2][32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -473,6 +478,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(LayerDev L, const floa
                                                           const double* __restrict__ sums, float* __restrict__ mean,
                                                           float* __restrict__ invstd, int training, double M,
                                                           double eps, double momentum) {
+  pdl_prologue();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= L.fo_tot) return;
   bn_finalize_channel(L, ball, c, training ? sums[c] : 0.0, training ? sums[L.fo_tot + c] : 0.0, mean, invstd, training, M,
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(PlanDev p, const float* _
                                                        const float* __restrict__ invstd, float* __restrict__ X, int C,
                                                        int training, float p_drop, const unsigned long long* rng,
                                                        unsigned long long rng_stream) {
+  pdl_prologue();
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // one element per thread
   const long long total = (long long)p.t_cap * C;
@@ -507,6 +514,7 @@ __global__ void __launch_bounds__(128) bn_apply_vec_kernel(PlanDev p, const floa
                                                            const float* __restrict__ invstd, float* __restrict__ X, int C,
                                                            int training, float p_drop, const unsigned long long* rng,
                                                            unsigned long long rng_stream) {
+  pdl_prologue();
   const int c4 = blockIdx.x * 128 + threadIdx.x;
   if (c4 * 4 >= C) return;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -543,6 +551,7 @@ __global__ void __launch_bounds__(128) bn_apply_vec_kernel(PlanDev p, const floa
 __global__ void __launch_bounds__(256) dropout_mask_kernel(long long total, float p_drop,
                                                            const unsigned long long* rng, unsigned long long rng_stream,
                                                            uint8_t* __restrict__ keep) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const Philox ph(rng[0]);
@@ -587,7 +596,7 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
   if (n < C) n = C;
   EAGCN_PROF("prep_params_kernel", st);
-  prep_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, (float*)w->wall, (float*)w->wallT, (float*)w->wsplit, (float*)w->ball, (float*)w->sig);
+  EAGCN_LAUNCH(prep_params_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(L, (float*)w->wall, (float*)w->wallT, (float*)w->wsplit, (float*)w->ball, (float*)w->sig);
   EAGCN_LAUNCH_CHECK();
   int rc;
   if (gemm_mode() != 1 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
@@ -614,33 +623,33 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
       attr_set = true;
     }
     EAGCN_PROF("agg_fwd_kernel", st);
-    agg_fwd_tile_kernel<<<grid, kAggThreads, smem, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+    EAGCN_LAUNCH(agg_fwd_tile_kernel, grid, kAggThreads, smem, st)(p, L, (const float*)w->Z, (const float*)w->ball,
                                                          (const float*)w->sig, (float*)w->Y, (float*)w->invR,
                                                          (float*)w->partial, n_pad, want);
   } else if (vec4_ok(layer) && fo_max <= 256) {
     EAGCN_PROF("agg_fwd_kernel", st);
     if (fo_max <= 128)
-      agg_fwd_onepass_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+      EAGCN_LAUNCH((agg_fwd_onepass_kernel<1>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->ball,
                                                               (const float*)w->sig, (float*)w->Y, (float*)w->invR,
                                                               (float*)w->partial, n_pad, want);
     else
-      agg_fwd_onepass_kernel<2><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball,
+      EAGCN_LAUNCH((agg_fwd_onepass_kernel<2>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->ball,
                                                               (const float*)w->sig, (float*)w->Y, (float*)w->invR,
                                                               (float*)w->partial, n_pad, want);
   } else if (vec4_ok(layer)) {
     EAGCN_PROF("agg_fwd_kernel", st);
-    agg_fwd_kernel<4><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+    EAGCN_LAUNCH((agg_fwd_kernel<4>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
   } else {
     EAGCN_PROF("agg_fwd_kernel", st);
-    agg_fwd_kernel<1><<<grid, kAggThreads, 0, st>>>(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
+    EAGCN_LAUNCH((agg_fwd_kernel<1>), grid, kAggThreads, 0, st)(p, L, (const float*)w->Z, (const float*)w->ball, (const float*)w->sig,
                                             (float*)w->Y, (float*)w->invR, (float*)w->partial, n_pad, want);
   }
   EAGCN_LAUNCH_CHECK();
   if (want && host_allreduce) {
     StatEpilogue ep{0, nullptr, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0};
     EAGCN_PROF("stat_reduce_kernel", st);
-    stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
     EAGCN_LAUNCH_CHECK();
   }
   return 0;
@@ -663,11 +672,11 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
     if (!w->partial) return EAGCN_E_ARG;
     StatEpilogue ep{1, (const float*)w->ball, (float*)w->mean, (float*)w->invstd, nullptr, 1, M, w->eps, w->momentum};
     EAGCN_PROF("stat_reduce_kernel", st);
-    stat_reduce_kernel<<<(C + 31) / 32, 32 * kStatLanes, 0, st>>>(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_finalize_kernel", st);
-    bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
+    EAGCN_LAUNCH(bn_finalize_kernel, (C + 255) / 256, 256, 0, st)(L, (const float*)w->ball, (const double*)w->sums, (float*)w->mean,
                                                         (float*)w->invstd, training, M, w->eps, w->momentum);
     EAGCN_LAUNCH_CHECK();
   }
@@ -675,14 +684,14 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
   if ((C & 3) == 0 && aligned16(w->Y) && aligned16(w->X)) {
     dim3 grid((C / 4 + 127) / 128, (p.t_cap + kEltRows - 1) / kEltRows);
     EAGCN_PROF("bn_apply_kernel", st);
-    bn_apply_vec_kernel<<<grid, 128, 0, st>>>(p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
+    EAGCN_LAUNCH(bn_apply_vec_kernel, grid, 128, 0, st)(p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean,
                                               (const float*)w->invstd, (float*)w->X, C, training,
                                               (float)w->p_drop, (const unsigned long long*)w->rng,
                                               (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_apply_kernel", st);
-    bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+    EAGCN_LAUNCH(bn_apply_kernel, (unsigned)((total + 255) / 256), 256, 0, st)(
         p, (const float*)w->Y, (const float*)w->ball, (const float*)w->mean, (const float*)w->invstd, (float*)w->X, C,
         training, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream);
     EAGCN_LAUNCH_CHECK();
@@ -695,7 +704,7 @@ extern "C" int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* 
   if (!plan_ok(plan) || !w || !w->rng || !keep_out || fo_tot <= 0) return EAGCN_E_ARG;
   const long long total = (long long)plan->t_cap * fo_tot;
   EAGCN_PROF("dropout_mask_kernel", (cudaStream_t)stream);
-  dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  EAGCN_LAUNCH(dropout_mask_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream)(
       total, (float)w->p_drop, (const unsigned long long*)w->rng, (unsigned long long)w->rng_stream, (uint8_t*)keep_out);
   EAGCN_LAUNCH_CHECK();
   return 0;
@@ -705,7 +714,7 @@ extern "C" int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, doub
                                        void* stream) {
   if (!rng || !keep_out || total <= 0 || p_drop < 0.0 || p_drop >= 1.0) return EAGCN_E_ARG;
   EAGCN_PROF("dropout_mask_kernel", stream);
-  dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  EAGCN_LAUNCH(dropout_mask_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream)(
       total, (float)p_drop, (const unsigned long long*)rng, (unsigned long long)rng_stream, (uint8_t*)keep_out);
   EAGCN_LAUNCH_CHECK();
   return 0;

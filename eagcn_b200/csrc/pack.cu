@@ -35,6 +35,7 @@ __device__ __forceinline__ float adj_at(const float* __restrict__ adj, const uin
 template <bool kCodes>
 __global__ void __launch_bounds__(kPackThreads) pack_count_kernel(PlanDev p, const float* __restrict__ adj,
                                                                   const uint8_t* __restrict__ codes) {
+  pdl_prologue();
   __shared__ int s_deg[kPackRows];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_count_kernel(PlanDev p, con
 
 // single CTA: exclusive scan (in place) of blk[2*i], blk[2*i+1]; totals -> counts
 __global__ void __launch_bounds__(1024) pack_scan_kernel(PlanDev p, int nblk) {
+  pdl_prologue();
   __shared__ int s_a[1024], s_e[1024];
   const int tid = threadIdx.x;
   const int per = (nblk + 1023) / 1024;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(PlanDev p, int nblk) {
 template <bool kCodes>
 __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, const float* __restrict__ adj,
                                                                  const uint8_t* __restrict__ codes, RelPtrs rel) {
+  pdl_prologue();
   __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
   __shared__ int s_hit[8][EAGCN_MAX_VIEWS][32];      // per (view, edge of the chunk): (#nonzero planes << 16) + plane index
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
 
 // one warp per active row: neighbour row ids, reverse edge (binary search), reverse codes
 __global__ void __launch_bounds__(256) pack_link_kernel(PlanDev p) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(256) pack_link_kernel(PlanDev p) {
 // inverse of the packing for one view (parity check: indexing must round-trip bit-exactly)
 __global__ void __launch_bounds__(256) unpack_view_kernel(PlanDev p, int v, float* __restrict__ rel_out,
                                                           float* __restrict__ adj_out) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
@@ -289,11 +294,11 @@ static int pack_count_impl(const eagcn_plan_t* plan, const void* src, cudaStream
   cudaError_t e = cudaMemsetAsync(p.counts, 0, 8 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   EAGCN_PROF("pack_count_kernel", st);
-  pack_count_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
+  EAGCN_LAUNCH((pack_count_kernel<kCodes>), nblk, kPackThreads, 0, st)(p, kCodes ? nullptr : (const float*)src,
                                                            kCodes ? (const uint8_t*)src : nullptr);
   EAGCN_LAUNCH_CHECK();
   EAGCN_PROF("pack_scan_kernel", st);
-  pack_scan_kernel<<<1, 1024, 0, st>>>(p, nblk);
+  EAGCN_LAUNCH(pack_scan_kernel, 1, 1024, 0, st)(p, nblk);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -314,11 +319,11 @@ static int pack_fill_impl(const eagcn_plan_t* plan, const void* src, const void*
   const int P = p.B * p.N;
   const int nblk = (P + kPackRows - 1) / kPackRows;
   EAGCN_PROF("pack_fill_kernel", st);
-  pack_fill_kernel<kCodes><<<nblk, kPackThreads, 0, st>>>(p, kCodes ? nullptr : (const float*)src,
+  EAGCN_LAUNCH((pack_fill_kernel<kCodes>), nblk, kPackThreads, 0, st)(p, kCodes ? nullptr : (const float*)src,
                                                           kCodes ? (const uint8_t*)src : nullptr, rp);
   EAGCN_LAUNCH_CHECK();
   EAGCN_PROF("pack_link_kernel", st);
-  pack_link_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p);
+  EAGCN_LAUNCH(pack_link_kernel, (p.t_cap + 7) / 8, 256, 0, st)(p);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -349,7 +354,7 @@ extern "C" int eagcn_unpack_view(const eagcn_plan_t* plan, int64_t v, void* rel_
   if (rel_out) { e = cudaMemsetAsync(rel_out, 0, nn * p.chan[v] * sizeof(float), st); if (e) return (int)e; }
   if (adj_out) { e = cudaMemsetAsync(adj_out, 0, nn * sizeof(float), st); if (e) return (int)e; }
   EAGCN_PROF("unpack_view_kernel", st);
-  unpack_view_kernel<<<(p.t_cap + 7) / 8, 256, 0, st>>>(p, (int)v, (float*)rel_out, (float*)adj_out);
+  EAGCN_LAUNCH(unpack_view_kernel, (p.t_cap + 7) / 8, 256, 0, st)(p, (int)v, (float*)rel_out, (float*)adj_out);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

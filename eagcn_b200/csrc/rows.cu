@@ -11,6 +11,7 @@ namespace eagcn {
 // one warp per row, lanes stride the feature dimension (float4 when F % 4 == 0)
 __global__ void __launch_bounds__(256) rows_gather_kernel(PlanDev p, const float* __restrict__ dense,
                                                           float* __restrict__ packed, int F) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
   if (t >= p.t_cap) return;
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(PlanDev p, const float
 
 __global__ void __launch_bounds__(256) rows_scatter_kernel(PlanDev p, const float* __restrict__ packed,
                                                            float* __restrict__ dense, int F) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pos = blockIdx.x * 8 + warp;
   if (pos >= p.B * p.N) return;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(256) rows_scatter_kernel(PlanDev p, const floa
 // largest molecule would otherwise be a 132-deep serial chain), the groups are combined in fixed order
 __global__ void __launch_bounds__(512) readout_sum_kernel(PlanDev p, const float* __restrict__ packed,
                                                           float* __restrict__ out, int F) {
+  pdl_prologue();
   __shared__ float s[8][64];
   const int b = blockIdx.x;
   const int cx = threadIdx.x & 63, g = threadIdx.x >> 6;
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(512) readout_sum_kernel(PlanDev p, const float
 
 __global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const float* __restrict__ dout,
                                                               float* __restrict__ dpacked, int F) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
   if (t >= p.t_cap) return;
@@ -91,7 +95,7 @@ extern "C" int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, vo
   if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
   EAGCN_PROF("rows_gather_kernel", (cudaStream_t)stream);
-  rows_gather_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dense, (float*)packed, (int)F);
+  EAGCN_LAUNCH(rows_gather_kernel, (p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream)(p, (const float*)dense, (float*)packed, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -99,7 +103,7 @@ extern "C" int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, 
   if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
   EAGCN_PROF("rows_scatter_kernel", (cudaStream_t)stream);
-  rows_scatter_kernel<<<(p.B * p.N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)dense, (int)F);
+  EAGCN_LAUNCH(rows_scatter_kernel, (p.B * p.N + 7) / 8, 256, 0, (cudaStream_t)stream)(p, (const float*)packed, (float*)dense, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -108,7 +112,7 @@ extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, v
   PlanDev p = to_dev(plan);
   dim3 grid(p.B, (unsigned)((F + 63) / 64));
   EAGCN_PROF("readout_sum_kernel", (cudaStream_t)stream);
-  readout_sum_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(p, (const float*)packed, (float*)out, (int)F);
+  EAGCN_LAUNCH(readout_sum_kernel, grid, 512, 0, (cudaStream_t)stream)(p, (const float*)packed, (float*)out, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }
@@ -116,7 +120,7 @@ extern "C" int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout,
   if (!plan_ok(plan) || !dout || !dpacked || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
   EAGCN_PROF("readout_sum_bwd_kernel", (cudaStream_t)stream);
-  readout_sum_bwd_kernel<<<(p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, (const float*)dout, (float*)dpacked, (int)F);
+  EAGCN_LAUNCH(readout_sum_bwd_kernel, (p.t_cap + 7) / 8, 256, 0, (cudaStream_t)stream)(p, (const float*)dout, (float*)dpacked, (int)F);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -47,7 +47,9 @@ class Dense(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-stdv, stdv)
 
-    mm_engine = "cuda"          # 'cuda': eagcn_mm (split-K FFMA, fixed-order reduce); 'torch': library GEMM
+    # 'torch': library GEMM (measured 3x faster than the FFMA kernel on these skinny shapes: 63 vs 197 us per step);
+    # 'cuda': eagcn_mm (strict fp32, split-K with fixed-order reduction -- bit-reproducible)
+    mm_engine = "torch"
 
     def forward(self, input):
         if self.mm_engine == "cuda" and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 11
+#define EAGCN_ABI_VERSION 12
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -248,6 +248,12 @@ int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock st
 int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);
 int eagcn_get_agg_mode(void);
+/* --- programmatic dependent launch ------------------------------------------------------------- */
+/* 1 (default): kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization -- every kernel begins
+ * with griddepcontrol.launch_dependents + griddepcontrol.wait, so results are those of plain stream order while the
+ * scheduling latency of the next launch overlaps the running kernel; 0: plain launches.  Process-wide.            */
+int eagcn_set_pdl(int on);
+int eagcn_get_pdl(void);
 /* stand-alone projection product  C[m_cap, N] = A[m_cap, K] . B[N, K]^T  (fp32, rows contiguous; lda/ldb/ldc
  * in elements).  Only the first min(*m_dev, m_cap) rows are live (m_dev: device int32); the remaining
  * rows of C are written as zeros.  engine: 0 = tcgen05 3xTF32 (EAGCN_E_UNSUPPORTED if the layout does

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
                                                                  const uint8_t* __restrict__ codes, RelPtrs rel) {
   pdl_prologue();
   __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
+  __shared__ unsigned s_mask[8][8];
   __shared__ int s_hit[8][EAGCN_MAX_VIEWS][32];      // per (view, edge of the chunk): (#nonzero planes << 16) + plane index
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
@@ -154,9 +155,11 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
   }
   bool bad = false;
   for (int r = 0; r < kRowsPerWarp; ++r) {
-    const int lr = warp * kRowsPerWarp + r;
+    // rows interleaved over the warps (w, w+8, ...): the active rows of a molecule are consecutive, so consecutive
+    // rows per warp left some warps with four active rows and others with none -- the kernel ran at the slowest warp
+    const int lr = r * (kPackRows / kRowsPerWarp) + warp;
     const int row = row0 + lr;
-    if (row >= P) break;
+    if (row >= P) continue;
     const int deg = s_deg[lr];
     if (deg == 0 || s_t[lr] >= p.t_cap) continue;
     const int e0 = s_e[lr];
@@ -164,11 +167,28 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
     const int b = row / p.N, i = row - b * p.N;
     const size_t ba = ((size_t)b * p.N + i) * p.N, bc = (((size_t)b * p.V) * p.N + i) * p.N;
     int run = 0;
-    for (int j0 = 0; j0 < p.N; j0 += 32) {
-      const int j = j0 + lane;
-      const bool nz = (j < p.N) && adj_at<kCodes>(adj, codes, p, ba, bc, j) != 0.0f;
-      const unsigned m = __ballot_sync(0xffffffffu, nz);
+    for (int jb = 0; jb < p.N; jb += 256) {
+    // the adjacency row is fetched 8 chunks (256 columns) at a time: one memory round trip per row instead of one per
+    // 32-column chunk; the chunk masks go through shared memory (dynamic indexing)
+    {
+      float a8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int jj = jb + c * 32 + lane;
+        a8[c] = jj < p.N ? adj_at<kCodes>(adj, codes, p, ba, bc, jj) : 0.0f;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const unsigned mk = __ballot_sync(0xffffffffu, a8[c] != 0.0f);
+        if (lane == 0) s_mask[warp][c] = mk;
+      }
+      __syncwarp();
+    }
+    for (int c = 0; c < 8 && jb + c * 32 < p.N; ++c) {
+      const unsigned m = s_mask[warp][c];
       if (m == 0) continue;
+      const int j0 = jb + c * 32, j = j0 + lane;
+      const bool nz = (m >> lane) & 1u;
       const int ne = __popc(m);
       const int slot = __popc(m & ((1u << lane) - 1u));          // edge index of this lane inside the chunk
       if (nz) p.colpos[e0 + run + slot] = b * p.N + j;
@@ -223,6 +243,8 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
         __syncwarp();
       }
       run += ne;
+    }
+    __syncwarp();
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_NOT_ONEHOT);

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -105,6 +105,7 @@ _PROTOS = {
                          c_int64, c_void_p]),
     "eagcn_gemm_trace": (c_int, [c_void_p, c_int64]),
     "eagcn_gemm_trace_stride": (c_int64, []),
+    "eagcn_rng_fork": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

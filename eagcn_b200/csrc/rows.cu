@@ -88,8 +88,30 @@ __global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const f
   for (int c = lane; c < F; c += 32) dst[c] = __ldg(src + c);
 }
 
+// snapshot the philox (seed, offset) for one dropout call site and advance the live state: one launch instead of a
+// clone plus an add (both graph-replay safe, but two kernels per layer call)
+__global__ void rng_fork_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ snap,
+                                unsigned long long inc) {
+  pdl_prologue();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long seed = state[0], off = state[1];
+    snap[0] = seed; snap[1] = off;
+    state[1] = off + inc;
+  }
+}
+
 }  // namespace eagcn
 using namespace eagcn;
+
+extern "C" int eagcn_rng_fork(void* state, void* snapshot, int64_t increment, void* stream) {
+  if (!state || !snapshot || increment <= 0) return EAGCN_E_ARG;
+  EAGCN_PROF("rng_fork_kernel", stream);
+  EAGCN_LAUNCH(rng_fork_kernel, 1, 32, 0, stream)((unsigned long long*)state, (unsigned long long*)snapshot,
+                                                  (unsigned long long)increment);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
 
 extern "C" int eagcn_rows_gather(const eagcn_plan_t* plan, const void* dense, void* packed, int64_t F, void* stream) {
   if (!plan_ok(plan) || !dense || !packed || F <= 0) return EAGCN_E_ARG;

@@ -55,6 +55,12 @@ class RngState:
     def advance(self):
         self.state.add_(self._inc)
 
+    def fork(self):
+        """Snapshot for one dropout call site + advance of the live state, in one (graph-capturable) launch."""
+        snap = torch.empty_like(self.state)
+        check(lib().eagcn_rng_fork(ptr(self.state), ptr(snap), 1 << 20, _stream()), "eagcn_rng_fork")
+        return snap
+
 
 def manual_seed(seed, device=None):
     """Seed the dropout generator of the CUDA path (independent of torch's generator, layers.py:94)."""
@@ -129,7 +135,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         rng = RngState.get(dev)
         rng_snapshot = None
         if cfg.training and cfg.p_drop > 0.0:
-            rng_snapshot = rng.state.clone()        # backward regenerates the same keep mask from it
+            rng_snapshot = rng.fork()               # backward regenerates the same keep mask from it
         w.H, w.Z, w.Y, w.X, w.invR = ptr(H), ptr(Z), ptr(Y), ptr(X), ptr(invR)
         w.wall, w.ball, w.sig, w.partial, w.sums = ptr(wall), ptr(ball), ptr(sig), ptr(partial), ptr(sums)
         w.wallT, w.wsplit = ptr(wallT), ptr(wsplit)
@@ -144,8 +150,6 @@ class _GraphConvLayerFn(torch.autograd.Function):
         if cfg.training and cfg.stat_allreduce is not None:
             cfg.stat_allreduce(sums)
         check(L.eagcn_layer_forward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_forward_b")
-        if rng_snapshot is not None:
-            rng.advance()
         ctx.plan, ctx.cfg, ctx.buffers, ctx.params = plan, cfg, buffers, params
         ctx.saved = (H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot)
         return X
@@ -341,7 +345,7 @@ class _HeadFn(torch.autograd.Function):
         L = lib()
         part = torch.empty(int(L.eagcn_head_part_floats(B, F, D1, D2)), **f32)
         rng = RngState.get(dev)
-        snap = rng.state.clone() if (training and p_drop > 0.0) else None
+        snap = rng.fork() if (training and p_drop > 0.0) else None
         h = HeadStruct()
         h.B, h.F, h.D1, h.D2, h.NC = B, F, D1, D2, NC
         h.training, h.rng_stream = int(training), int(rng_stream)
@@ -359,8 +363,6 @@ class _HeadFn(torch.autograd.Function):
         h.a1, h.a2, h.out = a1.data_ptr(), a2.data_ptr(), out.data_ptr()
         h.part, h.bar = part.data_ptr(), _head_bar(dev).data_ptr()
         check(L.eagcn_head_forward(ctypes.byref(h), _stream()), "eagcn_head_forward")
-        if snap is not None:
-            rng.advance()
         ctx.cfg, ctx.bufs = cfg, bufs
         ctx.saved = (x0, params, a1, a2, stats, snap)
         return out, a2
@@ -422,14 +424,12 @@ class _BnActFn(torch.autograd.Function):
         mean = torch.empty(C, dtype=_F32, device=x.device)
         invstd = torch.empty(C, dtype=_F32, device=x.device)
         rng = RngState.get(x.device)
-        snap = rng.state.clone() if (training and p_drop > 0.0) else None
+        snap = rng.fork() if (training and p_drop > 0.0) else None
         g, b = gamma.detach().contiguous(), beta.detach().contiguous()
         check(lib().eagcn_bn_act_forward(ptr(x), ptr(y), ptr(g), ptr(b), ptr(rm), ptr(rv),
                                          ptr(nbt) if nbt is not None else None, ptr(mean), ptr(invstd), B, C,
                                          int(training), int(relu), float(p_drop), ptr(snap) if snap is not None else None,
                                          int(rng_stream), float(momentum), float(eps), _stream()), "eagcn_bn_act_forward")
-        if snap is not None:
-            rng.advance()
         ctx.cfg = cfg
         ctx.saved = (x, g, b, mean, invstd, snap)
         return y

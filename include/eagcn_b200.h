@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 12
+#define EAGCN_ABI_VERSION 13
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -179,6 +179,9 @@ int eagcn_attention_dense_bwd(const eagcn_plan_t* plan, const eagcn_layer_t* lay
 
 /* --- test hook: the keep mask eagcn_layer_forward_b draws (u8 [t_cap, fo_tot]) ------------- */
 int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t fo_tot, void* keep_out, void* stream);
+/* snapshot[0..1] = state[0..1] (philox seed, offset: device u64 [2]); state[1] += increment.  One call per dropout
+ * site and forward pass: forward and backward of that site both read the snapshot (F.dropout, layers.py:94).        */
+int eagcn_rng_fork(void* state, void* snapshot, int64_t increment, void* stream);
 /* same generator over a flat index range (the fused head draws element m*D1+k of stream rng_stream):
  * keep_out u8 [total]                                                                          */
 int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, double p_drop, int64_t total, void* keep_out, void* stream);

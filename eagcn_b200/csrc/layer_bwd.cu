@@ -227,19 +227,6 @@ __global__ void __launch_bounds__(128) bn_bwd_apply_vec_kernel(PlanDev p, const 
   }
 }
 
-// dvec = [dbias | dgamma | dbeta]
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ ball, const float* __restrict__ invstd,
-                                                              const double* __restrict__ bsums, float* __restrict__ dvec,
-                                                              int C, int training) {
-  pdl_prologue();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
-  const double s1 = bsums[c], s2 = bsums[C + c];
-  dvec[c] = training ? 0.0f : (float)((double)ball[C + c] * (double)invstd[c] * s1);
-  dvec[C + c] = (float)s2;
-  dvec[2 * C + c] = (float)s1;
-}
-
 // grid (row tiles, V); kAggWarps warps x kAggRows rows.  Fo_v handled in super-chunks of 512 channels (4 x 128).
 template <int VEC>
 __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(PlanDev p, LayerDev L, const float* __restrict__ Z,
@@ -564,19 +551,6 @@ __global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_tile_kernel(PlanDev p,
 }
 
 static bool tile_bwd_ok(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w);
-
-// datt[v][i] = sum over live tiles (fixed order)
-__global__ void __launch_bounds__(256) datt_reduce_kernel(PlanDev p, const float* __restrict__ dpart,
-                                                          float* __restrict__ datt, int V) {
-  pdl_prologue();
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= V * EAGCN_SIG_STRIDE) return;
-  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
-  const int ntile = (T + kStatRows - 1) / kStatRows;
-  double a = 0.0;
-  for (int t = 0; t < ntile; ++t) a += (double)dpart[(size_t)t * V * EAGCN_SIG_STRIDE + i];
-  datt[i] = (float)a;
-}
 
 // One launch finishing the layer backward:
 //  (a) dW: sum the split-K partials [ns][fin][C] in z order and store them VIEW-BLOCKED -- view v's [fin, fo_v]

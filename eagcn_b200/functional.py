@@ -32,6 +32,9 @@ class LayerConfig:
     # BatchNorm statistics across data-parallel ranks: callable(tensor) -> None that
     # all-reduces (sum) an fp64 [2, fo_tot] tensor in place, or None for per-replica statistics
     stat_allreduce: object = None
+    # also return z_pad [fo_tot]: the post-BatchNorm pre-activation every bond-less / padded row holds (Y = b there).
+    # 'Weighted_sum' does not mask those rows (layers.py:314-316), so their value and its gradient matter.
+    want_pad: bool = False
 
 
 class RngState:
@@ -152,10 +155,14 @@ class _GraphConvLayerFn(torch.autograd.Function):
         check(L.eagcn_layer_forward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_forward_b")
         ctx.plan, ctx.cfg, ctx.buffers, ctx.params = plan, cfg, buffers, params
         ctx.saved = (H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot)
+        if cfg.want_pad:
+            # ball rows: bias | gamma | beta.  mean / invstd are the statistics the kernels used (batch or running).
+            z_pad = ball[1] * (ball[0] - mean) * invstd + ball[2]
+            return X, z_pad
         return X
 
     @staticmethod
-    def backward(ctx, dX):
+    def backward(ctx, dX, gz=None):
         L = lib()
         plan, cfg, buffers, params = ctx.plan, ctx.cfg, ctx.buffers, ctx.params
         H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot = ctx.saved
@@ -164,7 +171,13 @@ class _GraphConvLayerFn(torch.autograd.Function):
         C = int(ls.fo_tot)
         T = plan.t_cap
         f32 = dict(dtype=_F32, device=dev)
-        dX = dX.contiguous()
+        dX = dX.contiguous() if dX is not None else torch.zeros(T, C, **f32)
+        # gradient reaching the padded rows' common pre-activation: they are part of the BatchNorm population, so their
+        # share S1_pad = sum g, S2_pad = sum g * xhat_pad of the two backward sums joins the active rows' sums
+        pad_sums = None
+        if gz is not None:
+            xhat_pad = ((ball[0] - mean) * invstd).double()
+            pad_sums = torch.stack((gz.double(), gz.double() * xhat_pad))
         w = WorkStruct()
         dY = torch.empty(T, C, **f32)
         Q = torch.empty(T, C, **f32)
@@ -191,7 +204,14 @@ class _GraphConvLayerFn(torch.autograd.Function):
         check(L.eagcn_layer_backward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_a")
         if cfg.training and cfg.stat_allreduce is not None:
             cfg.stat_allreduce(bsums)
+        if pad_sums is not None and cfg.training:
+            bsums.add_(pad_sums)
         check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+        if pad_sums is not None:                      # dvec rows: d bias | d gamma | d beta
+            dvec[1].add_(pad_sums[1].float())
+            dvec[2].add_(pad_sums[0].float())
+            if not cfg.training:
+                dvec[0].add_((ball[1] * invstd).mul(pad_sums[0].float()))
         grads = []
         off = 0
         for v in range(plan.V):

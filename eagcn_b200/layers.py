@@ -216,10 +216,31 @@ class GraphConv_Layer(nn.Module):
         cls._plan_cache = (key, weakref.ref(adjs), plan)
         return plan
 
+    def _weighted_sum(self, plan, cfg, H, params, buffers, p_drop):
+        """layers.py:314-316 + 431-437: x = sum_v ave.weight[v] * x_v, WITHOUT the row mask of the 'Concate' branch.
+        Rows with bonds come from the kernels; every other row (padding, bond-less atoms) holds the same value per
+        view -- dropout(relu(BatchNorm(bias))) -- which the reference leaves in its output, so it is reproduced here
+        (value from the statistics the kernels used; its gradient re-enters the BatchNorm backward sums)."""
+        V, fo = 5, self.total_output
+        X, z_pad = EF.graph_conv_layer(plan, cfg, H, params, buffers)
+        w = self.ave.weight
+        x = EF.scatter_rows(plan, (X.view(plan.t_cap, V, fo) * w.view(1, V, 1)).sum(1))
+        pad_v = torch.relu(z_pad).view(V, fo)
+        inactive = 1.0 - plan.row_mask()                                               # [B,N]
+        if self.training and p_drop > 0.0:
+            # the reference draws an independent keep mask for every padded element too (F.dropout on the dense tensor)
+            keep = (torch.rand(plan.B, plan.N, V, fo, device=X.device) >= p_drop).to(X.dtype) / (1.0 - p_drop)
+            pad = (keep * (pad_v * w.view(V, 1)).view(1, 1, V, fo)).sum(2)
+            return x + inactive.unsqueeze(2) * pad
+        return x + inactive.unsqueeze(2) * (pad_v * w.view(V, 1)).sum(0).view(1, 1, fo)
+
     def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None):
-        if self.structure != "Concate":
-            raise EagcnError("the CUDA path implements structure='Concate' (layers.py:312-313); "
-                             f"got {self.structure!r}")
+        if self.structure not in ("Concate", "Weighted_sum"):
+            raise EagcnError(f"structure {self.structure!r} is not supported (layers.py:279-283)")
+        wsum = self.structure == "Weighted_sum"
+        if wsum and (isinstance(afms, PackedRows) or any(b.node_feature_out != self.total_output for b in self.blocks)):
+            raise EagcnError("structure='Weighted_sum' (layers.py:314-316) takes dense [B,N,F] features and five views "
+                             "of equal width: its un-masked padded rows have no packed-row representation")
         if isinstance(adjs, GraphPlan):
             plan = adjs
         else:
@@ -233,13 +254,18 @@ class GraphConv_Layer(nn.Module):
         p_drop = float(self.block1.dropout)
         cfg = EF.LayerConfig(fin=self.node_feature_in, fo=tuple(b.node_feature_out for b in self.blocks),
                              training=self.training, p_drop=p_drop, rng_stream=self.rng_stream,
-                             stat_allreduce=self.stat_allreduce)
+                             stat_allreduce=self.stat_allreduce, want_pad=wsum)
+        if wsum and self.stat_allreduce is not None:
+            raise EagcnError("structure='Weighted_sum' with global-batch BatchNorm is not implemented")
         params, buffers = [], []
         for b in self.blocks:
             params += b._view_params()
             buffers += b._bn_buffers()
-        X = EF.graph_conv_layer(plan, cfg, H, params, buffers)
-        x = PackedRows(X, plan) if packed_io else EF.scatter_rows(plan, X)            # layers.py:313
+        if wsum:
+            x = self._weighted_sum(plan, cfg, H, params, buffers, p_drop)
+        else:
+            X = EF.graph_conv_layer(plan, cfg, H, params, buffers)
+            x = PackedRows(X, plan) if packed_io else EF.scatter_rows(plan, X)        # layers.py:313
 
         A_weight = None
         if self.materialize_A:

@@ -62,13 +62,15 @@ class Dense(nn.Module):
 class LazyAtomRep:
     """Stand-in for ``x2.data.cpu()`` (models.py:102): materialises on first use."""
 
-    def __init__(self, packed: PackedRows):
-        self._packed = PackedRows(packed.rows.detach(), packed.plan)
+    def __init__(self, packed):
+        # PackedRows (Concate: dense() re-inserts the exact zeros of padded rows) or an already dense tensor
+        self._packed = PackedRows(packed.rows.detach(), packed.plan) if isinstance(packed, PackedRows) else packed.detach()
         self._value = None
 
     def materialize(self):
         if self._value is None:
-            self._value = self._packed.dense().cpu()
+            src = self._packed
+            self._value = (src.dense() if isinstance(src, PackedRows) else src).cpu()
             self._packed = None
         return self._value
 
@@ -86,8 +88,12 @@ class EAGCNStack(nn.Module):
     """
 
     def __init__(self, n_bfeat, n_afeat, widths, n_den1, n_den2, nclass, dropout, molfp_mode="sum",
-                 last_flags=None):
+                 last_flags=None, structure="Concate"):
         super().__init__()
+        if structure not in ("Concate", "Weighted_sum"):
+            raise EagcnError("EAGCNStack implements structure 'Concate' and 'Weighted_sum' (models.py:30-61); GCN / GAT "
+                             "are the reference's comparison baselines and stay on stock PyTorch")
+        self.structure = structure
         if molfp_mode not in ("sum", "ave"):
             raise EagcnError("CUDA read-out implements molfp_mode 'sum' / 'ave' (models.py:104-111)")
         self.molfp_mode, self.dropout = molfp_mode, dropout
@@ -100,11 +106,11 @@ class EAGCNStack(nn.Module):
         self.n_layers = len(widths)
         for l, w in enumerate(widths):
             last = bool(last_flags[l]) if last_flags is not None else False
-            layer = GraphConv_Layer(fin, n_bfeat, *w, dropout=dropout, structure="Concate", last=last)
+            layer = GraphConv_Layer(fin, n_bfeat, *w, dropout=dropout, structure=structure, last=last)
             layer.materialize_A = False
             layer.rng_stream = l
             setattr(self, f"layer{l + 1}", layer)
-            fin = sum(w)
+            fin = layer.total_output                                                # sum(w) | w[0] (layers.py:277-281)
         self.out_width = fin
         self.den1 = Dense(fin, n_den1)
         self.den2 = Dense(n_den1, n_den2)
@@ -123,11 +129,22 @@ class EAGCNStack(nn.Module):
             plan = adjs
         else:
             plan = GraphConv_Layer._plan_for(adjs, (TypeAtt, OrderAtt, AromAtt, ConjAtt, RingAtt))
-        h = afms if isinstance(afms, PackedRows) else PackedRows(EF.gather_rows(plan, afms), plan)
-        for layer in self.conv_layers:                                              # models.py:97-100
-            h, _ = layer(plan, h)
-        atom_representations = LazyAtomRep(h)                                       # models.py:102
-        x = EF.readout_sum(plan, h.rows)                                            # models.py:108
+        if self.structure == "Weighted_sum":
+            # the un-masked padded rows of this structure (layers.py:314-316) travel between layers and into the
+            # read-out sum exactly as in the reference: dense tensors end to end
+            if isinstance(afms, PackedRows):
+                raise EagcnError("structure='Weighted_sum' takes dense [B,N,F] atom features")
+            h = afms
+            for layer in self.conv_layers:                                          # models.py:97-100
+                h, _ = layer(plan, h)
+            atom_representations = LazyAtomRep(h)                                   # models.py:102
+            x = h.sum(1)                                                            # models.py:108 (padded rows included)
+        else:
+            h = afms if isinstance(afms, PackedRows) else PackedRows(EF.gather_rows(plan, afms), plan)
+            for layer in self.conv_layers:                                          # models.py:97-100
+                h, _ = layer(plan, h)
+            atom_representations = LazyAtomRep(h)                                   # models.py:102
+            x = EF.readout_sum(plan, h.rows)                                        # models.py:108
         if self.molfp_mode == "ave":                                                # models.py:109-111
             x = x / size.view(-1, 1).to(x.dtype)
         if self.fused_head and all(bn.momentum is not None and bn.affine and bn.track_running_stats
@@ -164,12 +181,14 @@ class EAGCN(EAGCNStack):
     def __init__(self, n_bfeat, n_afeat, n_sgc1_1, n_sgc1_2, n_sgc1_3, n_sgc1_4, n_sgc1_5,
                  n_sgc2_1, n_sgc2_2, n_sgc2_3, n_sgc2_4, n_sgc2_5, n_den1, n_den2, nclass, dropout,
                  structure="Concate", molfp_mode="sum", pool_num=5):
-        if structure != "Concate":
-            raise EagcnError("the CUDA path implements structure='Concate'; GCN/GAT/Weighted_sum are the "
-                             "reference's comparison baselines and stay on stock PyTorch")
         l1 = (n_sgc1_1, n_sgc1_2, n_sgc1_3, n_sgc1_4, n_sgc1_5)
         l2 = (n_sgc2_1, n_sgc2_2, n_sgc2_3, n_sgc2_4, n_sgc2_5)
+        if structure == "Weighted_sum":                                             # models.py:33-47: every view full width
+            l1, l2 = (sum(l1),) * 5, (sum(l2),) * 5
         l3 = tuple(2 * w for w in l2)                                               # models.py:56-61
         super().__init__(n_bfeat, n_afeat, [l1, l2, l3, l3], n_den1, n_den2, nclass, dropout, molfp_mode,
-                         last_flags=[False, False, False, True])
+                         last_flags=[False, False, False, True], structure=structure)
+        if structure == "Weighted_sum":
+            self.ngc1, self.ngc2 = l1[0], l2[0]
+            return
         self.ngc1, self.ngc2 = sum(l1), sum(l2)

@@ -59,6 +59,38 @@ def test_pack_roundtrip_bit_exact(case):
     assert torch.equal(plan.rcode[:, :E], plan3.rcode[:, :E])
 
 
+@pytest.mark.parametrize("B,fixed_n,pad_to,kind", [(6, 40, 300, "sparse"), (3, 290, 290, "sparse"), (2, 270, 300, "dense")])
+def test_pack_wide_padding_bit_exact(B, fixed_n, pad_to, kind):
+    """Padded widths beyond 256 columns (the packer fetches adjacency rows 256 columns at a time) and rows with more
+    than 256 neighbours: dense planes -> plan -> dense planes is the identity, and equals the uint8-code boundary."""
+    from eagcn_b200.plan import GraphPlan
+    from eagcn_b200.data import make_batch, DATASETS
+    dev = _cuda()
+    if kind == "dense":
+        batch = _dense_graph_batch(B, fixed_n, DATASETS["tox21"]["kb"], 8, seed=5)
+        import numpy as _np
+        pad = pad_to - fixed_n
+        batch.adj = _np.pad(batch.adj, ((0, 0), (0, pad), (0, pad)))
+        batch.afm = _np.pad(batch.afm, ((0, 0), (0, pad), (0, 0)))
+        batch.codes = _np.pad(batch.codes, ((0, 0), (0, 0), (0, pad), (0, pad)), constant_values=255)
+    else:
+        batch = make_batch(B, dataset="tox21", seed=11, fixed_n=fixed_n, pad_to=pad_to, n_afeat=8)
+    adj, afm, *rels = _to(dev, [torch.from_numpy(a) for a in batch.dense()])
+    plan = GraphPlan.build(adj, rels).check()
+    assert plan.n_edges == int(adj.sum())
+    for v in range(5):
+        rel_back, adj_back = plan.unpack_view(v)
+        assert torch.equal(rel_back, rels[v])
+        assert torch.equal(adj_back, adj)
+    plan2 = GraphPlan.from_codes(torch.from_numpy(batch.codes).to(dev), batch.channels).check()
+    E = plan.n_edges
+    assert plan2.n_edges == E
+    for name in ("col", "colpos", "rev"):
+        assert torch.equal(getattr(plan, name)[:E], getattr(plan2, name)[:E])
+    assert torch.equal(plan.code[:, :E], plan2.code[:, :E])
+    assert torch.equal(plan.rcode[:, :E], plan2.rcode[:, :E])
+
+
 def test_pack_rejects_malformed():
     from eagcn_b200.plan import GraphPlan
     dev = _cuda()
@@ -100,7 +132,7 @@ def _our_layer(g, dev):
     return layer
 
 
-@pytest.mark.parametrize("case", [c for c in golden_cases("layer_") if c != "layer_wsum"])
+@pytest.mark.parametrize("case", golden_cases("layer_"))
 def test_layer_forward_backward_vs_golden(case):
     dev = _cuda()
     g = Golden(case)
@@ -111,7 +143,10 @@ def test_layer_forward_backward_vs_golden(case):
     assert rel_err(x.cpu(), g.out["x"]) <= TOL
     assert rel_err(A.cpu(), g.out["A"]) <= TOL
     m = ins[0].max(2).values
-    assert float((x.detach() * (1 - m).unsqueeze(2)).abs().max()) == 0.0      # layers.py:313: exact zeros
+    if str(g.meta["structure"]) == "Concate":
+        assert float((x.detach() * (1 - m).unsqueeze(2)).abs().max()) == 0.0  # layers.py:313: exact zeros
+    else:                                                                     # layers.py:314-316: padded rows NOT masked
+        assert float((x.detach() * (1 - m).unsqueeze(2)).abs().max()) > 0.0
     loss = (x * g.cot["x"].to(dev)).sum() + (A * g.cot["A"].to(dev)).sum()
     loss.backward()
     assert rel_err(ins[1].grad.cpu(), g.grad["afm"]) <= 2 * TOL
@@ -135,13 +170,62 @@ def test_layer_forward_backward_vs_golden(case):
                 assert rel_err(sd[k].cpu(), ref) <= TOL, k
 
 
-def test_weighted_sum_not_silently_wrong():
-    from eagcn_b200._lib import EagcnError
+def test_weighted_sum_eval_and_dropout():
+    """'Weighted_sum' beyond the golden case (training, p = 0): eval mode against the oracle, and the training-mode
+    dropout on padded rows keeps the reference's statistics (mean over many draws == the p = 0 value)."""
+    from eagcn_b200 import layers as EL
     dev = _cuda()
     g = Golden("layer_wsum")
     layer = _our_layer(g, dev)
-    with pytest.raises(EagcnError):
-        layer(*_to(dev, g.dense()))
+    layer.eval()
+    ins = _to(dev, g.dense())
+    ins[1].requires_grad_(True)
+    x, _ = layer(*ins)
+    sd = O.clone_sd({("layer1." + k): v for k, v in layer.state_dict().items()}, requires_grad=True)
+    dense = g.dense()
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    afm_ref = dense[1].clone().requires_grad_(True)
+    ref = O.layer_forward(sd, "layer1.", dense[0], afm_ref, codes, False, structure="Weighted_sum")
+    assert rel_err(x.cpu(), ref["x"]) <= TOL
+    R = torch.randn(ref["x"].shape, generator=torch.Generator().manual_seed(2))
+    (ref["x"] * R).sum().backward()
+    (x * R.to(dev)).sum().backward()
+    assert rel_err(ins[1].grad.cpu(), afm_ref.grad) <= 2 * TOL
+    named = dict(layer.named_parameters())
+    scale = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    for k, prm in named.items():
+        ref_g = sd["layer1." + k].grad
+        if ref_g is None:
+            continue
+        assert prm.grad is not None, k
+        assert float((prm.grad.cpu() - ref_g).abs().max()) / max(float(ref_g.abs().max()), 1e-3 * scale) <= 5 * TOL, k
+    # dropout on the un-masked padded rows: unbiased
+    layer2 = EL.GraphConv_Layer(layer.node_feature_in, layer.block1.bond_feature_num,
+                                *[layer.total_output] * 5, dropout=0.5, structure="Weighted_sum").to(dev)
+    layer2.load_state_dict(layer.state_dict())
+    layer2.train()
+    with torch.no_grad():
+        m = ins[0].max(2).values
+        x0, _ = _train_p0(layer2, ins)
+        acc = torch.zeros_like(x0)
+        n = 200
+        for _ in range(n):
+            xi, _ = layer2(*[t.detach() for t in ins])
+            acc += xi
+        pad_mean = (acc / n) * (1 - m).unsqueeze(2)
+        pad_ref = x0 * (1 - m).unsqueeze(2)
+        assert float((pad_mean - pad_ref).abs().max()) <= 0.25 * float(pad_ref.abs().max()) + 1e-6
+
+
+def _train_p0(layer, ins):
+    p = [b.dropout for b in layer.blocks]
+    for b in layer.blocks:
+        b.dropout = 0.0
+    try:
+        return layer(*[t.detach() for t in ins])
+    finally:
+        for b, q in zip(layer.blocks, p):
+            b.dropout = q
 
 
 # ------------------------------------------------------------------ model vs golden
@@ -605,3 +689,49 @@ def test_bn_act_vs_torch(B, C, training, relu, p):
     assert rel_err(xa.grad, xb.grad) <= 2 * TOL
     assert rel_err(bn.weight.grad, ref_bn.weight.grad) <= 2 * TOL
     assert rel_err(bn.bias.grad, ref_bn.bias.grad) <= 2 * TOL
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_weighted_sum_model_vs_oracle(training):
+    """EAGCN(structure='Weighted_sum') (models.py:33-47, layers.py:314-316): four layers whose un-masked padded rows
+    flow into the read-out sum, against the oracle, outputs and gradients."""
+    from eagcn_b200 import models as EM
+    from eagcn_b200.data import make_batch
+    dev = _cuda()
+    kb = 5
+    batch = make_batch(6, dataset="freesolv", seed=31, kb=kb)
+    torch.manual_seed(5)
+    model = EM.EAGCN(kb, 24, 2, 1, 1, 1, 1, 3, 1, 1, 1, 2, 8, 4, 3, dropout=0.0, structure="Weighted_sum").to(dev)
+    gen = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if n.endswith("bn.weight") or n.endswith("BN.weight") or "bn_den" in n and n.endswith("weight"):
+                prm.copy_(torch.rand(prm.shape, generator=gen) + 0.5)
+            elif n.endswith("ave.weight"):
+                prm.copy_(torch.rand(prm.shape, generator=gen) + 0.2)
+    model.train(training)
+    dense = [torch.from_numpy(a) for a in batch.dense()]
+    sizes = torch.from_numpy(batch.sizes)
+    sd = O.clone_sd(model.state_dict(), requires_grad=True)
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    h_ref, _ = O.stack_forward(sd, dense[0], dense[1], codes, 4, training, structure="Weighted_sum",
+                               last_flags=[False, False, False, True])
+    out_ref, g_ref = O.head_forward(sd, h_ref, sizes, training)
+    ins = _to(dev, dense)
+    out, atom_rep, g_rep = model(*ins, size=sizes.to(dev))
+    assert rel_err(atom_rep.materialize(), h_ref.detach()) <= TOL
+    assert rel_err(out.cpu(), out_ref) <= 2 * TOL
+    R = torch.randn(out_ref.shape, generator=gen)
+    (out_ref * R).sum().backward()
+    (out * R.to(dev)).sum().backward()
+    named = dict(model.named_parameters())
+    scale = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    checked = 0
+    for k, prm in named.items():
+        ref_g = sd[k].grad
+        if ref_g is None or prm.grad is None:
+            continue
+        denom = max(float(ref_g.abs().max()), 1e-2 * scale)
+        assert float((prm.grad.cpu() - ref_g).abs().max()) / denom <= 2e-4, k
+        checked += 1
+    assert checked >= 40

@@ -85,6 +85,27 @@ class GraphConv_base(nn.Module):
         return f"{self.__class__.__name__} ({self.in_features} -> {self.out_features})"
 
 
+class Diff_Pooling(nn.Module):
+    """layers.py:492-506 (the definition in effect): soft assignment of the atoms to ``out_size`` clusters from the
+    last layer's normalised attention A [B,N,N] and atom features X [B,N,F].  Not on the hot path: two bmm + two mm on
+    one dense [B,N,N] map, composed from library ops; A comes from the CUDA path (eagcn_attention_dense + the
+    'last' normalisation of GraphConv_Layer) and carries the gradients of self_r / ave_A / att."""
+
+    def __init__(self, in_feature, out_feature, out_size):
+        super().__init__()
+        self.feature_layer = GraphConv_base(in_feature, out_feature)
+        self.adjacent_layer = GraphConv_base(in_feature, out_size)
+
+    def forward(self, A, X):
+        X_feature = F.relu(self.feature_layer(A, X))                                  # layers.py:499
+        S = F.softmax(self.adjacent_layer(A, X), dim=2)                               # layers.py:500
+        S_T = torch.transpose(S, 1, 2)
+        X_feature = F.relu(torch.bmm(S_T, X_feature))                                 # layers.py:503
+        A_update = torch.bmm(torch.bmm(S_T, A), S)                                    # layers.py:504
+        A_update = F.dropout(A_update, p=0.3)              # layers.py:505: always on (training defaults to True)
+        return A_update, X_feature
+
+
 class AFM_BatchNorm(nn.Module):
     """layers.py:394-412: BatchNorm1d over the feature axis of [B,N,F], statistics over ALL B*N
     positions.  ``weight`` [1,1] / ``bias`` [1] exist only for state_dict compatibility (the reference

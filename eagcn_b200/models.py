@@ -23,7 +23,7 @@ from torch.nn.parameter import Parameter
 
 from . import functional as EF
 from ._lib import EagcnError
-from .layers import GraphConv_Layer, PackedRows, _param_device
+from .layers import Diff_Pooling, GraphConv_Layer, PackedRows, _param_device
 from .plan import GraphPlan
 
 
@@ -88,14 +88,14 @@ class EAGCNStack(nn.Module):
     """
 
     def __init__(self, n_bfeat, n_afeat, widths, n_den1, n_den2, nclass, dropout, molfp_mode="sum",
-                 last_flags=None, structure="Concate"):
+                 last_flags=None, structure="Concate", pool_num=5):
         super().__init__()
         if structure not in ("Concate", "Weighted_sum"):
             raise EagcnError("EAGCNStack implements structure 'Concate' and 'Weighted_sum' (models.py:30-61); GCN / GAT "
                              "are the reference's comparison baselines and stay on stock PyTorch")
         self.structure = structure
-        if molfp_mode not in ("sum", "ave"):
-            raise EagcnError("CUDA read-out implements molfp_mode 'sum' / 'ave' (models.py:104-111)")
+        if molfp_mode not in ("sum", "ave", "pool"):
+            raise EagcnError("read-out modes: 'sum' / 'ave' / 'pool' (models.py:104-111)")
         self.molfp_mode, self.dropout = molfp_mode, dropout
         # True: one CUDA kernel per direction for the dense head (eagcn_b200/csrc/head.cu, parity-tested).  Measured
         # slower than the ~35 stock PyTorch launches it replaces at B = 256 (un-pipelined operand loads), so it is
@@ -112,6 +112,12 @@ class EAGCNStack(nn.Module):
             setattr(self, f"layer{l + 1}", layer)
             fin = layer.total_output                                                # sum(w) | w[0] (layers.py:277-281)
         self.out_width = fin
+        if molfp_mode == "pool":                                                    # models.py:90-92
+            if structure != "Concate" or last_flags is None or not last_flags[-1]:
+                raise EagcnError("molfp_mode='pool' needs structure='Concate' and last=True on the final layer")
+            self.pool1 = Diff_Pooling(fin, fin, pool_num)
+            self.pool3 = Diff_Pooling(fin, fin, 1)            # constructed but unused by the reference's forward
+            layer.materialize_A = True                        # Diff_Pooling consumes the final layer's attention
         self.den1 = Dense(fin, n_den1)
         self.den2 = Dense(n_den1, n_den2)
         self.den3 = Dense(n_den2, nclass)
@@ -142,9 +148,13 @@ class EAGCNStack(nn.Module):
         else:
             h = afms if isinstance(afms, PackedRows) else PackedRows(EF.gather_rows(plan, afms), plan)
             for layer in self.conv_layers:                                          # models.py:97-100
-                h, _ = layer(plan, h)
+                h, A = layer(plan, h)
             atom_representations = LazyAtomRep(h)                                   # models.py:102
-            x = EF.readout_sum(plan, h.rows)                                        # models.py:108
+            if self.molfp_mode == "pool":                                           # models.py:104-106
+                _, xp = self.pool1(A, h.dense())
+                x = xp.sum(1)
+            else:
+                x = EF.readout_sum(plan, h.rows)                                    # models.py:108
         if self.molfp_mode == "ave":                                                # models.py:109-111
             x = x / size.view(-1, 1).to(x.dtype)
         if self.fused_head and all(bn.momentum is not None and bn.affine and bn.track_running_stats
@@ -187,7 +197,7 @@ class EAGCN(EAGCNStack):
             l1, l2 = (sum(l1),) * 5, (sum(l2),) * 5
         l3 = tuple(2 * w for w in l2)                                               # models.py:56-61
         super().__init__(n_bfeat, n_afeat, [l1, l2, l3, l3], n_den1, n_den2, nclass, dropout, molfp_mode,
-                         last_flags=[False, False, False, True], structure=structure)
+                         last_flags=[False, False, False, True], structure=structure, pool_num=pool_num)
         if structure == "Weighted_sum":
             self.ngc1, self.ngc2 = l1[0], l2[0]
             return

@@ -163,14 +163,29 @@ def stack_forward(sd, adj, afm, codes, n_layers, training, p=0.0, keeps=None, st
     return h, outs
 
 
-def head_forward(sd, x_atoms, sizes, training, p=0.0, keep=None, molfp_mode="sum", x0=None, relu_masks=None):
-    """Read-out + dense head (models.py:104-121), molfp_mode in {'sum','ave'}.  x0: start from a given read-out
-    [B,F] instead of x_atoms.  relu_masks: optional (mask1 [B,D1], mask2 [B,D2]) replacing the two ReLU decisions
-    (see block_forward)."""
+def diff_pool(sd, pre, A, X):
+    """Diff_Pooling.forward (the class actually in effect, layers.py:492-506; the first definition at :476-490 is
+    inside a string literal).  GraphConv_base without bias (layers.py:38-45): bmm(A, X) then mm with the weight.
+    The returned A_update goes through an always-on F.dropout(p=0.3) in the reference but is never used by
+    models.py:104-106, so only X_feature is restated."""
+    ax = torch.bmm(A, X)                                                  # layers.py:39
+    feat = F.relu(ax.matmul(sd[pre + "feature_layer.weight"]))            # layers.py:499
+    S = F.softmax(ax.matmul(sd[pre + "adjacent_layer.weight"]), dim=2)    # layers.py:500
+    return F.relu(torch.bmm(S.transpose(1, 2), feat))                     # layers.py:501-503
+
+
+def head_forward(sd, x_atoms, sizes, training, p=0.0, keep=None, molfp_mode="sum", x0=None, relu_masks=None,
+                 A_last=None):
+    """Read-out + dense head (models.py:104-121), molfp_mode in {'sum','ave','pool'}.  x0: start from a given
+    read-out [B,F] instead of x_atoms.  relu_masks: optional (mask1 [B,D1], mask2 [B,D2]) replacing the two ReLU
+    decisions (see block_forward).  A_last: the last layer's normalised averaged attention [B,N,N] ('pool')."""
     if x0 is None:
-        x = x_atoms.sum(1)                                                # models.py:108
-        if molfp_mode == "ave":
-            x = x / sizes.view(-1, 1).to(x.dtype)                         # models.py:110-111
+        if molfp_mode == "pool":
+            x = diff_pool(sd, "pool1.", A_last, x_atoms).sum(1)           # models.py:104-106
+        else:
+            x = x_atoms.sum(1)                                            # models.py:108
+            if molfp_mode == "ave":
+                x = x / sizes.view(-1, 1).to(x.dtype)                     # models.py:110-111
     else:
         x = x0
 

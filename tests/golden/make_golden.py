@@ -1,6 +1,6 @@
 """Generate golden vectors FROM THE UNMODIFIED REFERENCE classes (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 
 Imports /root/reference/eagcn_pytorch/{layers,models,utils}.py through oracle/ref_loader.py,
 runs them (CPU, fp32) on small seeded synthetic batches (eagcn_b200.data.make_batch) and writes
@@ -99,11 +99,11 @@ def layer_case(case, B, seed, kb, fouts, fin=24, training=True, structure="Conca
     save(case, batch, sd0, extra)
 
 
-def model_case(case, B, seed, dataset, kb, sgc1, sgc2, den, nclass, training=True, molfp="sum"):
+def model_case(case, B, seed, dataset, kb, sgc1, sgc2, den, nclass, training=True, molfp="sum", structure="Concate"):
     _, M, _ = ref_loader.load()
     batch = make_batch(B, dataset=dataset, seed=seed, kb=kb)
     model = M.EAGCN(kb, 24, *([sgc1] * 5), *([sgc2] * 5), den[0], den[1], nclass, dropout=0.0,
-                    structure="Concate", molfp_mode=molfp)
+                    structure=structure, molfp_mode=molfp)
     randomise(model, seed)
     for name, p in model.named_parameters():     # head: keep activations O(1)
         if name.startswith("den"):
@@ -116,7 +116,7 @@ def model_case(case, B, seed, dataset, kb, sgc1, sgc2, den, nclass, training=Tru
     R = torch.randn(out.shape, generator=g)
     (out * R).sum().backward()
     extra = {"out.y": out, "out.atom_rep": atom_rep, "out.graph_rep": graph_rep, "cot.y": R,
-             "meta.training": int(training), "meta.molfp": np.array(molfp),
+             "meta.training": int(training), "meta.molfp": np.array(molfp), "meta.structure": np.array(structure),
              "meta.dims": np.array([kb, sgc1, sgc2, den[0], den[1], nclass])}
     for name, p in model.named_parameters():
         if p.grad is not None:
@@ -130,6 +130,11 @@ def model_case(case, B, seed, dataset, kb, sgc1, sgc2, den, nclass, training=Tru
 def main():
     assert ref_loader.available(), "needs /root/reference (build container)"
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])                      # optional: regenerate just the named cases
+    global layer_case, model_case
+    _lc, _mc = layer_case, model_case
+    layer_case = lambda case, **kw: _lc(case, **kw) if (not only or case in only) else None   # noqa: E731
+    model_case = lambda case, **kw: _mc(case, **kw) if (not only or case in only) else None   # noqa: E731
     layer_case("layer_train", B=5, seed=11, kb=7, fouts=(6, 5, 4, 3, 2))
     layer_case("layer_eval", B=4, seed=12, kb=5, fouts=(8, 8, 8, 8, 8), training=False)
     layer_case("layer_last", B=3, seed=13, kb=4, fouts=(4, 4, 4, 4, 4), last=True)
@@ -139,6 +144,9 @@ def main():
     model_case("model_train", B=6, seed=21, dataset="freesolv", kb=5, sgc1=4, sgc2=6, den=(8, 4), nclass=3)
     model_case("model_eval", B=4, seed=22, dataset="freesolv", kb=5, sgc1=4, sgc2=6, den=(8, 4), nclass=1,
                training=False, molfp="ave")
+    model_case("model_wsum", B=5, seed=23, dataset="freesolv", kb=5, sgc1=1, sgc2=2, den=(8, 4), nclass=2,
+               structure="Weighted_sum")
+    model_case("model_pool", B=5, seed=24, dataset="freesolv", kb=5, sgc1=3, sgc2=4, den=(8, 4), nclass=2, molfp="pool")
 
 
 if __name__ == "__main__":

@@ -74,8 +74,10 @@ def test_model_vs_golden(case):
     adj, afm, *rels = g.dense()
     codes = [O.codes_from_onehot(adj, r) for r in rels]
     training = bool(g.meta["training"])
-    h, outs = O.stack_forward(sd, adj, afm, codes, 4, training, last_flags=[0, 0, 0, 1])
-    y, grep = O.head_forward(sd, h, torch.from_numpy(g.batch.sizes), training, molfp_mode=str(g.meta["molfp"]))
+    structure = str(g.meta["structure"]) if "structure" in g.meta else "Concate"
+    h, outs = O.stack_forward(sd, adj, afm, codes, 4, training, structure=structure, last_flags=[0, 0, 0, 1])
+    y, grep = O.head_forward(sd, h, torch.from_numpy(g.batch.sizes), training, molfp_mode=str(g.meta["molfp"]),
+                             A_last=outs[-1]["A_weight"])
     assert rel_err(h, g.out["atom_rep"]) <= TOL
     assert rel_err(y, g.out["y"]) <= 2 * TOL
     assert rel_err(grep, g.out["graph_rep"]) <= 2 * TOL

@@ -186,6 +186,8 @@ def run_b200(args):
     EF.set_gemm_engine(args.gemm)
     EF.set_agg_engine(args.agg)
     model = build_model(dev)
+    EF.Overlap.enabled = bool(args.overlap)
+    _lib.lib().eagcn_set_bn_act_mode(0 if args.bn_act == "vec" else 1)
     if args.no_pdl:
         _lib.lib().eagcn_set_pdl(0)
     from eagcn_b200 import models as _M2
@@ -228,6 +230,8 @@ def run_b200(args):
     def step_dense(s):
         for p in params:
             p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
+        if not args.layers_only:
+            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
         plan = GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
         if args.layers_only:
             return layers_only(plan, s)
@@ -240,6 +244,8 @@ def run_b200(args):
         planes are gathered at bonded pairs by the packer straight from host memory (zero-copy over PCIe)."""
         for p in params:
             p.grad = None
+        if not args.layers_only:
+            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
         plan = GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
         out, _, _ = model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
@@ -248,6 +254,8 @@ def run_b200(args):
     def step_codes(s):
         for p in params:
             p.grad = None
+        if not args.layers_only:
+            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
         plan = GraphPlan.from_codes(s.dev_codes, s.hb.channels, t_cap=s.t_cap, e_cap=s.e_cap)
         out, _, _ = model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
@@ -338,6 +346,7 @@ def run_b200(args):
         with torch.cuda.graph(g2, pool=pool):
             for p in params:
                 p.grad = None
+            model.prefetch_params()
             out, _, _ = model(s.zc_plan, s.dev_dense[1], size=s.size)
             out.sum().backward()
             if world > 1:
@@ -416,15 +425,20 @@ def run_b200(args):
     # ---- e2e: pinned host buffers -> H2D -> step -> D2H, every step ----
     out_host = torch.empty(BATCH, NCLASS).pin_memory()
 
-    # A real input pipeline prefetches: the H2D copy of batch i+1 (copy stream) overlaps the step of batch i.
-    # Every step still pays one full H2D + one D2H inside the timed region and ends with a host sync on its result.
+    # A real input pipeline prefetches.  Three stages on three streams: the H2D copies of batch i+depth (copy stream), the
+    # packing of batch i+1 from host memory (zero-copy layout only; pack stream) and the step of batch i (work stream)
+    # overlap.  Every step still pays one full H2D + one D2H inside the timed region and ends with a host sync on its
+    # result.
     copy_stream = torch.cuda.Stream()
-    h2d_done = [torch.cuda.Event() for _ in range(NB)]
+    pack_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event() for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    depth = max(1, min(args.e2e_depth, NB - 1))
 
     def make_e2e(layout):
-        state = {"prefetched": -1}
+        state = {"copied": -1, "ready": -1, "first": True}
 
-        def h2d(i):
+        def copy(i):
             s = slots[i % NB]
             with torch.cuda.stream(copy_stream):
                 if layout == "dense":
@@ -433,35 +447,52 @@ def run_b200(args):
                 elif layout == "zc":
                     s.dev_dense[0].copy_(s.host_dense[0], non_blocking=True)
                     s.dev_dense[1].copy_(s.host_dense[1], non_blocking=True)
-                    s.g_zc_pack.replay()                      # graph plan of this batch, gathered from host memory
                 else:
                     s.dev_codes.copy_(s.host_codes, non_blocking=True)
                     s.dev_dense[1].copy_(s.host_afm, non_blocking=True)
-                h2d_done[i % NB].record(copy_stream)
-            state["prefetched"] = i
+                copied[i % NB].record(copy_stream)
+            state["copied"] = i
+
+        def make_ready(i):
+            s = slots[i % NB]
+            if layout == "zc":
+                with torch.cuda.stream(pack_stream):
+                    pack_stream.wait_event(copied[i % NB])
+                    s.g_zc_pack.replay()                      # graph plan of this batch, gathered from host memory
+                    ready[i % NB].record(pack_stream)
+            state["ready"] = i
+
+        def advance(i_copy, i_ready):
+            for j in range(state["copied"] + 1, i_copy + 1):
+                copy(j)
+            for j in range(state["ready"] + 1, i_ready + 1):
+                make_ready(j)
 
         def step(i):
             s = slots[i % NB]
-            if state["prefetched"] != i:                     # first step of a run: nothing prefetched yet
+            if state["first"]:                                # first step of a run: nothing prefetched yet
+                state["first"] = False
+                state["copied"] = state["ready"] = i - 1
                 copy_stream.wait_stream(torch.cuda.current_stream())
-                h2d(i)
-            torch.cuda.current_stream().wait_event(h2d_done[i % NB])
+                pack_stream.wait_stream(torch.cuda.current_stream())
+            advance(i, i)
+            torch.cuda.current_stream().wait_event(ready[i % NB] if layout == "zc" else copied[i % NB])
             g, gout = {"dense": (s.g_dense, s.g_dense_out), "zc": (s.g_zc_main, s.g_zc_main_out),
                        "codes": (s.g_codes, s.g_codes_out)}[layout]
             g.replay()
             bucket.all_reduce()
             out_host.copy_(gout, non_blocking=True)
-            h2d(i + 1)                                        # prefetch the next batch while this step runs
+            advance(i + depth, i + 1)                         # prefetch while this step runs
             torch.cuda.current_stream().synchronize()         # the user reads this step's result
         return step
 
     k_e2e = max(5, min(args.steps, 30))
     ms_e2e_full, _ = timed(make_e2e("dense"), k_e2e, 3)
-    copy_stream.synchronize()
+    torch.cuda.synchronize()
     ms_e2e, _ = timed(make_e2e("zc"), k_e2e, 3)
-    copy_stream.synchronize()
+    torch.cuda.synchronize()
     ms_e2e_p, _ = timed(make_e2e("codes"), k_e2e, 3)
-    copy_stream.synchronize()
+    torch.cuda.synchronize()
     h2d_dense = int(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in slots]))
     h2d_zc = int(np.mean([s.host_dense[0].numel() * 4 + s.host_dense[1].numel() * 4 for s in slots]))
     zc_reads = int(np.mean([s.E * (KB + 10) * 32 for s in slots]))      # one 32-byte sector per (bonded pair, plane)
@@ -530,7 +561,13 @@ def run_b200(args):
                        "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
                        "mode": "train fwd+bwd", "bn_sync": "local",
                        "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else
-                       ("library GEMMs + fused CUDA BatchNorm/ReLU/dropout kernels" if model.head_bn == "cuda" else "stock PyTorch ops"),
+                       ({"tile": "CUDA tile GEMMs (mm_tile, split-K combined in-kernel)", "cuda": "CUDA FFMA GEMMs (eagcn_mm)",
+                         "torch": "library GEMMs"}[_M2.Dense.mm_engine] + " + fused CUDA BatchNorm/ReLU/dropout kernels ("
+                        + ("float4" if _lib.lib().eagcn_get_bn_act_mode() == 0 else "32-channel") + ")"
+                        if model.head_bn == "cuda" else "stock PyTorch ops"),
+                       "overlap": "side-stream graph branches: parameter prep || packing, dW || dH + next layer, head dW || dX"
+                       if EF.Overlap.enabled else "single stream",
+                       "e2e_pipeline": f"H2D {depth} batches ahead, packing 1 ahead, step: 3 streams",
                        "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
                                        2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
                        "pdl": bool(_lib.lib().eagcn_get_pdl()), "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
@@ -684,7 +721,13 @@ def main():
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
-    ap.add_argument("--dense-mm", default="torch", choices=["cuda", "torch"], help="GEMM of the head's dense layers")
+    ap.add_argument("--dense-mm", default="tile", choices=["tile", "cuda", "torch"], help="GEMM of the head's dense layers")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
+                    help="1: independent branches of a step on a side stream (parallel graph branches); 0: one stream")
+    ap.add_argument("--bn-act", default="vec", choices=["vec", "c32"], help="head BatchNorm kernels: float4 or 32-channel")
+    ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2],
+                    help="e2e input pipeline: H2D copies issued this many batches ahead (2: copy of batch i+2, packing of "
+                         "batch i+1 and the step of batch i overlap)")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -53,7 +53,7 @@ class WorkStruct(ctypes.Structure):
                 ("p_drop", c_double), ("eps", c_double), ("momentum", c_double),
                 ("dX", c_void_p), ("dY", c_void_p), ("Q", c_void_p), ("dH", c_void_p), ("dwall", c_void_p),
                 ("dvec", c_void_p), ("datt", c_void_p), ("bsums", c_void_p), ("gemm_ws", c_void_p),
-                ("gemm_ws_bytes", c_int64), ("wallT", c_void_p), ("wsplit", c_void_p)]
+                ("gemm_ws_bytes", c_int64), ("wallT", c_void_p), ("wsplit", c_void_p), ("phase", c_int64)]
 
 
 _P3 = c_void_p * 3
@@ -72,6 +72,7 @@ class HeadStruct(ctypes.Structure):
 
 _PROTOS = {
     "eagcn_version": (c_int, []),
+    "eagcn_sizeof": (c_int64, [c_int]),
     "eagcn_stat_tiles": (c_int64, [c_int64]),
     "eagcn_partial_floats": (c_int64, [c_int64, c_int64, c_int64]),
     "eagcn_gemm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
@@ -84,6 +85,7 @@ _PROTOS = {
     "eagcn_rows_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "eagcn_readout_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "eagcn_readout_sum_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "eagcn_layer_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_layer_forward_a": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_layer_forward_b": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_layer_backward_a": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -100,12 +102,19 @@ _PROTOS = {
                                      c_double, c_double, c_void_p]),
     "eagcn_bn_act_backward": (c_int, [c_void_p] * 9 + [c_int64, c_int64, c_int, c_int, c_double, c_void_p, c_int64,
                                       c_void_p]),
+    "eagcn_set_bn_act_mode": (c_int, [c_int]),
+    "eagcn_get_bn_act_mode": (c_int, []),
     "eagcn_mm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "eagcn_mm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                          c_int64, c_void_p]),
+    "eagcn_mm_tile_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "eagcn_mm_tile_tickets": (c_int64, [c_int64, c_int64]),
+    "eagcn_mm_tile": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                              c_int64, c_void_p, c_void_p]),
     "eagcn_gemm_trace": (c_int, [c_void_p, c_int64]),
     "eagcn_gemm_trace_stride": (c_int64, []),
     "eagcn_rng_fork": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "eagcn_rng_fork_n": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),
@@ -144,6 +153,10 @@ def lib():
         v = L.eagcn_version()
         if v != ABI_VERSION:
             raise EagcnError(f"libeagcn_sm100.so ABI {v} != python binding {ABI_VERSION}: rebuild")
+        for which, cls in enumerate((PlanStruct, LayerStruct, WorkStruct, HeadStruct)):
+            if L.eagcn_sizeof(which) != ctypes.sizeof(cls):
+                raise EagcnError(f"{cls.__name__}: ctypes mirror is {ctypes.sizeof(cls)} bytes, the library's struct "
+                                 f"{L.eagcn_sizeof(which)}: rebuild")
         _lib = L
     return _lib
 

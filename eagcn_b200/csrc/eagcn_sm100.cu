@@ -8,8 +8,18 @@
 #include "attention.cu"
 #include "head.cu"
 #include "bn_act.cu"
+#include "mm_tile.cu"
 
 extern "C" int eagcn_version(void) { return EAGCN_ABI_VERSION; }
+extern "C" int64_t eagcn_sizeof(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(eagcn_plan_t);
+    case 1: return (int64_t)sizeof(eagcn_layer_t);
+    case 2: return (int64_t)sizeof(eagcn_work_t);
+    case 3: return (int64_t)sizeof(eagcn_head_t);
+    default: return -1;
+  }
+}
 extern "C" int eagcn_set_gemm_mode(int mode) {
   if (mode < 0 || mode > 2) return EAGCN_E_ARG;
   eagcn::gemm_mode() = mode;

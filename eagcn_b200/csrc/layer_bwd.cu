@@ -668,6 +668,8 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   int fo_max = 0;
   for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
+  const int phase = w->phase ? (int)w->phase : 7;     // bit0: aggregation backward, bit1: dH, bit2: dW + parameter sums
+  if (phase & 1) {
   if (tile_bwd_ok(plan, layer, w)) {
     // fused: w->dY holds g = dX*relu'*dropout (written by backward_a); dY itself only ever exists in shared memory
     BnFold bn{(const float*)w->dY, (const float*)w->mean, (const float*)w->invstd, (const double*)w->bsums, M,
@@ -714,8 +716,9 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
   }
   }
   EAGCN_LAUNCH_CHECK();
+  }
   int rc = 0;
-  if (!w->dH) {
+  if (!(phase & 2) || !w->dH) {
     // the layer input needs no gradient (first layer fed by data): skip dH = Q W^T altogether
   } else if (gemm_mode() != 1 && w->wsplit && tc::tc_supported((const float*)w->Q, C, (const float*)w->wsplit, C, C))
     rc = tc::gemm_tc_nt((const float*)w->Q, C, (const float*)w->wsplit, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
@@ -724,6 +727,7 @@ extern "C" int eagcn_layer_backward_b(const eagcn_plan_t* plan, const eagcn_laye
     rc = gemm_nt((const float*)w->Q, C, (const float*)w->wall, C, (float*)w->dH, L.fin, p.t_cap, L.fin, C,
                  p.counts + EAGCN_CNT_T, st);
   if (rc) return rc;
+  if (!(phase & 4)) return 0;
   int ns = 0;
   if (gemm_mode() == 0 && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->Q, C, p.t_cap))
     rc = tc::gemm_tc_tn((const float*)w->H, L.fin, (const float*)w->Q, C, (float*)w->gemm_ws,

@@ -571,8 +571,34 @@ bool layer_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l) {
   return s == l->fo_tot;
 }
 
+// wall / wallT / wsplit / ball / sig of one layer from the module parameters (they change every optimiser step)
+static int launch_prep_params(const LayerDev& L, const eagcn_work_t* w, cudaStream_t st) {
+  const int C = L.fo_tot;
+  long long n = (long long)L.fin * C;
+  if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
+  if (n < C) n = C;
+  EAGCN_PROF("prep_params_kernel", st);
+  EAGCN_LAUNCH(prep_params_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(L, (float*)w->wall, (float*)w->wallT, (float*)w->wsplit, (float*)w->ball, (float*)w->sig);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace eagcn
 using namespace eagcn;
+
+extern "C" int eagcn_layer_prepare(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream) {
+  // plan: only V and chan[] are read (the sigmoid tables have C_v entries); no plan array is touched
+  if (!plan || plan->V <= 0 || plan->V > EAGCN_MAX_VIEWS || !w || !layer || layer->V != plan->V || layer->fin <= 0 ||
+      layer->fo_tot <= 0)
+    return EAGCN_E_ARG;
+  if (!w->wall || !w->ball || !w->sig) return EAGCN_E_ARG;
+  for (int v = 0; v < layer->V; ++v)
+    if (!layer->att_w[v] || !layer->self_r[v] || !layer->W[v] || !layer->bias[v] || !layer->gamma[v] || !layer->beta[v] ||
+        plan->chan[v] > 254)
+      return EAGCN_E_ARG;
+  LayerDev L = to_dev(layer, plan);
+  return launch_prep_params(L, w, (cudaStream_t)stream);
+}
 
 extern "C" int64_t eagcn_stat_tiles(int64_t t_cap) { return (t_cap + kStatRows - 1) / kStatRows; }
 
@@ -585,13 +611,11 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   PlanDev p = to_dev(plan);
   LayerDev L = to_dev(layer, plan);
   const int C = L.fo_tot;
-  long long n = (long long)L.fin * C;
-  if (n < (long long)L.V * EAGCN_SIG_STRIDE) n = (long long)L.V * EAGCN_SIG_STRIDE;
-  if (n < C) n = C;
-  EAGCN_PROF("prep_params_kernel", st);
-  EAGCN_LAUNCH(prep_params_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(L, (float*)w->wall, (float*)w->wallT, (float*)w->wsplit, (float*)w->ball, (float*)w->sig);
-  EAGCN_LAUNCH_CHECK();
   int rc;
+  if (!(w->training & 4)) {              // bit2: eagcn_layer_prepare already ran for these buffers (on any stream)
+    rc = launch_prep_params(L, w, st);
+    if (rc) return rc;
+  }
   if (gemm_mode() != 1 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
     rc = tc::gemm_tc_nt((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, (float*)w->Z, C, p.t_cap, C, L.fin,
                         p.counts + EAGCN_CNT_T, st, "gemm_tc_nn", (const float*)w->wallT + (size_t)L.fin * C);

@@ -91,12 +91,12 @@ __global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const f
 // snapshot the philox (seed, offset) for one dropout call site and advance the live state: one launch instead of a
 // clone plus an add (both graph-replay safe, but two kernels per layer call)
 __global__ void rng_fork_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ snap,
-                                unsigned long long inc) {
+                                unsigned long long inc, int n) {
   pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const unsigned long long seed = state[0], off = state[1];
-    snap[0] = seed; snap[1] = off;
-    state[1] = off + inc;
+    for (int i = 0; i < n; ++i) { snap[2 * i] = seed; snap[2 * i + 1] = off + (unsigned long long)i * inc; }
+    state[1] = off + (unsigned long long)n * inc;
   }
 }
 
@@ -107,7 +107,16 @@ extern "C" int eagcn_rng_fork(void* state, void* snapshot, int64_t increment, vo
   if (!state || !snapshot || increment <= 0) return EAGCN_E_ARG;
   EAGCN_PROF("rng_fork_kernel", stream);
   EAGCN_LAUNCH(rng_fork_kernel, 1, 32, 0, stream)((unsigned long long*)state, (unsigned long long*)snapshot,
-                                                  (unsigned long long)increment);
+                                                  (unsigned long long)increment, 1);
+  EAGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eagcn_rng_fork_n(void* state, void* snapshots, int64_t n, int64_t increment, void* stream) {
+  if (!state || !snapshots || increment <= 0 || n <= 0 || n > 4096) return EAGCN_E_ARG;
+  EAGCN_PROF("rng_fork_kernel", stream);
+  EAGCN_LAUNCH(rng_fork_kernel, 1, 32, 0, stream)((unsigned long long*)state, (unsigned long long*)snapshots,
+                                                  (unsigned long long)increment, (int)n);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -8,6 +8,7 @@ one CUDA graph.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -17,6 +18,86 @@ from ._lib import HeadStruct, LayerStruct, WorkStruct, check, lib, ptr
 from .plan import GraphPlan, _stream
 
 _F32 = torch.float32
+
+
+class Overlap:
+    """Independent branches of a step on a side stream (captured into a CUDA graph as parallel branches).
+
+    A training step is a chain of ~40 small kernels; three groups of them do not depend on their stream neighbours:
+      * the per-step parameter preparation (W_all concat / hi-lo split / sigmoid tables) and the dropout-generator
+        fork depend only on the parameters -- they run beside the graph-plan packing (``prefetch``);
+      * dW_all = H^T Q (+ the attention-gradient sums) and dH = Q W_all^T both depend only on Q -- dW runs beside dH and
+        beside the next layer's backward;
+      * dW = x^T dy and dx = dy W^T of a Dense layer.
+    Fork = the side stream waits for the current stream; join = the current stream waits for the side stream.  The
+    join of the backward branches is deferred to the end of the backward pass (autograd engine callback) when the
+    parameters receive fresh gradients (``p.grad is None``: autograd adopts the returned tensor without touching it);
+    otherwise it happens before the layer's backward returns.  Every tensor a side-stream kernel touches is kept
+    alive until the join, so the caching allocator cannot hand its memory to a main-stream kernel early.
+    ``Overlap.enabled = False`` (or EAGCN_OVERLAP=0) puts everything back on one stream."""
+    enabled = os.environ.get("EAGCN_OVERLAP", "1") != "0"
+    defer_param_grads = True
+    _streams = {}
+    _pending = {}          # device index -> list of keep-alive tuples of the un-joined backward branches
+    _cb_armed = {}
+
+    @classmethod
+    def side(cls, dev):
+        key = torch.device(dev).index or 0
+        if key not in cls._streams:
+            cls._streams[key] = torch.cuda.Stream(device=dev)
+        return cls._streams[key]
+
+    @classmethod
+    def fork(cls, dev):
+        """The side stream, ordered after everything enqueued on the current stream so far."""
+        s = cls.side(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        return s
+
+    @classmethod
+    def join(cls, dev):
+        key = torch.device(dev).index or 0
+        torch.cuda.current_stream(dev).wait_stream(cls.side(dev))
+        cls._pending.pop(key, None)
+        cls._cb_armed[key] = False
+
+    _fwd_open = {}
+
+    @classmethod
+    def fork_fwd(cls, dev):
+        """Side stream for the forward prefetch (parameter preparation + dropout-generator fork)."""
+        cls.join_pending(dev)
+        cls._fwd_open[torch.device(dev).index or 0] = True
+        return cls.fork(dev)
+
+    @classmethod
+    def join_fwd(cls, dev):
+        """First consumer of prefetched data: the current stream waits for the side stream (once per prefetch)."""
+        key = torch.device(dev).index or 0
+        if cls._fwd_open.get(key):
+            cls._fwd_open[key] = False
+            torch.cuda.current_stream(dev).wait_stream(cls.side(dev))
+
+    @classmethod
+    def join_pending(cls, dev):
+        """Join now if a backward branch is still open (start of a new step after an aborted backward)."""
+        if cls._pending.get(torch.device(dev).index or 0):
+            cls.join(dev)
+
+    @classmethod
+    def defer_join(cls, dev, keep):
+        """Join at the end of the running backward pass; ``keep`` stays referenced until then."""
+        key = torch.device(dev).index or 0
+        cls._pending.setdefault(key, []).append(keep)
+        if not cls._cb_armed.get(key):
+            cls._cb_armed[key] = True
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.join(dev))
+
+    @staticmethod
+    def fresh(params):
+        """True when autograd will adopt the returned gradient tensors as-is (no accumulate / copy kernel)."""
+        return Overlap.defer_param_grads and all(p is None or (p.grad is None and not p._backward_hooks) for p in params)
 
 
 @dataclass
@@ -35,6 +116,8 @@ class LayerConfig:
     # also return z_pad [fo_tot]: the post-BatchNorm pre-activation every bond-less / padded row holds (Y = b there).
     # 'Weighted_sum' does not mask those rows (layers.py:314-316), so their value and its gradient matter.
     want_pad: bool = False
+    # LayerPrep from prepare_layer(): wall / wallT / wsplit / ball / sig already filled (possibly on the side stream)
+    prep: object = None
 
 
 class RngState:
@@ -44,6 +127,7 @@ class RngState:
     def __init__(self, device, seed=0):
         self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
         self._inc = torch.tensor([0, 1 << 20], dtype=torch.int64, device=device)
+        self._queue = []
 
     @classmethod
     def get(cls, device):
@@ -60,9 +144,21 @@ class RngState:
 
     def fork(self):
         """Snapshot for one dropout call site + advance of the live state, in one (graph-capturable) launch."""
+        if self._queue:
+            Overlap.join_fwd(self.state.device)
+            return self._queue.pop(0)
         snap = torch.empty_like(self.state)
         check(lib().eagcn_rng_fork(ptr(self.state), ptr(snap), 1 << 20, _stream()), "eagcn_rng_fork")
         return snap
+
+    def prefork(self, n, stream=None):
+        """The next ``n`` fork() calls in ONE launch (on ``stream``): they then only hand out the snapshots.  Same
+        (seed, offset) sequence as n separate forks; snapshots left over from an earlier prefork are dropped."""
+        snaps = torch.empty(n, 2, dtype=torch.int64, device=self.state.device)
+        check(lib().eagcn_rng_fork_n(ptr(self.state), ptr(snaps), n, 1 << 20,
+                                     _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)),
+              "eagcn_rng_fork_n")
+        self._queue = [snaps[i] for i in range(n)]
 
 
 def manual_seed(seed, device=None):
@@ -115,6 +211,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
             raise ValueError(f"packed input must be float32 [{plan.t_cap}, {cfg.fin}] on {dev}, "
                              f"got {tuple(H.shape)} {H.dtype} on {H.device}")
         H = H.contiguous()
+        ctx.param_refs = params
         params = tuple(p.detach() for p in params)
         _check_params(plan, cfg, params, buffers)
         ls = _layer_struct(plan, cfg, params, buffers)
@@ -126,11 +223,14 @@ class _GraphConvLayerFn(torch.autograd.Function):
         Y = torch.empty(T, C, **f32)
         X = torch.empty(T, C, **f32)
         invR = torch.empty(plan.V, T, **f32)
-        wall = torch.empty(cfg.fin, C, **f32)
-        wallT = torch.empty(2, C, cfg.fin, **f32)
-        wsplit = torch.empty(2, cfg.fin, C, **f32)
-        ball = torch.empty(4, C, **f32)
-        sig = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
+        prep = cfg.prep
+        if prep is not None and not prep.matches(cfg, params, plan):
+            prep = None
+        if prep is not None:
+            prep.join()                                 # the side stream filled these buffers
+            wall, wallT, wsplit, ball, sig = prep.wall, prep.wallT, prep.wsplit, prep.ball, prep.sig
+        else:
+            wall, wallT, wsplit, ball, sig = _prep_buffers(cfg.fin, C, plan.V, dev)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
         sums = torch.empty(2, C, dtype=torch.float64, device=dev)
         mean = torch.empty(C, **f32)
@@ -144,7 +244,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.wallT, w.wsplit = ptr(wallT), ptr(wsplit)
         w.mean, w.invstd = ptr(mean), ptr(invstd)
         w.rng = ptr(rng_snapshot)
-        w.training = (1 if cfg.training else 0) | (2 if (cfg.training and cfg.stat_allreduce is not None) else 0)
+        w.training = ((1 if cfg.training else 0) | (2 if (cfg.training and cfg.stat_allreduce is not None) else 0) |
+                      (4 if prep is not None else 0))
         w.rng_stream = int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
@@ -206,7 +307,23 @@ class _GraphConvLayerFn(torch.autograd.Function):
             cfg.stat_allreduce(bsums)
         if pad_sums is not None and cfg.training:
             bsums.add_(pad_sums)
-        check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+        if Overlap.enabled and need_dH and pad_sums is None:
+            # dW_all = H^T Q (+ parameter sums) on the side stream, beside dH = Q W_all^T (and, when the parameters
+            # take fresh gradients, beside everything that follows in this backward pass)
+            w.phase = 1
+            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+            side = Overlap.fork(dev)
+            w.phase = 4
+            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), ctypes.c_void_p(side.cuda_stream)),
+                  "eagcn_layer_backward_b")
+            w.phase = 2
+            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+            if Overlap.fresh(ctx.param_refs):
+                Overlap.defer_join(dev, (H, Q, gemm_ws, dwall, partial, datt, Z, Y, dY))
+            else:
+                Overlap.join(dev)
+        else:
+            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
         if pad_sums is not None:                      # dvec rows: d bias | d gamma | d beta
             dvec[1].add_(pad_sums[1].float())
             dvec[2].add_(pad_sums[0].float())
@@ -222,6 +339,53 @@ class _GraphConvLayerFn(torch.autograd.Function):
                       dvec[0, off:off + fo], dvec[1, off:off + fo], dvec[2, off:off + fo]]
             off += fo
         return (None, None, None, dH, *grads)
+
+
+def _prep_buffers(fin, C, V, dev):
+    f32 = dict(dtype=_F32, device=dev)
+    return (torch.empty(fin, C, **f32), torch.empty(2, C, fin, **f32), torch.empty(2, fin, C, **f32),
+            torch.empty(4, C, **f32), torch.empty(V, _lib.SIG_STRIDE, **f32))
+
+
+class LayerPrep:
+    """Per-step parameter-derived buffers of one layer (W_all, its transposed / hi-lo split copies, bias / gamma / beta
+    rows, sigmoid tables), filled by eagcn_layer_prepare -- on the side stream when ``stream`` is given, so that it runs
+    beside the packing of the batch.  Valid until the parameters change (one optimiser step)."""
+
+    def __init__(self, fin, fo, channels, params, dev, stream=None):
+        self.fin, self.fo, self.channels = int(fin), tuple(int(f) for f in fo), tuple(int(c) for c in channels)
+        self.keys = tuple((p.data_ptr(), p._version) for p in params)
+        C, V = sum(self.fo), len(self.fo)
+        self.wall, self.wallT, self.wsplit, self.ball, self.sig = _prep_buffers(self.fin, C, V, dev)
+        self.dev, self.side = dev, stream is not None
+        ps = _lib.PlanStruct()
+        ps.V = V
+        for v, c in enumerate(self.channels):
+            ps.chan[v] = c
+        ls = LayerStruct()
+        ls.fin, ls.V, ls.fo_tot = self.fin, V, C
+        off = 0
+        for v in range(V):
+            ls.fo[v], ls.off[v] = self.fo[v], off
+            off += self.fo[v]
+            a, r, W, b, g, be = params[6 * v: 6 * v + 6]
+            ls.att_w[v], ls.self_r[v], ls.W[v], ls.bias[v] = a.data_ptr(), r.data_ptr(), W.data_ptr(), b.data_ptr()
+            ls.gamma[v], ls.beta[v] = g.data_ptr(), be.data_ptr()
+        for v in range(V, _lib.MAX_VIEWS + 1):
+            ls.off[v] = off
+        w = WorkStruct()
+        w.wall, w.wallT, w.wsplit, w.ball, w.sig = ptr(self.wall), ptr(self.wallT), ptr(self.wsplit), ptr(self.ball), ptr(self.sig)
+        st = _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        check(lib().eagcn_layer_prepare(ctypes.byref(ps), ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_prepare")
+
+    def matches(self, cfg, params, plan):
+        return (self.fin == cfg.fin and self.fo == tuple(cfg.fo) and self.channels == tuple(plan.channels[:plan.V]) and
+                self.keys == tuple((p.data_ptr(), p._version) for p in params) and self.dev == plan.device)
+
+    def join(self):
+        if self.side:
+            Overlap.join_fwd(self.dev)
+            self.side = False
 
 
 def graph_conv_layer(plan: GraphPlan, cfg: LayerConfig, H, params, buffers):
@@ -484,28 +648,83 @@ def _mm(A, transA, B, transB):
     return C
 
 
+_tickets = {}
+
+
+def _ticket_buf(dev, lane, n):
+    """Persistent zero-initialised int32 ticket array of the tile GEMM (the kernel leaves it zero).  One array per
+    (device, lane): lane 0 serves the calls on the current stream, lane 1 those on the side stream -- calls within a
+    lane are stream-ordered, calls of different lanes may run concurrently."""
+    key = (torch.device(dev).index or 0, lane)
+    t = _tickets.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros(max(int(n), 1 << 14), dtype=torch.int32, device=dev)
+        _tickets[key] = t
+    return t
+
+
+def _mm_tile(A, transA, B, transB, stream=None):
+    """op(A) @ op(B) on the small-matrix tile kernel (split-K combined inside the launch; bit-reproducible)."""
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    if (B.shape[1] if transB else B.shape[0]) != K:
+        raise ValueError("mm: inner dimensions differ")
+    L = lib()
+    C = torch.empty(M, N, dtype=_F32, device=A.device)
+    nbytes = int(L.eagcn_mm_tile_workspace_bytes(M, N, K))
+    ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
+    tk = _ticket_buf(A.device, 0 if stream is None else 1, int(L.eagcn_mm_tile_tickets(M, N))) if nbytes else None
+    st = _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+    check(L.eagcn_mm_tile(ptr(A), A.shape[1], int(transA), ptr(B), B.shape[1], int(transB), ptr(C), M, N, K,
+                          ptr(ws), nbytes, ptr(tk), st), "eagcn_mm_tile")
+    return C, ws
+
+
 class _DenseMmFn(torch.autograd.Function):
-    """y = x @ W (layers.py:382-388) with dX = dY @ W^T and dW = x^T @ dY on the same split-K FFMA kernel."""
+    """y = x @ W (layers.py:382-388) with dX = dY @ W^T and dW = x^T @ dY.  engine 'tile': mm_tile.cu, the weight
+    gradient on the side stream beside dX (Overlap); engine 'cuda': the split-K FFMA kernel of gemm_simt.cu."""
 
     @staticmethod
-    def forward(ctx, x, W):
+    def forward(ctx, x, W, engine):
         if not x.is_cuda:
             raise EagcnError("eagcn_b200.dense_mm is CUDA-only (sm_100a, no CPU fallback)")
+        ctx.w_ref = W
         x, W = x.contiguous(), W.detach().contiguous()
         ctx.save_for_backward(x, W)
+        ctx.engine = engine
+        if engine == "tile":
+            return _mm_tile(x, False, W, False)[0]
         return _mm(x, False, W, False)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = _mm(dy, False, W, True) if ctx.needs_input_grad[0] else None
-        dW = _mm(x, True, dy, False) if ctx.needs_input_grad[1] else None
-        return dx, dW
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.engine != "tile":
+            dx = _mm(dy, False, W, True) if need_dx else None
+            dW = _mm(x, True, dy, False) if need_dw else None
+            return dx, dW, None
+        dx = dW = None
+        if need_dw and need_dx and Overlap.enabled:
+            side = Overlap.fork(dy.device)
+            dW, ws = _mm_tile(x, True, dy, False, stream=side)
+            dx = _mm_tile(dy, False, W, True)[0]
+            if Overlap.fresh((ctx.w_ref,)):
+                Overlap.defer_join(dy.device, (x, dy, dW, ws))
+            else:
+                Overlap.join(dy.device)
+            return dx, dW, None
+        if need_dx:
+            dx = _mm_tile(dy, False, W, True)[0]
+        if need_dw:
+            dW = _mm_tile(x, True, dy, False)[0]
+        return dx, dW, None
 
 
-def dense_mm(x, W):
-    return _DenseMmFn.apply(x, W)
+def dense_mm(x, W, engine="tile"):
+    return _DenseMmFn.apply(x, W, engine)
 
 
 def bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):

@@ -255,7 +255,23 @@ class GraphConv_Layer(nn.Module):
             return x + inactive.unsqueeze(2) * pad
         return x + inactive.unsqueeze(2) * (pad_v * w.view(V, 1)).sum(0).view(1, 1, fo)
 
-    def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None):
+    def _flat_params(self):
+        params, buffers = [], []
+        for b in self.blocks:
+            params += b._view_params()
+            buffers += b._bn_buffers()
+        return params, buffers
+
+    def prepare(self, stream=None):
+        """Per-step parameter preparation of this layer ahead of its forward call (EF.LayerPrep): pass the result as
+        ``forward(..., prep=...)``.  With ``stream`` (a side stream) it overlaps whatever runs on the current stream --
+        the packing of the batch, typically."""
+        params, _ = self._flat_params()
+        chans = tuple(b.bond_feature_num for b in self.blocks)
+        return EF.LayerPrep(self.node_feature_in, tuple(b.node_feature_out for b in self.blocks), chans,
+                            [p.detach() for p in params], params[0].device, stream)
+
+    def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None, prep=None):
         if self.structure not in ("Concate", "Weighted_sum"):
             raise EagcnError(f"structure {self.structure!r} is not supported (layers.py:279-283)")
         wsum = self.structure == "Weighted_sum"
@@ -275,13 +291,10 @@ class GraphConv_Layer(nn.Module):
         p_drop = float(self.block1.dropout)
         cfg = EF.LayerConfig(fin=self.node_feature_in, fo=tuple(b.node_feature_out for b in self.blocks),
                              training=self.training, p_drop=p_drop, rng_stream=self.rng_stream,
-                             stat_allreduce=self.stat_allreduce, want_pad=wsum)
+                             stat_allreduce=self.stat_allreduce, want_pad=wsum, prep=prep)
         if wsum and self.stat_allreduce is not None:
             raise EagcnError("structure='Weighted_sum' with global-batch BatchNorm is not implemented")
-        params, buffers = [], []
-        for b in self.blocks:
-            params += b._view_params()
-            buffers += b._bn_buffers()
+        params, buffers = self._flat_params()
         if wsum:
             x = self._weighted_sum(plan, cfg, H, params, buffers, p_drop)
         else:

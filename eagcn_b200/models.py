@@ -47,13 +47,15 @@ class Dense(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-stdv, stdv)
 
-    # 'torch': library GEMM (measured 3x faster than the FFMA kernel on these skinny shapes: 63 vs 197 us per step);
-    # 'cuda': eagcn_mm (strict fp32, split-K with fixed-order reduction -- bit-reproducible)
-    mm_engine = "torch"
+    # 'tile' : eagcn_mm_tile (mm_tile.cu: 32x32 tiles, whole K range staged at once, split-K combined inside the launch,
+    #          weight gradient on the side stream) -- strict fp32, bit-reproducible;
+    # 'torch': library GEMM (un-split 32x32x16 SIMT kernel on these skinny shapes: 63 us per step over 9 products);
+    # 'cuda' : eagcn_mm (128x64 tiles of the projection FFMA kernel: 197 us per step)
+    mm_engine = "tile"
 
     def forward(self, input):
-        if self.mm_engine == "cuda" and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:
-            out = EF.dense_mm(input, self.weight)                                   # layers.py:382-388
+        if self.mm_engine in ("tile", "cuda") and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:
+            out = EF.dense_mm(input, self.weight, self.mm_engine)                   # layers.py:382-388
         else:
             out = torch.mm(input, self.weight)
         return out + self.bias if self.bias is not None else out
@@ -130,11 +132,31 @@ class EAGCNStack(nn.Module):
     def conv_layers(self):
         return [getattr(self, f"layer{l + 1}") for l in range(self.n_layers)]
 
+    def prefetch_params(self):
+        """Optional hint, called BEFORE the batch's GraphPlan is built: launches everything of the coming forward pass
+        that depends only on the parameters (per-layer W_all concat / split / sigmoid tables, the dropout-generator
+        fork of every dropout site) on a side stream, so that it runs beside the packing kernels.  ``forward`` picks
+        the result up (and falls back to preparing in line when the parameters changed in between).  ``forward``
+        calls it itself when it is handed dense tensors and has to build the plan."""
+        if not EF.Overlap.enabled or self.structure != "Concate":
+            return
+        dev = self.den1.weight.device
+        if dev.type != "cuda":
+            return
+        side = EF.Overlap.fork_fwd(dev)
+        if self.training and float(self.dropout) > 0.0:
+            EF.RngState.get(dev).prefork(self.n_layers + 1, side)       # one site per layer + the head's dropout
+        self._prefetched = [layer.prepare(side) for layer in self.conv_layers]
+
     def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None, size=None):
         if isinstance(adjs, GraphPlan):
             plan = adjs
         else:
+            if getattr(self, "_prefetched", None) is None and torch.is_tensor(adjs) and adjs.is_cuda:
+                self.prefetch_params()
             plan = GraphConv_Layer._plan_for(adjs, (TypeAtt, OrderAtt, AromAtt, ConjAtt, RingAtt))
+        preps = getattr(self, "_prefetched", None) or [None] * self.n_layers
+        self._prefetched = None
         if self.structure == "Weighted_sum":
             # the un-masked padded rows of this structure (layers.py:314-316) travel between layers and into the
             # read-out sum exactly as in the reference: dense tensors end to end
@@ -147,8 +169,9 @@ class EAGCNStack(nn.Module):
             x = h.sum(1)                                                            # models.py:108 (padded rows included)
         else:
             h = afms if isinstance(afms, PackedRows) else PackedRows(EF.gather_rows(plan, afms), plan)
-            for layer in self.conv_layers:                                          # models.py:97-100
-                h, A = layer(plan, h)
+            for layer, prep in zip(self.conv_layers, preps):                        # models.py:97-100
+                h, A = layer(plan, h, prep=prep)
+            EF.Overlap.join_fwd(plan.device)                                        # no-op once a layer consumed the prefetch
             atom_representations = LazyAtomRep(h)                                   # models.py:102
             if self.molfp_mode == "pool":                                           # models.py:104-106
                 _, xp = self.pool1(A, h.dense())

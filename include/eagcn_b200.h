@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 13
+#define EAGCN_ABI_VERSION 14
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -106,7 +106,8 @@ typedef struct eagcn_work {
   void* mean;     /* f32 [fo_tot]                                                         */
   void* invstd;   /* f32 [fo_tot]                                                         */
   void* rng;      /* u64 [2]               philox seed, offset (device; graph-replay safe) */
-  int64_t training;     /* bit0: training mode (batch statistics, dropout); bit1: the host all-reduces `sums`
+  int64_t training;     /* bit2: eagcn_layer_prepare was already called for wall / wallT / wsplit / ball / sig;
+                         * bit0: training mode (batch statistics, dropout); bit1: the host all-reduces `sums`
                          * between forward_a and forward_b and `bsums` between backward_a and backward_b
                          * (global-batch BatchNorm); without bit1 the reductions are fused into fewer kernels */
   int64_t rng_stream;   /* distinguishes layers sharing one rng state                      */
@@ -129,9 +130,16 @@ typedef struct eagcn_work {
   int64_t gemm_ws_bytes;
   void* wallT;    /* f32 [2, fo_tot, fin]  W_all transposed, split hi / lo (K-major B operand of Z = H W)   */
   void* wsplit;   /* f32 [2, fin, fo_tot]  W_all split hi / lo          (K-major B operand of dH = Q W^T)   */
+  int64_t phase;  /* eagcn_layer_backward_b only.  0: everything.  Otherwise a bit set of the parts to launch, so that
+                   * the host can put independent parts on different streams: 1 = aggregation backward (Q, attention
+                   * partials; needs backward_a), 2 = dH = Q W^T (needs 1), 4 = dW = H^T Q + d att / d self_r sums
+                   * (needs 1; independent of 2)                                                          */
 } eagcn_work_t;
 
 int eagcn_version(void);
+/* sizeof of the ABI structs as compiled (0: eagcn_plan_t, 1: eagcn_layer_t, 2: eagcn_work_t, 3: eagcn_head_t): lets a
+ * foreign-function binding verify its mirror of the layouts at load time                                          */
+int64_t eagcn_sizeof(int which);
 /* number of CTAs/tiles the statistics partial buffer must hold for a given t_cap */
 int64_t eagcn_stat_tiles(int64_t t_cap);
 /* floats the `partial` buffer must hold (BatchNorm partials, then attention-gradient partials) */
@@ -163,6 +171,10 @@ int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout, void* dpac
 /* --- one GraphConv_Layer (layers.py:293-325, structure == 'Concate') ---------------------- */
 /* part A: weights concat + sigmoid tables, Z = H @ W_all (layers.py:40), attention score /
  * row-normalise / aggregate / +bias (layers.py:82-92,39,43) -> Y, BatchNorm batch sums -> sums */
+/* optional first step of part A, callable on another stream before the plan's arrays exist (only plan->V and
+ * plan->chan are read): fills work.wall / wallT / wsplit / ball / sig from the parameters.  eagcn_layer_forward_a skips
+ * it when bit2 of work.training is set.                                                                          */
+int eagcn_layer_prepare(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
 int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
 /* part B: BatchNorm finalize (+ running stats, layers.py:408-412), ReLU, dropout
  * (layers.py:93-94), concat (layers.py:313) -> X                                              */
@@ -182,6 +194,8 @@ int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t 
 /* snapshot[0..1] = state[0..1] (philox seed, offset: device u64 [2]); state[1] += increment.  One call per dropout
  * site and forward pass: forward and backward of that site both read the snapshot (F.dropout, layers.py:94).        */
 int eagcn_rng_fork(void* state, void* snapshot, int64_t increment, void* stream);
+/* n call sites in one launch: snapshots u64 [n][2], snapshot i = (seed, offset + i*increment); offset += n*increment */
+int eagcn_rng_fork_n(void* state, void* snapshots, int64_t n, int64_t increment, void* stream);
 /* same generator over a flat index range (the fused head draws element m*D1+k of stream rng_stream):
  * keep_out u8 [total]                                                                          */
 int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, double p_drop, int64_t total, void* keep_out, void* stream);
@@ -227,6 +241,11 @@ int eagcn_bn_act_backward(const void* x, const void* dy, const void* gamma, cons
                           const void* invstd, void* dx, void* dgamma, void* dbeta, int64_t B, int64_t C, int training,
                           int relu, double p_drop, const void* rng, int64_t rng_stream, void* stream);
 
+/* 0 (default): float4 kernels (4 or 8 channels per CTA, one Philox call per 4 elements) when C % 4 == 0, the arrays are
+ * 16-byte aligned and B <= 1024; 1: always the 32-channel kernels.  Process-wide.                                 */
+int eagcn_set_bn_act_mode(int mode);
+int eagcn_get_bn_act_mode(void);
+
 /* --- dense layers of the head ------------------------------------------------------------------ */
 /* C[M,N] = op(A) . op(B) in strict fp32 (FFMA), row-major; transX != 0: the operand is stored transposed (A as [K,M],
  * B as [N,K]); lda / ldb = row strides in elements; C is dense (ldc = N).  Split-K with a fixed-order reduction
@@ -235,6 +254,16 @@ int eagcn_bn_act_backward(const void* x, const void* dy, const void* gamma, cons
 int64_t eagcn_mm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eagcn_mm(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C, int64_t M, int64_t N,
              int64_t K, void* ws, int64_t ws_bytes, void* stream);
+
+/* Same product on the small-matrix tile kernel (mm_tile.cu): 32x32 tiles, split-K combined INSIDE the launch (the last
+ * CTA to reach a tile sums the partials in z order: bit-reproducible, no second kernel).  `tickets`: device int32
+ * [eagcn_mm_tile_tickets(M,N)], zero when first used; the kernel leaves it zero, so one array can serve every call that
+ * is ordered after the previous one (calls that may run concurrently need separate arrays).  ws:
+ * eagcn_mm_tile_workspace_bytes(M,N,K) bytes (0: neither ws nor tickets are needed).                                 */
+int64_t eagcn_mm_tile_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int64_t eagcn_mm_tile_tickets(int64_t M, int64_t N);
+int eagcn_mm_tile(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C, int64_t M,
+                  int64_t N, int64_t K, void* ws, int64_t ws_bytes, void* tickets, void* stream);
 
 /* --- projection GEMM engine ------------------------------------------------------------------ */
 /* 0 (default): tcgen05 3xTF32 tensor-core kernel where the operand layout allows it (16-byte aligned

@@ -105,3 +105,86 @@ def test_dense_mm_autograd():
     ((xr @ Wr) * R.double()).sum().backward()
     assert float((x.grad.double() - xr.grad).abs().max() / xr.grad.abs().max()) <= 2e-6
     assert float((W.grad.double() - Wr.grad).abs().max() / Wr.grad.abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB", [
+    (256, 256, 700, False, False),      # den1 forward (Tox21 head)
+    (256, 64, 256, False, False),       # den2 forward
+    (256, 12, 64, False, False),        # den3 forward
+    (256, 700, 256, False, True),       # dX of den1
+    (700, 256, 256, True, False),       # dW of den1
+    (64, 12, 256, True, False),         # dW of den3
+    (256, 1, 64, False, False),         # regression head: one output column (scalar edge path)
+    (1, 64, 256, True, False),
+    (37, 45, 131, False, False),        # nothing aligned
+    (37, 45, 131, True, True),
+    (33, 31, 7, False, True),           # K shorter than one vector group
+    (512, 1400, 256, False, True),      # wide read-out (4-layer model)
+])
+def test_mm_tile_vs_float64(M, N, K, tA, tB):
+    """eagcn_mm_tile (mm_tile.cu, the dense layers of the head: layers.py:382-388) against a float64 product; the
+    in-kernel split-K combine is bit-reproducible and leaves its ticket array zero."""
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    g = torch.Generator().manual_seed(M * 131 + N * 7 + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g).to(dev)
+    B = torch.randn((N, K) if tB else (K, N), generator=g).to(dev)
+    C, _ = EF._mm_tile(A, tA, B, tB)
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-6, err
+    for _ in range(3):
+        C2, _ = EF._mm_tile(A, tA, B, tB)
+        assert torch.equal(C, C2)
+    for t in EF._tickets.values():
+        assert int(t.abs().sum()) == 0
+
+
+def test_mm_tile_strided_operands():
+    """lda / ldb larger than the logical width (views into wider buffers)."""
+    from eagcn_b200 import functional as EF, _lib
+    from eagcn_b200._lib import check, lib, ptr
+    dev = _cuda()
+    g = torch.Generator().manual_seed(5)
+    Abig = torch.randn(100, 90, generator=g).to(dev)
+    Bbig = torch.randn(70, 50, generator=g).to(dev)
+    M, K, N = 100, 70, 44
+    C = torch.empty(M, N, device=dev)
+    L = lib()
+    nbytes = int(L.eagcn_mm_tile_workspace_bytes(M, N, K))
+    ws = torch.empty(max(nbytes // 4, 1), device=dev)
+    tk = torch.zeros(int(L.eagcn_mm_tile_tickets(M, N)), dtype=torch.int32, device=dev)
+    import ctypes
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(L.eagcn_mm_tile(ptr(Abig), 90, 0, ptr(Bbig), 50, 0, ptr(C), M, N, K, ptr(ws), nbytes, ptr(tk), st), "mm_tile")
+    ref = Abig[:, :K].double() @ Bbig[:, :N].double()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) <= 2e-6
+    # invalid arguments come back as status codes, never as a crash
+    assert L.eagcn_mm_tile(None, 90, 0, ptr(Bbig), 50, 0, ptr(C), M, N, K, ptr(ws), nbytes, ptr(tk), st) == _lib.lib().eagcn_mm_tile(None, 90, 0, ptr(Bbig), 50, 0, ptr(C), M, N, K, ptr(ws), nbytes, ptr(tk), st) < 0
+    assert L.eagcn_mm_tile(ptr(Abig), 10, 0, ptr(Bbig), 50, 0, ptr(C), M, N, K, ptr(ws), nbytes, ptr(tk), st) < 0
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_dense_mm_tile_autograd(overlap):
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    old = EF.Overlap.enabled
+    EF.Overlap.enabled = overlap
+    try:
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(256, 300, generator=g).to(dev).requires_grad_(True)
+        W = torch.randn(300, 64, generator=g).to(dev).requires_grad_(True)
+        R = torch.randn(256, 64, generator=g).to(dev)
+        (EF.dense_mm(x, W, "tile") * R).sum().backward()
+        torch.cuda.synchronize()
+        xr = x.detach().double().requires_grad_(True); Wr = W.detach().double().requires_grad_(True)
+        ((xr @ Wr) * R.double()).sum().backward()
+        assert float((x.grad.double() - xr.grad).abs().max() / xr.grad.abs().max()) <= 2e-6
+        assert float((W.grad.double() - Wr.grad).abs().max() / Wr.grad.abs().max()) <= 2e-6
+        # accumulation into an existing .grad (the join must then precede the accumulate kernel)
+        g0 = W.grad.clone()
+        (EF.dense_mm(x, W, "tile") * R).sum().backward()
+        torch.cuda.synchronize()
+        assert float((W.grad - 2 * g0).abs().max() / g0.abs().max()) <= 1e-6
+    finally:
+        EF.Overlap.enabled = old

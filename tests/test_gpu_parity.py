@@ -652,12 +652,25 @@ def test_agg_engines_agree(kind, B, fin, fo, training, p):
     (64, 96, False, True, 0.3),         # eval: running statistics, dropout off
     (300, 40, True, True, 0.3),         # B > 256: multi-pass path
     (5, 8, True, False, 0.0),
+    (512, 700, True, True, 0.3),        # Lipophilicity batch: 4 rows per thread, 8 channels per CTA
+    (1000, 64, True, True, 0.3),        # B <= 1024: one float4 group per CTA
+    (1100, 64, True, True, 0.3),        # beyond the register-resident range: 32-channel multi-pass kernels
 ])
-def test_bn_act_vs_torch(B, C, training, relu, p):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn_act_vs_torch(B, C, training, relu, p, mode):
     """eagcn_bn_act_forward/backward against stock torch fp32 ops (batch_norm -> relu -> dropout with the same keep
-    mask), values, running statistics and all gradients."""
-    from eagcn_b200 import functional as EF
+    mask), values, running statistics and all gradients.  mode 0: float4 kernels (where the layout allows), 1: the
+    32-channel kernels."""
+    from eagcn_b200 import functional as EF, _lib
     dev = _cuda()
+    _lib.lib().eagcn_set_bn_act_mode(mode)
+    try:
+        _bn_act_case(EF, dev, B, C, training, relu, p)
+    finally:
+        _lib.lib().eagcn_set_bn_act_mode(0)
+
+
+def _bn_act_case(EF, dev, B, C, training, relu, p):
     g = torch.Generator().manual_seed(B * 1000 + C)
     x = (torch.randn(B, C, generator=g) * 2.0 + 0.7).to(dev)
     bn = torch.nn.BatchNorm1d(C).to(dev)
@@ -738,3 +751,82 @@ def test_weighted_sum_model_vs_oracle(training):
         assert float((prm.grad.cpu() - ref_g).abs().max()) / denom <= 2e-4, k
         checked += 1
     assert checked >= 40
+
+
+# ------------------------------------------------------------------ side-stream branches change nothing
+def _model_step(dev, overlap, graph):
+    """One training step (fwd + bwd) of a 2-layer model; returns outputs and all gradients."""
+    from eagcn_b200 import functional as EF, models as EM
+    from eagcn_b200.data import make_batch
+    from eagcn_b200.plan import GraphPlan
+    EF.Overlap.enabled = overlap
+    torch.manual_seed(0)
+    model = EM.EAGCNStack(17, 24, [(16,) * 5, (24,) * 5], 32, 16, 3, dropout=0.3).to(dev)
+    model.train()
+    batch = make_batch(24, "freesolv", seed=3)
+    dense = [torch.from_numpy(a).to(dev) for a in batch.dense()]
+    size = torch.from_numpy(batch.sizes).to(dev)
+    T, E = int((batch.adj.sum(2) > 0).sum()), int(batch.adj.sum())
+    params = [p for p in model.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        model.prefetch_params()
+        plan = GraphPlan.build(dense[0], dense[2:], t_cap=T, e_cap=E)
+        out, _, grep = model(plan, dense[1], size=size)
+        (out.sum() + grep.sum()).backward()
+        return out
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            EF.manual_seed(7)
+            out = step()
+        if graph:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            EF.manual_seed(7)
+            with torch.cuda.graph(g):
+                out = step()
+            EF.manual_seed(7)
+            g.replay()
+        torch.cuda.synchronize()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    return out.detach().clone(), grads
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_overlap_branches_bit_identical(graph):
+    """Overlap (parameter prep || packing, dW || dH + next layer, head dW || dX; deferred joins) only re-orders
+    independent kernels: outputs and every gradient are bit-identical to the single-stream run, eagerly and as a
+    captured CUDA graph (the side-stream work becomes parallel graph branches)."""
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    old = EF.Overlap.enabled
+    try:
+        o0, g0 = _model_step(dev, False, False)
+        o1, g1 = _model_step(dev, True, graph)
+    finally:
+        EF.Overlap.enabled = old
+    assert torch.equal(o0, o1)
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+
+
+def test_rng_prefork_matches_forks():
+    from eagcn_b200 import functional as EF
+    dev = _cuda()
+    r = EF.RngState.get(dev)
+    EF.manual_seed(11)
+    a = [r.fork().clone() for _ in range(3)]
+    end_a = r.state.clone()
+    EF.manual_seed(11)
+    r.prefork(3)
+    b = [r.fork().clone() for _ in range(3)]
+    assert not r._queue
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert torch.equal(end_a, r.state)

@@ -97,7 +97,8 @@ class Overlap:
     @staticmethod
     def fresh(params):
         """True when autograd will adopt the returned gradient tensors as-is (no accumulate / copy kernel)."""
-        return Overlap.defer_param_grads and all(p is None or (p.grad is None and not p._backward_hooks) for p in params)
+        return Overlap.defer_param_grads and all(
+            p is None or not p.requires_grad or (p.is_leaf and p.grad is None and not p._backward_hooks) for p in params)
 
 
 @dataclass
@@ -138,6 +139,7 @@ class RngState:
 
     def seed(self, seed):
         self.state.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+        self._queue = []
 
     def advance(self):
         self.state.add_(self._inc)
@@ -712,7 +714,8 @@ class _DenseMmFn(torch.autograd.Function):
             dW, ws = _mm_tile(x, True, dy, False, stream=side)
             dx = _mm_tile(dy, False, W, True)[0]
             if Overlap.fresh((ctx.w_ref,)):
-                Overlap.defer_join(dy.device, (x, dy, dW, ws))
+                # dW itself is NOT kept: an extra reference would make autograd copy it instead of adopting it
+                Overlap.defer_join(dy.device, (x, dy, ws))
             else:
                 Overlap.join(dy.device)
             return dx, dW, None

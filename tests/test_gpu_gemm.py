@@ -120,6 +120,10 @@ def test_dense_mm_autograd():
     (37, 45, 131, True, True),
     (33, 31, 7, False, True),           # K shorter than one vector group
     (512, 1400, 256, False, True),      # wide read-out (4-layer model)
+    (256, 256, 1400, False, False),     # den1 forward of the 4-layer model: 11 split-K slabs
+    (40, 33, 1, False, False),          # K = 1: both strides of an operand are 1
+    (40, 33, 1, True, True),
+    (64, 64, 300, True, True),          # three slabs through the two-stage pipeline, both operands k-contiguous
 ])
 def test_mm_tile_vs_float64(M, N, K, tA, tB):
     """eagcn_mm_tile (mm_tile.cu, the dense layers of the head: layers.py:382-388) against a float64 product; the

@@ -115,12 +115,18 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(PlanDev p, int nblk) {
   }
 }
 
+// plane_lanes != 0: plane-per-lane gather (fewest instructions; one 32-byte sector per (pair, plane) -- right for planes
+// in device memory, where the kernel is bound by the DRAM random-access rate: ~0.5 M 64-byte atoms per Tox21 batch);
+// 0: column-coalesced gather (neighbouring bonded columns of one plane share a load: fewest memory REQUESTS -- right for
+// planes left in pinned host memory, where the PCIe read-request rate is the bound).
 template <bool kCodes>
 __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, const float* __restrict__ adj,
-                                                                 const uint8_t* __restrict__ codes, RelPtrs rel) {
+                                                                 const uint8_t* __restrict__ codes, RelPtrs rel,
+                                                                 int plane_lanes) {
   pdl_prologue();
   __shared__ int s_deg[kPackRows], s_t[kPackRows], s_e[kPackRows];
-  __shared__ unsigned s_mask[8][8];
+  __shared__ unsigned s_mask[8][kRowsPerWarp][8];
+  __shared__ int s_run[8][kRowsPerWarp];             // edges of a row already emitted (rows wider than 256 columns)
   __shared__ int s_hit[8][EAGCN_MAX_VIEWS][32];      // per (view, edge of the chunk): (#nonzero planes << 16) + plane index
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.B * p.N;
@@ -128,6 +134,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
   if (threadIdx.x < kPackRows) {
     const int row = row0 + threadIdx.x;
     s_deg[threadIdx.x] = row < P ? p.deg[row] : 0;
+    s_run[threadIdx.x / kRowsPerWarp][threadIdx.x % kRowsPerWarp] = 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -154,97 +161,162 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
     if (T <= p.t_cap) p.row_ptr[T] = E;
   }
   bool bad = false;
-  for (int r = 0; r < kRowsPerWarp; ++r) {
-    // rows interleaved over the warps (w, w+8, ...): the active rows of a molecule are consecutive, so consecutive
-    // rows per warp left some warps with four active rows and others with none -- the kernel ran at the slowest warp
-    const int lr = r * (kPackRows / kRowsPerWarp) + warp;
-    const int row = row0 + lr;
-    if (row >= P) continue;
-    const int deg = s_deg[lr];
-    if (deg == 0 || s_t[lr] >= p.t_cap) continue;
-    const int e0 = s_e[lr];
-    if (e0 + deg > p.e_cap) continue;            // status already flagged by the scan
-    const int b = row / p.N, i = row - b * p.N;
-    const size_t ba = ((size_t)b * p.N + i) * p.N, bc = (((size_t)b * p.V) * p.N + i) * p.N;
-    int run = 0;
-    for (int jb = 0; jb < p.N; jb += 256) {
-    // the adjacency row is fetched 8 chunks (256 columns) at a time: one memory round trip per row instead of one per
-    // 32-column chunk; the chunk masks go through shared memory (dynamic indexing)
+  // ---- per-lane constants of the plane-per-lane gather (sum_v C_v <= 64: every shipped configuration) ----
+  // lane l owns one-hot planes l and l + 32 of the concatenated (view, channel) list; lane v < V decodes view v
+  int sumC = 0;
+  for (int v = 0; v < p.V; ++v) sumC += p.chan[v];
+  const bool fast = !kCodes && sumC <= 64 && plane_lanes;
+  const float* pl_ptr[2] = {nullptr, nullptr};   // plane base: rel[v] + c * N * N
+  long long pl_bstride[2] = {0, 0};              // C_v * N * N: offset of the next molecule
+  int my_off = 0, my_C = 0;                      // lane v < V: first plane and channel count of view v
+  if (fast) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int c = lane + 32 * h, v = 0;
+      if (c < sumC) {
+        while (c >= p.chan[v]) { c -= p.chan[v]; ++v; }
+        pl_ptr[h] = rel.p[v] + (size_t)c * p.N * p.N;
+        pl_bstride[h] = (long long)p.chan[v] * p.N * p.N;
+      }
+    }
+    if (lane < p.V) {
+      for (int v = 0; v < lane; ++v) my_off += p.chan[v];
+      my_C = p.chan[lane];
+    }
+  }
+  for (int jb = 0; jb < p.N; jb += 256) {
+    // ---- phase A: the adjacency rows of all of this warp's active rows, 256 columns at a time, in ONE memory round
+    // trip (rows are interleaved over the warps -- w, w+8, ... -- because the active rows of a molecule are
+    // consecutive); the per-chunk edge masks go through shared memory (dynamic indexing)
     {
-      float a8[8];
+      float a8[kRowsPerWarp][8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int jj = jb + c * 32 + lane;
-        a8[c] = jj < p.N ? adj_at<kCodes>(adj, codes, p, ba, bc, jj) : 0.0f;
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int lr = r * (kPackRows / kRowsPerWarp) + warp;
+        const int row = row0 + lr;
+        const bool live = row < P && s_deg[lr] > 0 && s_t[lr] < p.t_cap && s_e[lr] + s_deg[lr] <= p.e_cap;
+        const int b = live ? row / p.N : 0, i = live ? row - b * p.N : 0;
+        const size_t ba = ((size_t)b * p.N + i) * p.N, bc = (((size_t)b * p.V) * p.N + i) * p.N;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int jj = jb + c * 32 + lane;
+          a8[r][c] = (live && jj < p.N) ? adj_at<kCodes>(adj, codes, p, ba, bc, jj) : 0.0f;
+        }
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const unsigned mk = __ballot_sync(0xffffffffu, a8[c] != 0.0f);
-        if (lane == 0) s_mask[warp][c] = mk;
-      }
+      for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const unsigned mk = __ballot_sync(0xffffffffu, a8[r][c] != 0.0f);
+          if (lane == 0) s_mask[warp][r][c] = mk;
+        }
       __syncwarp();
     }
-    for (int c = 0; c < 8 && jb + c * 32 < p.N; ++c) {
-      const unsigned m = s_mask[warp][c];
-      if (m == 0) continue;
-      const int j0 = jb + c * 32, j = j0 + lane;
-      const bool nz = (m >> lane) & 1u;
-      const int ne = __popc(m);
-      const int slot = __popc(m & ((1u << lane) - 1u));          // edge index of this lane inside the chunk
-      if (nz) p.colpos[e0 + run + slot] = b * p.N + j;
-      if (kCodes) {
-        for (int v = 0; v < p.V; ++v) {
-          const int C = p.chan[v];
-          if (nz) {
-            const int c = __ldg(codes + bc + (size_t)v * p.N * p.N + j);
-            if (c > C) bad = true;
-            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)(c > C ? C : c);
-          }
-        }
-      } else {
-        // gather ALL views' one-hot planes at the ne bonded pairs of this chunk in one batch: the (plane, edge)
-        // pairs of every view are spread over the lanes (consecutive lanes -> neighbouring columns of one plane)
-        // and up to 4 loads per lane are in flight before any is consumed.
-        for (int v = 0; v < p.V; ++v) s_hit[warp][v][lane] = 0;
-        __syncwarp();
-        int sc = 0;
-        for (int v = 0; v < p.V; ++v) sc += p.chan[v];
-        const int total = ne * sc;
-        for (int base = 0; base < total; base += 128) {
-          float x[4]; int vv[4], cc[4], kk[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * 32 + lane;
-            x[u] = 0.0f; vv[u] = 0; cc[u] = 0; kk[u] = 0;
-            if (idx < total) {
-              int gc = idx / ne, v = 0;
-              kk[u] = idx - gc * ne;
-              while (gc >= p.chan[v]) { gc -= p.chan[v]; ++v; }
-              vv[u] = v; cc[u] = gc;
-              const int jj = __fns(m, 0, kk[u] + 1);               // lane position of the k-th edge
-              x[u] = __ldg(rel.p[v] + ((((size_t)b * p.chan[v]) + gc) * p.N + i) * p.N + j0 + jj);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (x[u] != 0.0f) {
-              if (x[u] != 1.0f) bad = true;
-              atomicAdd(&s_hit[warp][vv[u]][kk[u]], (1 << 16) + cc[u]);
-            }
-        }
-        __syncwarp();
-        if (nz) {
+    // ---- phase B: per row, per 32-column chunk with bonds ----
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int lr = r * (kPackRows / kRowsPerWarp) + warp;
+      const int row = row0 + lr;
+      if (row >= P) continue;
+      const int deg = s_deg[lr];
+      if (deg == 0 || s_t[lr] >= p.t_cap) continue;
+      const int e0 = s_e[lr];
+      if (e0 + deg > p.e_cap) continue;            // status already flagged by the scan
+      const int b = row / p.N, i = row - b * p.N;
+      const size_t bc = (((size_t)b * p.V) * p.N + i) * p.N;
+      const size_t rowoff = (size_t)i * p.N;
+      int run = s_run[warp][r];
+      for (int c = 0; c < 8 && jb + c * 32 < p.N; ++c) {
+        const unsigned m = s_mask[warp][r][c];
+        if (m == 0) continue;
+        const int j0 = jb + c * 32, j = j0 + lane;
+        const bool nz = (m >> lane) & 1u;
+        const int ne = __popc(m);
+        const int slot = __popc(m & ((1u << lane) - 1u));          // edge index of this lane inside the chunk
+        if (nz) p.colpos[e0 + run + slot] = b * p.N + j;
+        if (kCodes) {
           for (int v = 0; v < p.V; ++v) {
-            const int h = s_hit[warp][v][slot];
-            if ((h >> 16) > 1) bad = true;
-            p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)((h >> 16) == 1 ? (h & 0xFFFF) : p.chan[v]);
+            const int C = p.chan[v];
+            if (nz) {
+              const int cc = __ldg(codes + bc + (size_t)v * p.N * p.N + j);
+              if (cc > C) bad = true;
+              p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)(cc > C ? C : cc);
+            }
           }
+        } else if (fast) {
+          // plane-per-lane gather: for each bonded pair, lane l reads planes l and l + 32 at (i, j); two ballots give the
+          // 64-bit set of non-zero planes, lane v cuts out view v's bits (exactly one -> its index, none -> C_v).  Four
+          // pairs (8 loads per lane) are in flight before the first ballot.
+          const float* q0 = pl_ptr[0] ? pl_ptr[0] + (size_t)b * pl_bstride[0] + rowoff + j0 : nullptr;
+          const float* q1 = pl_ptr[1] ? pl_ptr[1] + (size_t)b * pl_bstride[1] + rowoff + j0 : nullptr;
+          unsigned mm = m;
+          for (int k0 = 0; k0 < ne; k0 += 4) {
+            float x0[4], x1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              x0[u] = 0.0f; x1[u] = 0.0f;
+              if (k0 + u < ne) {
+                const int jj = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (q0) x0[u] = __ldg(q0 + jj);
+                if (q1) x1[u] = __ldg(q1 + jj);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if ((x0[u] != 0.0f && x0[u] != 1.0f) || (x1[u] != 0.0f && x1[u] != 1.0f)) bad = true;
+              const unsigned h0 = __ballot_sync(0xffffffffu, x0[u] != 0.0f);
+              const unsigned h1 = __ballot_sync(0xffffffffu, x1[u] != 0.0f);
+              if (lane < p.V && k0 + u < ne) {
+                const unsigned long long hits = ((unsigned long long)h1 << 32) | h0;
+                const unsigned long long sub = (hits >> my_off) & (my_C >= 64 ? ~0ull : ((1ull << my_C) - 1ull));
+                const int cnt = __popcll(sub);
+                if (cnt > 1) bad = true;
+                p.code[(size_t)lane * p.e_cap + e0 + run + k0 + u] = (uint8_t)(cnt == 1 ? __ffsll((long long)sub) - 1 : my_C);
+              }
+            }
+          }
+        } else {
+          // generic gather (sum_v C_v > 64): the (plane, edge) pairs of every view are spread over the lanes
+          // (consecutive lanes -> neighbouring columns of one plane), up to 4 loads per lane in flight
+          for (int v = 0; v < p.V; ++v) s_hit[warp][v][lane] = 0;
+          __syncwarp();
+          const int total = ne * sumC;
+          for (int base = 0; base < total; base += 128) {
+            float x[4]; int vv[4], cc[4], kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = base + u * 32 + lane;
+              x[u] = 0.0f; vv[u] = 0; cc[u] = 0; kk[u] = 0;
+              if (idx < total) {
+                int gc = idx / ne, v = 0;
+                kk[u] = idx - gc * ne;
+                while (gc >= p.chan[v]) { gc -= p.chan[v]; ++v; }
+                vv[u] = v; cc[u] = gc;
+                const int jj = __fns(m, 0, kk[u] + 1);               // lane position of the k-th edge
+                x[u] = __ldg(rel.p[v] + ((((size_t)b * p.chan[v]) + gc) * p.N + i) * p.N + j0 + jj);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (x[u] != 0.0f) {
+                if (x[u] != 1.0f) bad = true;
+                atomicAdd(&s_hit[warp][vv[u]][kk[u]], (1 << 16) + cc[u]);
+              }
+          }
+          __syncwarp();
+          if (nz) {
+            for (int v = 0; v < p.V; ++v) {
+              const int h = s_hit[warp][v][slot];
+              if ((h >> 16) > 1) bad = true;
+              p.code[(size_t)v * p.e_cap + e0 + run + slot] = (uint8_t)((h >> 16) == 1 ? (h & 0xFFFF) : p.chan[v]);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        run += ne;
       }
-      run += ne;
-    }
-    __syncwarp();
+      if (lane == 0) s_run[warp][r] = run;
+      __syncwarp();
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_NOT_ONEHOT);
@@ -341,8 +413,14 @@ static int pack_fill_impl(const eagcn_plan_t* plan, const void* src, const void*
   const int P = p.B * p.N;
   const int nblk = (P + kPackRows - 1) / kPackRows;
   EAGCN_PROF("pack_fill_kernel", st);
+  int plane_lanes = 1;
+  if (!kCodes) {                       // where do the one-hot planes live?  (host-side query, no synchronisation)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, rel[0]) != cudaSuccess) (void)cudaGetLastError();   // unregistered pointer: not ours
+    else if (at.type == cudaMemoryTypeHost) plane_lanes = 0;
+  }
   EAGCN_LAUNCH((pack_fill_kernel<kCodes>), nblk, kPackThreads, 0, st)(p, kCodes ? nullptr : (const float*)src,
-                                                          kCodes ? (const uint8_t*)src : nullptr, rp);
+                                                          kCodes ? (const uint8_t*)src : nullptr, rp, plane_lanes);
   EAGCN_LAUNCH_CHECK();
   EAGCN_PROF("pack_link_kernel", st);
   EAGCN_LAUNCH(pack_link_kernel, (p.t_cap + 7) / 8, 256, 0, st)(p);

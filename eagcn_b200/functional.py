@@ -56,6 +56,19 @@ class Overlap:
         return s
 
     @classmethod
+    def fork_point(cls, dev):
+        """Mark a branch point on the current stream; work enqueued on it afterwards is NOT waited for by fork_from."""
+        e = torch.cuda.Event()
+        e.record(torch.cuda.current_stream(dev))
+        return e
+
+    @classmethod
+    def fork_from(cls, dev, event):
+        s = cls.side(dev)
+        s.wait_event(event)
+        return s
+
+    @classmethod
     def join(cls, dev):
         key = torch.device(dev).index or 0
         torch.cuda.current_stream(dev).wait_stream(cls.side(dev))
@@ -314,12 +327,13 @@ class _GraphConvLayerFn(torch.autograd.Function):
             # take fresh gradients, beside everything that follows in this backward pass)
             w.phase = 1
             check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
-            side = Overlap.fork(dev)
+            forked = Overlap.fork_point(dev)            # the branch point: after the aggregation backward
+            w.phase = 2                                 # dH first: it is the one on the critical path (next layer's input)
+            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
+            side = Overlap.fork_from(dev, forked)
             w.phase = 4
             check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), ctypes.c_void_p(side.cuda_stream)),
                   "eagcn_layer_backward_b")
-            w.phase = 2
-            check(L.eagcn_layer_backward_b(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_b")
             if Overlap.fresh(ctx.param_refs):
                 Overlap.defer_join(dev, (H, Q, gemm_ws, dwall, partial, datt, Z, Y, dY))
             else:

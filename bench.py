@@ -155,6 +155,7 @@ def algorithmic(T, E, B, N):
         acc("agg_fwd_kernel", 4 * 2 * T * C + E * (4 + V) + 4 * V * T, 2 * (E + T) * C)
         acc("agg_bwd_kernel", 4 * 4 * T * C + E * (4 + 2 * V) + 4 * V * T, 4 * (E + T) * C)
         acc("bn_apply_kernel", 8 * T * C, 0)
+        acc("bn_stat_apply_kernel", 8 * T * C, 0)
         acc("bn_bwd_partial_kernel", 8 * T * C, 0)
         acc("bn_bwd_apply_kernel", 12 * T * C, 0)
         fin = C
@@ -188,6 +189,7 @@ def run_b200(args):
     model = build_model(dev)
     EF.Overlap.enabled = bool(args.overlap)
     _lib.lib().eagcn_set_bn_act_mode(0 if args.bn_act == "vec" else 1)
+    _lib.lib().eagcn_set_fuse_mode(0 if args.fuse_bn else 1)
     if args.no_pdl:
         _lib.lib().eagcn_set_pdl(0)
     from eagcn_b200 import models as _M2
@@ -725,6 +727,8 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="1: independent branches of a step on a side stream (parallel graph branches); 0: one stream")
     ap.add_argument("--bn-act", default="vec", choices=["vec", "c32"], help="head BatchNorm kernels: float4 or 32-channel")
+    ap.add_argument("--fuse-bn", type=int, default=1, choices=[0, 1],
+                    help="1: statistics reduction fused into the forward BatchNorm apply kernel; 0: separate kernels")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2],
                     help="e2e input pipeline: H2D copies issued this many batches ahead (2: copy of batch i+2, packing of "
                          "batch i+1 and the step of batch i overlap)")

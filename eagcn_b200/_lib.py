@@ -115,6 +115,8 @@ _PROTOS = {
     "eagcn_gemm_trace_stride": (c_int64, []),
     "eagcn_rng_fork": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "eagcn_rng_fork_n": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "eagcn_set_fuse_mode": (c_int, [c_int]),
+    "eagcn_get_fuse_mode": (c_int, []),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

@@ -32,6 +32,12 @@ extern "C" int eagcn_set_agg_mode(int mode) {
   return 0;
 }
 extern "C" int eagcn_get_agg_mode(void) { return eagcn::agg_mode(); }
+extern "C" int eagcn_set_fuse_mode(int mode) {
+  if (mode < 0 || mode > 1) return EAGCN_E_ARG;
+  eagcn::fuse_mode() = mode;
+  return 0;
+}
+extern "C" int eagcn_get_fuse_mode(void) { return eagcn::fuse_mode(); }
 extern "C" int eagcn_set_pdl(int on) { eagcn::pdl_mode() = on ? 1 : 0; return 0; }
 extern "C" int eagcn_get_pdl(void) { return eagcn::pdl_mode(); }
 extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,

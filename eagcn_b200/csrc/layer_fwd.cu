@@ -25,6 +25,7 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const int* Mdev, cudaStream_t st);
 inline int& gemm_mode() { static int m = 0; return m; }
 inline int& agg_mode() { static int m = 0; return m; }   // 0: shared-memory tile kernels when eligible, 1: generic
+inline int& fuse_mode() { static int m = 0; return m; }  // 0: statistics reduction fused into the BatchNorm apply kernel, 1: separate
 
 // ---------------------------------------------------------------------------------------------
 // wallT: [2][fo_tot][fin] and wsplit: [2][fin][fo_tot] hold the exact TF32 split of every weight
@@ -466,6 +467,113 @@ __global__ void __launch_bounds__(32 * kStatLanes) stat_reduce_kernel(PlanDev p,
   }
 }
 
+// Training-mode forward with per-replica statistics: stat_reduce (kind 1) and bn_apply in ONE launch.  grid (ceil(C/32), R):
+// every CTA of a channel block repeats the (cheap, L2-resident) fixed-order reduction of the tile partials for its 32
+// channels -- the same order as stat_reduce_kernel, so the statistics are bit-identical -- and then normalises its share
+// of the rows; the CTAs with blockIdx.y == 0 also publish sums / mean / invstd and update the running statistics.
+// Saves one dependent launch per layer (the step is bound by launch count and latency).
+__global__ void __launch_bounds__(32 * kStatLanes) bn_stat_apply_kernel(
+    PlanDev p, LayerDev L, const float* __restrict__ partial, double* __restrict__ sums, const float* __restrict__ Y,
+    const float* __restrict__ ball, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ X, int C,
+    double M, double eps, double momentum, float p_drop, const unsigned long long* rng, unsigned long long rng_stream) {
+  pdl_prologue();
+  __shared__ double s[kStatLanes][2][32];
+  __shared__ __align__(16) float s_mu[32], s_is[32];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  const int ntile = (T + kStatRows - 1) / kStatRows;
+  // apply-phase mapping: 8 float4 channel lanes x 128 row lanes over this CTA's share of the rows.  The thread's first
+  // kPre rows of Y are requested NOW, so that their memory latency runs under the reduction below.
+  constexpr int kPre = 6;
+  const int c4l = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int cc = blockIdx.x * 32 + c4l * 4;
+  const int per = (p.t_cap + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(p.t_cap, r0 + per);
+  float4 yv[kPre];
+#pragma unroll
+  for (int k = 0; k < kPre; ++k) {
+    const int t = r0 + rl + 128 * k;
+    yv[k] = (cc < C && t < r1 && t < T) ? __ldg(reinterpret_cast<const float4*>(Y + (size_t)t * C + cc))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int t = ty; t < ntile; t += kStatLanes) {
+      a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
+      b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
+    }
+  }
+  s[ty][0][cx] = a; s[ty][1][cx] = b;
+  __syncthreads();
+  if (ty < 2 && c < C) {                 // warp 0 finishes the S1 column, warp 1 the S2 column
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStatLanes; ++w) acc += s[w][ty][cx];
+    if (blockIdx.y == 0) sums[ty * C + c] = acc;
+    s[0][ty][cx] = acc;
+  }
+  __syncthreads();
+  if (ty == 0) {
+    float mu = 0.f, is = 0.f;
+    if (c < C) {
+      const double s1 = s[0][0][cx], s2 = s[0][1][cx];
+      const double bb = (double)ball[c];
+      const double m1 = s1 / M;                            // mean of (Y - b) over all positions
+      double var = s2 / M - m1 * m1;                       // biased variance (shift-invariant)
+      if (var < 0.0) var = 0.0;
+      const double mud = bb + m1;
+      mu = (float)mud;
+      is = (float)(1.0 / sqrt(var + eps));
+      if (blockIdx.y == 0) {                               // publish + running statistics (bn_finalize_channel)
+        int v = 0;
+        while (v + 1 < L.V && c >= L.off[v + 1]) ++v;
+        const int cc = c - L.off[v];
+        mean[c] = mu; invstd[c] = is;
+        const double unb = M > 1.0 ? var * (M / (M - 1.0)) : var;
+        L.run_mean[v][cc] = (float)((1.0 - momentum) * (double)L.run_mean[v][cc] + momentum * mud);
+        L.run_var[v][cc] = (float)((1.0 - momentum) * (double)L.run_var[v][cc] + momentum * unb);
+        if (cc == 0 && L.nbt[v]) L.nbt[v][0] += 1;
+      }
+    }
+    s_mu[cx] = mu; s_is[cx] = is;
+  }
+  __syncthreads();
+  // ---- apply ----
+  if (cc >= C) return;
+  const float4 mu = *reinterpret_cast<const float4*>(s_mu + c4l * 4), is = *reinterpret_cast<const float4*>(s_is + c4l * 4);
+  const float4 ga = *reinterpret_cast<const float4*>(ball + C + cc), be = *reinterpret_cast<const float4*>(ball + 2 * C + cc);
+  const bool drop = p_drop > 0.0f;
+  const float scale = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  unsigned long long seed = 0, off = 0;
+  if (drop) { seed = rng[0]; off = rng[1]; }
+  const Philox ph(seed);
+  for (int k = 0, t = r0 + rl; t < r1; t += 128, ++k) {
+    const size_t idx = (size_t)t * C + cc;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) {
+      float4 y;
+      switch (k) {                                          // registers for the prefetched rows, memory beyond
+        case 0: y = yv[0]; break; case 1: y = yv[1]; break; case 2: y = yv[2]; break;
+        case 3: y = yv[3]; break; case 4: y = yv[4]; break; case 5: y = yv[5]; break;
+        default: y = __ldg(reinterpret_cast<const float4*>(Y + idx)); break;
+      }
+      o.x = fmaxf((y.x - mu.x) * is.x * ga.x + be.x, 0.f);
+      o.y = fmaxf((y.y - mu.y) * is.y * ga.y + be.y, 0.f);
+      o.z = fmaxf((y.z - mu.z) * is.z * ga.z + be.z, 0.f);
+      o.w = fmaxf((y.w - mu.w) * is.w * ga.w + be.w, 0.f);
+      if (drop) {
+        bool k[4];
+        dropout_keep4(ph, off, rng_stream, (unsigned long long)idx, p_drop, k);
+        o.x = k[0] ? o.x * scale : 0.f; o.y = k[1] ? o.y * scale : 0.f;
+        o.z = k[2] ? o.z * scale : 0.f; o.w = k[3] ? o.w * scale : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(X + idx) = o;
+  }
+}
+
 // BatchNorm finalize from already reduced (and possibly all-reduced) sums
 __global__ void __launch_bounds__(256) bn_finalize_kernel(LayerDev L, const float* __restrict__ ball,
                                                           const double* __restrict__ sums, float* __restrict__ mean,
@@ -684,6 +792,21 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const int training = (w->training & 1) ? 1 : 0;
+  if (training && !(w->training & 2) && fuse_mode() == 0 && (C & 3) == 0 && aligned16(w->Y) && aligned16(w->X) &&
+      aligned16(w->ball)) {
+    // per-replica statistics, float4 layout: reduction of the tile partials + finalize + normalise/ReLU/dropout in ONE launch
+    if (!w->partial) return EAGCN_E_ARG;
+    const int nblk = (C + 31) / 32;
+    int R = 148 / nblk;                   // 1024-thread CTAs at ~60 registers: one per SM -> a single wave
+    R = R < 1 ? 1 : (R > 16 ? 16 : R);
+    EAGCN_PROF("bn_stat_apply_kernel", st);
+    EAGCN_LAUNCH(bn_stat_apply_kernel, dim3(nblk, R), 32 * kStatLanes, 0, st)(
+        p, L, (const float*)w->partial, (double*)w->sums, (const float*)w->Y, (const float*)w->ball, (float*)w->mean,
+        (float*)w->invstd, (float*)w->X, C, M, w->eps, w->momentum, (float)w->p_drop, (const unsigned long long*)w->rng,
+        (unsigned long long)w->rng_stream);
+    EAGCN_LAUNCH_CHECK();
+    return 0;
+  }
   if (training && !(w->training & 2)) {
     // per-replica statistics: reduce the tile partials and finalize in one kernel
     if (!w->partial) return EAGCN_E_ARG;

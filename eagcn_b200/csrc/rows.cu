@@ -74,6 +74,37 @@ __global__ void __launch_bounds__(512) readout_sum_kernel(PlanDev p, const float
   }
 }
 
+// float4 form (F % 4 == 0): grid (B, ceil(F/256)); 64 float4 channel lanes x 4 row groups.  The 512-thread scalar kernel
+// above needs B * F/64 = 2 816 CTAs (five waves of tiny CTAs: 8.9 us for 13.6 MB); this one 768 CTAs with 16-byte loads.
+__global__ void __launch_bounds__(256) readout_sum_vec_kernel(PlanDev p, const float* __restrict__ packed,
+                                                              float* __restrict__ out, int F) {
+  pdl_prologue();
+  __shared__ float4 s[4][64];
+  const int b = blockIdx.x;
+  const int cx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int nc4 = F >> 2, c4 = blockIdx.y * 64 + cx;
+  const int t0 = p.mol_ptr[b], t1 = p.mol_ptr[b + 1];
+  const int per = (t1 - t0 + 3) >> 2;
+  const int a0 = t0 + g * per, a1 = min(t1, a0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < nc4) {
+    const float4* src = reinterpret_cast<const float4*>(packed) + c4;
+#pragma unroll 4
+    for (int t = a0; t < a1; ++t) {
+      const float4 v = __ldg(src + (size_t)t * nc4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  s[g][cx] = acc;
+  __syncthreads();
+  if (g == 0 && c4 < nc4) {
+    float4 r = s[0][cx];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { const float4 v = s[k][cx]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    reinterpret_cast<float4*>(out)[(size_t)b * nc4 + c4] = r;
+  }
+}
+
 __global__ void __launch_bounds__(256) readout_sum_bwd_kernel(PlanDev p, const float* __restrict__ dout,
                                                               float* __restrict__ dpacked, int F) {
   pdl_prologue();
@@ -141,9 +172,14 @@ extern "C" int eagcn_rows_scatter(const eagcn_plan_t* plan, const void* packed, 
 extern "C" int eagcn_readout_sum(const eagcn_plan_t* plan, const void* packed, void* out, int64_t F, void* stream) {
   if (!plan_ok(plan) || !out || !packed || F <= 0) return EAGCN_E_ARG;
   PlanDev p = to_dev(plan);
-  dim3 grid(p.B, (unsigned)((F + 63) / 64));
   EAGCN_PROF("readout_sum_kernel", (cudaStream_t)stream);
-  EAGCN_LAUNCH(readout_sum_kernel, grid, 512, 0, (cudaStream_t)stream)(p, (const float*)packed, (float*)out, (int)F);
+  if ((F & 3) == 0 && aligned16(packed) && aligned16(out)) {
+    dim3 grid(p.B, (unsigned)((F / 4 + 63) / 64));
+    EAGCN_LAUNCH(readout_sum_vec_kernel, grid, 256, 0, (cudaStream_t)stream)(p, (const float*)packed, (float*)out, (int)F);
+  } else {
+    dim3 grid(p.B, (unsigned)((F + 63) / 64));
+    EAGCN_LAUNCH(readout_sum_kernel, grid, 512, 0, (cudaStream_t)stream)(p, (const float*)packed, (float*)out, (int)F);
+  }
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

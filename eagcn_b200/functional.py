@@ -724,9 +724,10 @@ class _DenseMmFn(torch.autograd.Function):
             return dx, dW, None
         dx = dW = None
         if need_dw and need_dx and Overlap.enabled:
-            side = Overlap.fork(dy.device)
+            forked = Overlap.fork_point(dy.device)
+            dx = _mm_tile(dy, False, W, True)[0]          # first: the rest of the backward pass waits for it
+            side = Overlap.fork_from(dy.device, forked)
             dW, ws = _mm_tile(x, True, dy, False, stream=side)
-            dx = _mm_tile(dy, False, W, True)[0]
             if Overlap.fresh((ctx.w_ref,)):
                 # dW itself is NOT kept: an extra reference would make autograd copy it instead of adopting it
                 Overlap.defer_join(dy.device, (x, dy, ws))

@@ -280,6 +280,12 @@ int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock st
 int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);
 int eagcn_get_agg_mode(void);
+/* --- forward BatchNorm fusion ------------------------------------------------------------------- */
+/* 0 (default): in training mode with per-replica statistics eagcn_layer_forward_b is ONE launch (reduction of the tile
+ * partials + finalize + normalise / ReLU / dropout; bit-identical statistics); 1: the separate stat_reduce and
+ * bn_apply kernels.  Process-wide.                                                                              */
+int eagcn_set_fuse_mode(int mode);
+int eagcn_get_fuse_mode(void);
 /* --- programmatic dependent launch ------------------------------------------------------------- */
 /* 1 (default): kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization -- every kernel begins
  * with griddepcontrol.launch_dependents + griddepcontrol.wait, so results are those of plain stream order while the

@@ -830,3 +830,36 @@ def test_rng_prefork_matches_forks():
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert torch.equal(end_a, r.state)
+
+
+def test_fused_bn_forward_bit_identical():
+    """eagcn_layer_forward_b as one launch (statistics reduction + finalize + apply) against the separate kernels:
+    same reduction order, so outputs, saved statistics and running statistics are bit-identical."""
+    from eagcn_b200 import functional as EF, models as EM, _lib
+    from eagcn_b200.data import make_batch
+    dev = _cuda()
+    batch = make_batch(32, "tox21", seed=5)
+    dense = [torch.from_numpy(a).to(dev) for a in batch.dense()]
+    size = torch.from_numpy(batch.sizes).to(dev)
+    res = []
+    for mode in (1, 0):
+        _lib.lib().eagcn_set_fuse_mode(mode)
+        try:
+            torch.manual_seed(0)
+            model = EM.EAGCNStack(30, 24, [(16,) * 5, (28,) * 5], 32, 16, 3, dropout=0.3).to(dev)
+            model.train()
+            EF.manual_seed(5)
+            out, atom, _ = model(*dense, size)
+            out.sum().backward()
+            torch.cuda.synchronize()
+            res.append((out.detach().clone(), atom.materialize().clone(),
+                        {k: v.detach().clone() for k, v in model.state_dict().items()},
+                        {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}))
+        finally:
+            _lib.lib().eagcn_set_fuse_mode(0)
+    (o0, a0, sd0, g0), (o1, a1, sd1, g1) = res
+    assert torch.equal(o0, o1) and torch.equal(a0, a1)
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k

@@ -190,6 +190,7 @@ def run_b200(args):
     EF.Overlap.enabled = bool(args.overlap)
     _lib.lib().eagcn_set_bn_act_mode(0 if args.bn_act == "vec" else 1)
     _lib.lib().eagcn_set_fuse_mode(0 if args.fuse_bn else 1)
+    _lib.lib().eagcn_set_tc_bk(args.tc_bk)
     if args.no_pdl:
         _lib.lib().eagcn_set_pdl(0)
     from eagcn_b200 import models as _M2
@@ -305,8 +306,9 @@ def run_b200(args):
             if nkb <= 0:
                 continue
             t0 = h[4]
-            kb = [[int(x - t0) for x in tr[l, 8 + 5 * k: 13 + 5 * k].tolist()] for k in range(min(nkb, 64))]
-            out.append({"num_kb": nkb, "BN": h[1], "stages": h[2], "mode": h[3], "epi_start": h[5] - t0,
+            per = (stride - 8) // 64
+            kb = [[int(x - t0) for x in tr[l, 8 + per * k: 8 + per * k + 8].tolist()] for k in range(min(nkb, 64))]
+            out.append({"num_kb": nkb, "BN": h[1], "stages": h[2], "mode": h[3], "bk": h[7], "epi_start": h[5] - t0,
                         "epi_end": h[6] - t0, "kb": kb})
         print(json.dumps({"gemm_trace": out}))
         return
@@ -727,6 +729,8 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="1: independent branches of a step on a side stream (parallel graph branches); 0: one stream")
     ap.add_argument("--bn-act", default="vec", choices=["vec", "c32"], help="head BatchNorm kernels: float4 or 32-channel")
+    ap.add_argument("--tc-bk", type=int, default=0, choices=[0, 16, 32],
+                    help="k-block of the K-major tcgen05 products (0: pipeline model picks per shape)")
     ap.add_argument("--fuse-bn", type=int, default=1, choices=[0, 1],
                     help="1: statistics reduction fused into the forward BatchNorm apply kernel; 0: separate kernels")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2],

@@ -117,6 +117,7 @@ _PROTOS = {
     "eagcn_rng_fork_n": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "eagcn_set_fuse_mode": (c_int, [c_int]),
     "eagcn_get_fuse_mode": (c_int, []),
+    "eagcn_set_tc_bk": (c_int, [c_int]),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

@@ -38,6 +38,11 @@ extern "C" int eagcn_set_fuse_mode(int mode) {
   return 0;
 }
 extern "C" int eagcn_get_fuse_mode(void) { return eagcn::fuse_mode(); }
+extern "C" int eagcn_set_tc_bk(int bk) {
+  if (bk != 0 && bk != 16 && bk != 32) return EAGCN_E_ARG;
+  eagcn::tc::nt_bk_override() = bk;
+  return 0;
+}
 extern "C" int eagcn_set_pdl(int on) { eagcn::pdl_mode() = on ? 1 : 0; return 0; }
 extern "C" int eagcn_get_pdl(void) { return eagcn::pdl_mode(); }
 extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,

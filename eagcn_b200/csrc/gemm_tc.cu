@@ -32,9 +32,12 @@ namespace eagcn {
 namespace tc {
 
 constexpr int BM = 128;            // UMMA M
-constexpr int BK = 32;             // fp32 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int BK = 32;             // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row (TN mode: always)
+// NT mode can instead run k-blocks of 16 elements (64-byte rows, SWIZZLE_64B): half the bytes per pipeline stage, so
+// twice the stages fit (the 2-stage BK = 32 pipeline of the wide tiles exposes TMA latency + transform: 2 090 cycles
+// per 32 k against 1 290 of tensor-pipe work).  Parity-tested, but measured slower end to end; see pick_bn.
 constexpr int UK = 8;              // UMMA K for kind::tf32 (32 bytes)
-constexpr int MAX_STAGES = 4;      // smem ring depth is chosen on the host (as many stages as fit in 200 KB)
+constexpr int MAX_STAGES = 6;      // smem ring depth is chosen on the host (as many stages as fit in 200 KB)
 constexpr int kThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 transform + epilogue
 constexpr int kXformThreads = 256;
 constexpr int kSmemBudget = 224 * 1024;   // dynamic shared memory per CTA (227 KB opt-in limit minus the static part)
@@ -78,13 +81,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 (1024 B: 8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// bk == 16: SWIZZLE_64B (layout 4), 8 rows x 64 B = 512 B per group.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((bk == 16 ? 512 : 1024) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(bk == 16 ? 4 : 2) << 61;
   return d;
 }
 
@@ -152,10 +156,11 @@ struct TcArgs {
   int b_split;                     // NT: B arrives already split (mapB = hi, mapB2 = lo): no transform of B
   const int* Kdev;                 // TN: live K rows = min(*Kdev, K)
   int kchunk;                      // TN: K rows per blockIdx.z
+  int bk;                          // elements per k-block: 32 (SWIZZLE_128B) or, NT only, 16 (SWIZZLE_64B)
   long long split_stride;          // TN: elements between split partials
   long long* trace;                // diagnostic: clock64 stamps of CTA (0,0,0)'s pipeline events (nullptr: off)
 };
-constexpr int kTraceKb = 64, kTraceStride = 8 + 5 * kTraceKb;
+constexpr int kTraceKb = 64, kTracePer = 8, kTraceStride = 8 + kTracePer * kTraceKb;
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -169,18 +174,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
   const bool tn = g.mode == 1;
   const int M = tn ? g.Mcap : min(*g.Mdev, g.Mcap);
-  int k_lo = 0, num_kb = (g.K + BK - 1) / BK;
+  const int bk = g.bk;
+  int k_lo = 0, num_kb = (g.K + bk - 1) / bk;
   if (tn) {
     const int Kt = min(*g.Kdev, g.K);
     k_lo = blockIdx.z * g.kchunk;
     const int k_hi = min(Kt, k_lo + g.kchunk);
-    num_kb = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
+    num_kb = k_hi > k_lo ? (k_hi - k_lo + bk - 1) / bk : 0;
     g.C += (long long)blockIdx.z * g.split_stride;
   }
 
   const bool tr = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (tr && threadIdx.x == 0) {
-    g.trace[0] = num_kb; g.trace[1] = g.BN; g.trace[2] = g.stages; g.trace[3] = g.mode; g.trace[4] = clock64();
+    g.trace[0] = num_kb; g.trace[1] = g.BN; g.trace[2] = g.stages; g.trace[3] = g.mode; g.trace[4] = clock64(); g.trace[7] = bk;
   }
   if (m0 >= M || num_kb == 0) {        // nothing to accumulate: keep the tile defined (zeros)
     for (int i = threadIdx.x; i < BM * g.BN; i += kThreads) {
@@ -192,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   // 1024-byte aligned carve-up: per stage [A raw/hi | A lo | B raw/hi | B lo]
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t bytesA = BM * BK * 4, bytesB = (uint32_t)g.BN * BK * 4;
+  const uint32_t bytesA = BM * bk * 4, bytesB = (uint32_t)g.BN * bk * 4;
   const uint32_t stage_bytes = 2 * bytesA + 2 * bytesB;
   auto sA_hi = [&](int s) { return base + (size_t)s * stage_bytes; };
   auto sA_lo = [&](int s) { return base + (size_t)s * stage_bytes + bytesA; };
@@ -220,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_d = tmem_base_smem;
   const uint32_t tmem_c = tmem_d + (uint32_t)g.BN;                 // correction accumulator: columns [BN, 2*BN)
   // TN: 32-wide MN boxes actually inside the tensors (the others are zero-filled by the transform warps)
-  const uint32_t box_bytes = BK * 128;
+  const uint32_t box_bytes = bk * 128;
   const int nboxA = tn ? min(BM / 32, (g.Mcap - m0 + 31) / 32) : 0;
   const int nboxB = tn ? min(g.BN / 32, (g.N - n0 + 31) / 32) : 0;
 
@@ -230,14 +236,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % g.stages, it = kb / g.stages;
         if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
-        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 0] = clock64();
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 0] = clock64();
         if (!tn) {
           mbar_expect_tx(&bar_full[s], bytesA + (g.b_split ? 2 : 1) * bytesB);
-          tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * BK, m0);
-          tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * BK, n0);
-          if (g.b_split) tma_load_2d(&mapB2, &bar_full[s], sB_lo(s), kb * BK, n0);
+          tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * bk, m0);
+          tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * bk, n0);
+          if (g.b_split) tma_load_2d(&mapB2, &bar_full[s], sB_lo(s), kb * bk, n0);
         } else {
-          const int krow = k_lo + kb * BK;
+          const int krow = k_lo + kb * bk;
           mbar_expect_tx(&bar_full[s], (uint32_t)(nboxA + nboxB) * box_bytes);
           for (int i = 0; i < nboxA; ++i) tma_load_2d(&mapA, &bar_full[s], sA_hi(s) + i * box_bytes, m0 + 32 * i, krow);
           for (int i = 0; i < nboxB; ++i) tma_load_2d(&mapB, &bar_full[s], sB_hi(s) + i * box_bytes, n0 + 32 * i, krow);
@@ -251,38 +257,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // TN: a_major (bit 15) = b_major (bit 16) = 1 (MN-major)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % g.stages, it = kb / g.stages;
-      mbar_wait(&bar_ready[s], it & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 3] = clock64();
-        const uint64_t dAh = tn ? make_desc_mn(smem_u32(sA_hi(s)), box_bytes) : make_desc(smem_u32(sA_hi(s)));
-        const uint64_t dAl = tn ? make_desc_mn(smem_u32(sA_lo(s)), box_bytes) : make_desc(smem_u32(sA_lo(s)));
-        const uint64_t dBh = tn ? make_desc_mn(smem_u32(sB_hi(s)), box_bytes) : make_desc(smem_u32(sB_hi(s)));
-        const uint64_t dBl = tn ? make_desc_mn(smem_u32(sB_lo(s)), box_bytes) : make_desc(smem_u32(sB_lo(s)));
-#pragma unroll
-        for (int k = 0; k < BK / UK; ++k) {
-          // NT: +32 bytes per UMMA_K inside the 128B swizzle row;  TN: +1024 bytes (next group of 8 k rows)
+    // a single thread runs the whole issue loop: nothing of it needs the other 31 lanes, and re-converging the warp
+    // every k-block (__syncwarp + 32 lanes polling the barrier) sat on the critical path of the tensor pipe
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 5] = clock64();
+        mbar_wait(&bar_ready[s], ph);
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 6] = clock64();
+        tc_fence_after();
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 3] = clock64();
+        const uint64_t dAh = tn ? make_desc_mn(smem_u32(sA_hi(s)), box_bytes) : make_desc(smem_u32(sA_hi(s)), bk);
+        const uint64_t dAl = tn ? make_desc_mn(smem_u32(sA_lo(s)), box_bytes) : make_desc(smem_u32(sA_lo(s)), bk);
+        const uint64_t dBh = tn ? make_desc_mn(smem_u32(sB_hi(s)), box_bytes) : make_desc(smem_u32(sB_hi(s)), bk);
+        const uint64_t dBl = tn ? make_desc_mn(smem_u32(sB_lo(s)), box_bytes) : make_desc(smem_u32(sB_lo(s)), bk);
+        const int nk = bk / UK;
+#pragma unroll 4
+        for (int k = 0; k < nk; ++k) {
+          // NT: +32 bytes per UMMA_K inside the swizzled (128 B or 64 B) row;  TN: +1024 bytes (next group of 8 k rows)
           const uint64_t adv = tn ? (uint64_t)((k * 1024) >> 4) : (uint64_t)((k * UK * 4) >> 4);
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
           umma_tf32(tmem_c, dAl + adv, dBh + adv, idesc, acc);    // correction terms -> second accumulator
           umma_tf32(tmem_c, dAh + adv, dBl + adv, idesc, 1u);
           umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);    // main term
         }
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 4] = clock64();
         umma_commit(&bar_empty[s]);                               // smem stage free once these MMAs retire
         if (kb == num_kb - 1) umma_commit(&bar_acc);              // accumulator complete
-        if (tr && kb < kTraceKb) g.trace[8 + kb * 5 + 4] = clock64();
+        if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 7] = clock64();
+        if (++s == g.stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ===================== transform (hi/lo split), then epilogue =====================
     const int xt = threadIdx.x - 64;                              // 0..255
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % g.stages, it = kb / g.stages;
       mbar_wait(&bar_full[s], it & 1);
-      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * 5 + 1] = clock64();
+      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * kTracePer + 1] = clock64();
       if (tn) {                                                    // boxes outside the tensors were not loaded
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         uint4* ah = reinterpret_cast<uint4*>(sA_hi(s));
@@ -296,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       fence_proxy_async();                                         // generic-proxy writes -> visible to UMMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ready[s]);                   // 8 arrivals per stage instead of 256
-      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * 5 + 2] = clock64();
+      if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * kTracePer + 2] = clock64();
     }
     // ---- epilogue: TMEM -> registers -> global ----
     mbar_wait(&bar_acc, 0);
@@ -397,21 +410,22 @@ static EncodeTiledFn encode_fn() {
 // 2D fp32 row-major [rows, cols] (cols contiguous), box = [box_rows, 32 floats], 128B swizzle, OOB -> 0
 // (NT: rows = M or N index, cols = K;  TN: rows = K index, cols = M or N index -- same encoding)
 static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows,
-                     bool atom32 = false) {
+                     bool atom32 = false, int bk = BK) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(atom32 ? BK : bk), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int pick_stages(int BN, int num_kb) {
-  const int stage_bytes = 2 * BM * BK * 4 + 2 * BN * BK * 4;
+static int pick_stages(int BN, int num_kb, int bk = BK) {
+  const int stage_bytes = 2 * BM * bk * 4 + 2 * BN * bk * 4;
   int st = (kSmemBudget - 1024) / stage_bytes;
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (st > num_kb) st = num_kb;
@@ -422,28 +436,38 @@ static int pick_stages(int BN, int num_kb) {
 // per SM, so first avoid a nearly empty second wave; then a k-block costs max(MMA, (TMA round trip + transform +
 // MMA) / stages) -- a tile narrow enough for a third shared-memory stage (144 columns for N = 400, with the full
 // 224 KB of dynamic shared memory) hides most of the TMA round trip, which the clock trace shows exposed with two.
-static int pick_bn(int N, int mtiles, int K, bool b_presplit) {
-  int best = 128;
+inline int& nt_bk_override() { static int v = 0; return v; }   // 0: model picks; 16 / 32: forced (A/B measurements)
+
+static int pick_bn(int N, int mtiles, int K, bool b_presplit, int* bk_out) {
+  int best = 128, best_bk = BK;
   long long best_cost = 1LL << 60;
-  const int kb = (K + BK - 1) / BK;
-  for (int bn = 256; bn >= 64; bn -= 16) {                   // UMMA M = 128 needs N % 16 == 0
-    const int ntiles = (N + bn - 1) / bn;
-    const long long tiles = (long long)ntiles * mtiles;
-    const long long rounds = (tiles + 147) / 148;
-    const int stage_bytes = 2 * BM * BK * 4 + 2 * bn * BK * 4;
-    int stages = (kSmemBudget - 1024) / stage_bytes;
-    stages = stages > MAX_STAGES ? MAX_STAGES : stages;
-    stages = stages > kb ? kb : stages;
-    stages = stages < 1 ? 1 : stages;
-    const long long xform = 300 + 30 * (16 + (b_presplit ? 0 : bn / 8));
-    const long long mma = 12 * (bn / 2 > 75 ? bn / 2 : 75);
-    const long long tma = 1500 + 8 * (16 + bn / 4);                  // ~KB per k-block -> cycles (fit: 76 KB ~ 2100)
-    long long per_kb = (400 + tma + xform + 100 + mma) / stages;
-    per_kb = per_kb < mma ? mma : per_kb;
-    per_kb = per_kb < xform + 300 ? xform + 300 : per_kb;
-    const long long cost = rounds * (kb * per_kb + 4000 + 25 * bn) * 100 + (long long)(ntiles * bn - N);
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+  for (int bk = 32; bk >= 16; bk -= 16) {
+    // measured (r02 A/B, bench --tc-bk): the 64-byte k-blocks run 4-6 stages deep but pay the per-k-block hand-offs
+    // twice as often -- 704 k vs 723 k molecules/s -- so they are opt-in (eagcn_set_tc_bk(16)) until that cost is gone
+    if (bk != (nt_bk_override() ? nt_bk_override() : BK)) continue;
+    const int kb = (K + bk - 1) / bk;
+    for (int bn = 256; bn >= 64; bn -= 16) {                   // UMMA M = 128 needs N % 16 == 0
+      const int ntiles = (N + bn - 1) / bn;
+      const long long tiles = (long long)ntiles * mtiles;
+      const long long rounds = (tiles + 147) / 148;
+      const int stage_bytes = 2 * BM * bk * 4 + 2 * bn * bk * 4;
+      int stages = (kSmemBudget - 1024) / stage_bytes;
+      stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+      stages = stages > kb ? kb : stages;
+      stages = stages < 1 ? 1 : stages;
+      const int raw_kb = (BM * bk * 4 + (b_presplit ? 2 : 1) * bn * bk * 4) / 1024;   // KB landed per k-block
+      const int split_kb = (BM * bk * 4 + (b_presplit ? 0 : bn * bk * 4)) / 1024;     // KB the transform warps split
+      const long long xform = 300 + 30 * split_kb;
+      const long long mma = 3 * (bk / UK) * (bn / 2 > 75 ? bn / 2 : 75);
+      const long long tma = 1500 + 8 * raw_kb;                         // fit: 76 KB ~ 2100 cycles
+      long long per_kb = (400 + tma + xform + 100 + mma) / stages;
+      per_kb = per_kb < mma + 60 ? mma + 60 : per_kb;                  // + barrier hand-off per k-block
+      per_kb = per_kb < xform + 300 ? xform + 300 : per_kb;
+      const long long cost = rounds * (kb * per_kb + 4000 + 25 * bn) * 100 + (long long)(ntiles * bn - N);
+      if (cost < best_cost) { best_cost = cost; best = bn; best_bk = bk; }
+    }
   }
+  *bk_out = best_bk;
   return best;
 }
 
@@ -464,14 +488,15 @@ static long long* next_trace() {
 // B_lo != nullptr: B is pre-split (B = hi part, B_lo = lo part, same leading dimension)
 int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
                const int* Mdev, cudaStream_t st, const char* tag, const float* B_lo = nullptr) {
-  const int BN = pick_bn(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr);
+  int bk = BK;
+  const int BN = pick_bn(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr, &bk);
   CUtensorMap mA, mB, mB2;
-  if (!make_map(&mA, A, Mcap, K, lda, BM) || !make_map(&mB, B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
-  if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN)) return EAGCN_E_UNSUPPORTED;
-  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, 0, next_trace()};
+  if (!make_map(&mA, A, Mcap, K, lda, BM, false, bk) || !make_map(&mB, B, N, K, ldb, BN, false, bk)) return EAGCN_E_UNSUPPORTED;
+  if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN, false, bk)) return EAGCN_E_UNSUPPORTED;
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, bk, 0, next_trace()};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // main + correction accumulators
-  g.stages = pick_stages(BN, (K + BK - 1) / BK);
-  const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  g.stages = pick_stages(BN, (K + bk - 1) / bk, bk);
+  const size_t smem = (size_t)g.stages * (2 * BM * bk * 4 + 2 * BN * bk * 4) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -539,7 +564,7 @@ int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long
   if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;
   int kchunk = (Kcap + ns - 1) / ns;
   kchunk = ((kchunk + BK - 1) / BK) * BK;
-  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, (long long)M * N, next_trace()};
+  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, BK, (long long)M * N, next_trace()};
   g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   g.stages = pick_stages(BN, kchunk / BK);
   const size_t smem = (size_t)g.stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;

@@ -276,6 +276,9 @@ int eagcn_get_gemm_mode(void);
  * the layout allows it (every fo_v a multiple of 4 and <= 512, 16-byte aligned buffers); the backward tile kernel
  * also applies the BatchNorm/ReLU/dropout backward on the fly, so eagcn_layer_backward_b then leaves work.dY
  * unwritten.  1: always the generic warp-per-row kernels (dY materialised).  Process-wide.               */
+/* k-block of the K-major tcgen05 products: 0 (default) = chosen per shape by the pipeline model, 16 = 64-byte rows
+ * (SWIZZLE_64B, up to 6 stages), 32 = 128-byte rows (SWIZZLE_128B).  Process-wide; for measurements.            */
+int eagcn_set_tc_bk(int bk);
 int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock stamps of the GEMM pipeline (see .cu) */
 int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);

@@ -11,14 +11,27 @@ def _cuda():
     return torch.device("cuda", 0)
 
 
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 16, 32])
 @pytest.mark.parametrize("Mcap,T,N,K", [
     (128, 128, 64, 32), (256, 200, 400, 24), (512, 511, 700, 400), (384, 300, 24, 400), (256, 129, 176, 40),
-    (1024, 1000, 1400, 700), (128, 1, 16, 8),
+    (1024, 1000, 1400, 700), (128, 1, 16, 8), (4864, 4853, 400, 700), (4864, 4853, 700, 400),
 ])
 def test_gemm_nt_vs_float64(engine, Mcap, T, N, K):
-    from eagcn_b200 import functional as EF
+    """engine 0: tcgen05 with the k-block the pipeline model picks; 16 / 32: tcgen05 forced to 64-byte (SWIZZLE_64B) /
+    128-byte (SWIZZLE_128B) k-blocks; 1: FFMA."""
+    from eagcn_b200 import functional as EF, _lib
     dev = _cuda()
+    if engine in (16, 32):
+        _lib.lib().eagcn_set_tc_bk(engine)
+        try:
+            _gemm_nt_case(EF, dev, 0, Mcap, T, N, K)
+        finally:
+            _lib.lib().eagcn_set_tc_bk(0)
+        return
+    _gemm_nt_case(EF, dev, engine, Mcap, T, N, K)
+
+
+def _gemm_nt_case(EF, dev, engine, Mcap, T, N, K):
     g = torch.Generator(device="cpu").manual_seed(Mcap + N + K)
     A = torch.randn(Mcap, K, generator=g).to(dev)
     B = torch.randn(N, K, generator=g).to(dev)

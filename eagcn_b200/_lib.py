@@ -128,6 +128,7 @@ _PROTOS = {
                               c_void_p, c_int64, c_int, c_void_p]),
     "eagcn_dropout_mask_flat": (c_int, [c_void_p, c_int64, c_double, c_int64, c_void_p, c_void_p]),
     "eagcn_launch_count": (c_int64, []),
+    "eagcn_spin": (c_int, [c_int64, c_void_p]),
     "eagcn_profile": (c_int, [c_int]),
     "eagcn_profile_report": (c_int64, [ctypes.c_char_p, c_int64]),
 }

@@ -99,6 +99,23 @@ extern "C" int eagcn_mm(const void* A, int64_t lda, int transA, const void* B, i
 #include <string>
 extern "C" int64_t eagcn_launch_count(void) { return eagcn::prof().launches; }
 
+// Diagnostic: keep the stream busy for ~`ns` nanoseconds (one thread polling globaltimer).  bench.py enqueues it ahead of
+// a profiled eager step so that the host runs ahead of the device: the CUDA events around each kernel then bracket the
+// kernel itself, not the host's launch latency.
+namespace eagcn {
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+}  // namespace eagcn
+extern "C" int eagcn_spin(int64_t ns, void* stream) {
+  if (ns < 0 || ns > 100000000) return EAGCN_E_ARG;
+  eagcn::spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)ns);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 // Pipeline trace of the tcgen05 GEMM (diagnostic): the next `max_launches` GEMM launches write the clock64 stamps of
 // CTA (0,0,0) into buf (device int64, EAGCN_GEMM_TRACE_STRIDE entries per launch): [0] k-blocks, [1] BN, [2] stages,
 // [3] mode, [4] start, [5] epilogue start, [6] epilogue end, then per k-block at 8+5*kb: TMA issue, tile landed,

@@ -314,6 +314,9 @@ int eagcn_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, void* 
 /* kernels launched by this library since load (bench.py: gpu_launches; under CUDA-graph replay the
  * count taken while capturing one step is the number of kernel nodes replayed per step)          */
 int64_t eagcn_launch_count(void);
+/* keeps `stream` busy for ~ns nanoseconds (<= 0.1 s): lets the host queue a whole eager step behind it, so that the
+ * per-kernel events below bracket kernels, not launch latency                                        */
+int eagcn_spin(int64_t ns, void* stream);
 /* opt-in per-kernel CUDA-event timing: enable(1) / disable(0), both clear what was recorded      */
 int eagcn_profile(int enable);
 /* writes {"kernel": [launches, total_ms], ...} into buf; returns bytes written, 0 if cap too small */

@@ -16,6 +16,6 @@ timeout -s KILL 200 python bench.py --gemm-trace --no-cpu --nbatches 2 > gpurun_
 # ncu: launch list of eager steps (3 warm-up + 2 profiled; aggregate offline), then a full capture of the large kernels
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --profile-only --steps 2 --warmup 3 --nbatches 2 > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout -s KILL 500 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|agg_bwd|agg_fwd|pack_fill|bn_apply|bn_bwd_partial" -s 40 -c 14 \
+timeout -s KILL 500 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|agg_bwd|agg_fwd|pack_fill|bn_stat_apply|bn_bwd_partial|mm_tile|bn_act" -s 60 -c 30 \
     -o gpurun_out/${TAG}_prof -f python bench.py --profile-only --steps 2 --warmup 3 --nbatches 2 > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | grep ${TAG}

@@ -419,6 +419,25 @@ __global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_tile_kernel(PlanDev p,
   int* s_j = reinterpret_cast<int*>(s_ds + cap);             // [cap]  neighbour row
   int* s_cr = s_j + cap;                                     // [cap]  code | row-in-tile << 8
   float* s_d = reinterpret_cast<float*>(s_cr + cap);         // [cap + kStatRows]  dots: rows first, then edges
+  // (row group, float4 channel) mapping of the dY staging and of the Q phase
+  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
+  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
+  // The thread's first kPreRows rows of g and Y are requested NOW: their DRAM latency then runs under the staging of
+  // the fold parameters / row pointers and the barrier below (Nsight: 30 % of the kernel's samples sat on these loads
+  // when they were issued two rows at a time after the barrier).
+  constexpr int kPreRows = 4;
+  float4 pg[kPreRows], py[kPreRows];
+#pragma unroll
+  for (int k = 0; k < kPreRows; ++k) {
+    const int r = rg + k * nrg;
+    if (rg < nrg && r < nrows) {
+      const size_t rowoff = (size_t)(t0 + r) * ld + off;
+      pg[k] = __ldg(reinterpret_cast<const float4*>(bn.G + rowoff) + c4);
+      py[k] = __ldg(reinterpret_cast<const float4*>(Y + rowoff) + c4);
+    } else {
+      pg[k] = make_float4(0.f, 0.f, 0.f, 0.f); py[k] = pg[k];
+    }
+  }
   // ---- stage: Z slab, BatchNorm fold parameters, row pointers ----
   slab_load(sZ, Z, t0, nrows, ld, off, fo, &s_bar);
   {
@@ -435,12 +454,23 @@ __global__ void __launch_bounds__(kAggThreads, 4) agg_bwd_tile_kernel(PlanDev p,
   if (tid < nrows) s_invR[tid] = iR[t0 + tid];
   __syncthreads();
   // ---- stage: dY slab; a thread keeps one float4 channel's fold parameters in registers and walks rows ----
-  const int nrg = __float2int_rz(__fdividef((float)kAggThreads + 0.5f, (float)nc4));
-  const int rg = __float2int_rz(__fdividef((float)tid + 0.5f, (float)nc4)), c4 = tid - rg * nc4;
   if (rg < nrg) {
     const float4 mu = sP[c4], is = sP[nc4 + c4], a = sP[2 * nc4 + c4], c1 = sP[3 * nc4 + c4], c2 = sP[4 * nc4 + c4];
+#pragma unroll
+    for (int k = 0; k < kPreRows; ++k) {
+      const int r = rg + k * nrg;
+      if (r < nrows) {
+        const float4 g = pg[k], y = py[k];
+        float4 o;
+        o.x = fmaf(a.x, g.x, -fmaf((y.x - mu.x) * is.x, c2.x, c1.x));
+        o.y = fmaf(a.y, g.y, -fmaf((y.y - mu.y) * is.y, c2.y, c1.y));
+        o.z = fmaf(a.z, g.z, -fmaf((y.z - mu.z) * is.z, c2.z, c1.z));
+        o.w = fmaf(a.w, g.w, -fmaf((y.w - mu.w) * is.w, c2.w, c1.w));
+        sG[r * nc4 + c4] = o;
+      }
+    }
 #pragma unroll 2
-    for (int r = rg; r < nrows; r += nrg) {
+    for (int r = rg + kPreRows * nrg; r < nrows; r += nrg) {
       const size_t rowoff = (size_t)(t0 + r) * ld + off;
       const float4 g = __ldg(reinterpret_cast<const float4*>(bn.G + rowoff) + c4);
       const float4 y = __ldg(reinterpret_cast<const float4*>(Y + rowoff) + c4);

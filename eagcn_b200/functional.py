@@ -8,6 +8,7 @@ one CUDA graph.
 from __future__ import annotations
 
 import ctypes
+import dataclasses
 import os
 from dataclasses import dataclass, field
 
@@ -402,6 +403,43 @@ class LayerPrep:
         if self.side:
             Overlap.join_fwd(self.dev)
             self.side = False
+
+
+def pad_layer_args(cfg: LayerConfig, H, params, buffers):
+    """Widths that are not multiples of 4 floats (HIV layer 2: five views of 250, row stride 1 250) cannot use the TMA /
+    tcgen05 GEMM (16-byte row alignment) nor the float4 aggregation and BatchNorm kernels.  This builds the equivalent
+    layer call on widths rounded up to 4: zero weight columns (and zero weight rows for padded input channels), zero bias,
+    gamma 1, beta 0, running statistics 0 / 1 -- a padded channel is the constant 0 through projection, aggregation,
+    BatchNorm (variance 0, finite inverse std), ReLU and dropout, so it neither changes the real channels nor produces
+    non-finite values.  Returns (cfg_p, H_p, params_p, buffers_p, finish); ``finish(X_p)`` cuts the real channels out of
+    the padded output (autograd routes the gradients of the padded parameters back through ``F.pad``) and copies the
+    updated running statistics into the module's buffers.  Pure tensor code: shared by the CUDA path and its CPU test."""
+    import torch.nn.functional as F
+    V = len(cfg.fo)
+    pad4 = lambda n: (int(n) + 3) & ~3
+    fin_p, fo_p = pad4(cfg.fin), tuple(pad4(f) for f in cfg.fo)
+    e = fin_p - cfg.fin
+    H_p = F.pad(H, (0, e)) if e else H
+    params_p, buffers_p = [], []
+    for v in range(V):
+        a, r, W, b, g, be = params[6 * v: 6 * v + 6]
+        rm, rv, nbt = buffers[3 * v: 3 * v + 3]
+        d = fo_p[v] - cfg.fo[v]
+        params_p += [a, r, F.pad(W, (0, d, 0, e)), F.pad(b, (0, d)), F.pad(g, (0, d), value=1.0), F.pad(be, (0, d))]
+        buffers_p += [F.pad(rm, (0, d)), F.pad(rv, (0, d), value=1.0), nbt]
+    cfg_p = dataclasses.replace(cfg, fin=fin_p, fo=fo_p, prep=None)
+
+    def finish(X_p):
+        outs, off = [], 0
+        for v in range(V):
+            outs.append(X_p[:, off: off + cfg.fo[v]])
+            off += fo_p[v]
+            if cfg.training:
+                with torch.no_grad():
+                    buffers[3 * v].copy_(buffers_p[3 * v][:cfg.fo[v]])
+                    buffers[3 * v + 1].copy_(buffers_p[3 * v + 1][:cfg.fo[v]])
+        return torch.cat(outs, 1)
+    return cfg_p, H_p, params_p, buffers_p, finish
 
 
 def graph_conv_layer(plan: GraphPlan, cfg: LayerConfig, H, params, buffers):

@@ -193,6 +193,11 @@ class GraphConv_Layer(nn.Module):
     """All bond relations of one layer (layers.py:262-325), CUDA path."""
 
     _plan_cache = None          # (key, weakref to adjs, plan): the 4 layers of a model share one plan
+    # True: a layer whose widths are not multiples of 4 floats (HIV layer 2: 5 x 250) runs on widths rounded up to 4
+    # (EF.pad_layer_args: zero-padded parameters, real channels cut out afterwards) and so stays on the tensor-core GEMM
+    # and the float4 kernels instead of the FFMA / scalar fallbacks.  The padding algebra is CPU-tested
+    # (tests/test_pad_widths.py); it is opt-in until the padded shapes have been timed on a B200.
+    pad_widths = False
 
     def __init__(self, node_feature_in, bond_feature_num, node_out_1, node_out_2, node_out_3, node_out_4,
                  node_out_5, dropout, structure, last=False, adj_size=0):
@@ -298,7 +303,11 @@ class GraphConv_Layer(nn.Module):
         if wsum:
             x = self._weighted_sum(plan, cfg, H, params, buffers, p_drop)
         else:
-            X = EF.graph_conv_layer(plan, cfg, H, params, buffers)
+            if self.pad_widths and (cfg.fin % 4 or any(f % 4 for f in cfg.fo)):
+                cfg_p, H_p, params_p, buffers_p, finish = EF.pad_layer_args(cfg, H, params, buffers)
+                X = finish(EF.graph_conv_layer(plan, cfg_p, H_p, params_p, buffers_p))
+            else:
+                X = EF.graph_conv_layer(plan, cfg, H, params, buffers)
             x = PackedRows(X, plan) if packed_io else EF.scatter_rows(plan, X)        # layers.py:313
 
         A_weight = None

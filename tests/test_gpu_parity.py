@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
 (libeagcn_sm100.so) via eagcn_b200; the checker is the oracle / the golden vectors produced by the
 unmodified reference.  Tolerance: fp32, max|d|/max|ref| <= 1e-5 (north_star); indexing bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -863,3 +865,15 @@ def test_fused_bn_forward_bit_identical():
         assert torch.equal(sd0[k], sd1[k]), k
     for k in g0:
         assert torch.equal(g0[k], g1[k]), k
+
+
+@pytest.mark.skipif(not os.environ.get("EAGCN_EXPERIMENTAL"), reason="opt-in path, not yet timed on a B200 (EAGCN_EXPERIMENTAL=1)")
+def test_padded_widths_hiv_config_vs_oracle():
+    """GraphConv_Layer.pad_widths: HIV widths (5 x 250 in layer 2: row stride 1 250 floats) on the padded layout --
+    tensor-core GEMM + float4 kernels instead of the FFMA / scalar fallbacks; same parity bar."""
+    from eagcn_b200 import layers as EL
+    EL.GraphConv_Layer.pad_widths = True
+    try:
+        test_baseline_configs_forward_vs_oracle("config4 hiv widths 2-layer (padded)", "hiv", 12, 2, True)
+    finally:
+        EL.GraphConv_Layer.pad_widths = False

@@ -127,6 +127,59 @@ def model_case(case, B, seed, dataset, kb, sgc1, sgc2, den, nclass, training=Tru
     save(case, batch, sd0, extra)
 
 
+def stack_case(case, B, seed, dataset, kb, widths, den, nclass, training=True):
+    """BASELINE.json's "2-layer" / "3-layer" configurations: the reference hard-codes four layers (models.py:50-61), so
+    the golden is the reference's own GraphConv_Layer stacked ``len(widths)`` times, followed by the head of
+    models.py:108-120 built from the reference's Dense and torch's BatchNorm1d under the reference's attribute names."""
+    L, _, _ = ref_loader.load()
+    import torch.nn as nn
+    import torch.nn.functional as F
+    batch = make_batch(B, dataset=dataset, seed=seed, kb=kb)
+
+    class Stack(nn.Module):
+        def __init__(self):
+            super().__init__()
+            fin = 24
+            for l, w in enumerate(widths):
+                setattr(self, f"layer{l + 1}", L.GraphConv_Layer(fin, kb, *w, dropout=0.0, structure="Concate"))
+                fin = sum(w)
+            self.den1, self.den2, self.den3 = L.Dense(fin, den[0]), L.Dense(den[0], den[1]), L.Dense(den[1], nclass)
+            self.Graph_BN, self.bn_den1, self.bn_den2 = nn.BatchNorm1d(fin), nn.BatchNorm1d(den[0]), nn.BatchNorm1d(den[1])
+
+        def forward(self, adjs, afms, *rels):
+            x2 = afms
+            for l in range(len(widths)):                                   # models.py:97-100
+                x2, _ = getattr(self, f"layer{l + 1}")(adjs, x2, *rels)
+            x = self.Graph_BN(torch.sum(x2, 1))                            # models.py:108,112
+            x = F.relu(self.bn_den1(self.den1(x)))                         # models.py:114-115 (dropout 0)
+            x = self.den2(x)
+            g = x
+            x = self.den3(F.relu(self.bn_den2(x)))                         # models.py:119-120
+            return x, x2, g
+
+    model = Stack()
+    randomise(model, seed)
+    for name, p in model.named_parameters():     # head: keep activations O(1)
+        if name.startswith("den"):
+            p.data = p.data * 3.0
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    model.train(training)
+    ins = [t(a) for a in batch.dense()]
+    out, atom_rep, graph_rep = model(*ins)
+    g = torch.Generator().manual_seed(seed + 7)
+    R = torch.randn(out.shape, generator=g)
+    (out * R).sum().backward()
+    extra = {"out.y": out, "out.atom_rep": atom_rep, "out.graph_rep": graph_rep, "cot.y": R,
+             "meta.training": int(training), "meta.n_layers": len(widths)}
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            extra["grad." + name] = p.grad
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            extra["post." + k] = v
+    save(case, batch, sd0, extra)
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference (build container)"
     torch.set_num_threads(1)
@@ -147,6 +200,11 @@ def main():
     model_case("model_wsum", B=5, seed=23, dataset="freesolv", kb=5, sgc1=1, sgc2=2, den=(8, 4), nclass=2,
                structure="Weighted_sum")
     model_case("model_pool", B=5, seed=24, dataset="freesolv", kb=5, sgc1=3, sgc2=4, den=(8, 4), nclass=2, molfp="pool")
+    if not only or "stack_lipo3" in only:      # config 3: Lipophilicity, 3 layers + regression head (widths / 10)
+        stack_case("stack_lipo3", B=6, seed=31, dataset="lipo", kb=18, widths=[(6,) * 5, (10,) * 5, (20,) * 5],
+                   den=(12, 6), nclass=1)
+    if not only or "stack_hiv2" in only:       # config 4: HIV, 2 layers, widths that are not multiples of 4 (250 -> 25)
+        stack_case("stack_hiv2", B=6, seed=32, dataset="hiv", kb=30, widths=[(10,) * 5, (25,) * 5], den=(16, 8), nclass=1)
 
 
 if __name__ == "__main__":

@@ -93,6 +93,33 @@ def test_model_vs_golden(case):
         assert float((got - ref).abs().max()) / denom <= 2e-4, k
 
 
+@pytest.mark.parametrize("case", golden_cases("stack_"))
+def test_stack_vs_golden(case):
+    """BASELINE.json's 3-layer (Lipophilicity, regression head) and 2-layer (HIV widths, not multiples of 4)
+    configurations: the reference's GraphConv_Layer stacked 3 / 2 deep + the head of models.py:108-120."""
+    g = Golden(case)
+    sd = O.clone_sd(g.sd, requires_grad=True)
+    adj, afm, *rels = g.dense()
+    codes = [O.codes_from_onehot(adj, r) for r in rels]
+    n_layers = int(g.meta["n_layers"])
+    h, _ = O.stack_forward(sd, adj, afm, codes, n_layers, True)
+    y, grep = O.head_forward(sd, h, torch.from_numpy(g.batch.sizes), True)
+    assert rel_err(h, g.out["atom_rep"]) <= TOL
+    assert rel_err(y, g.out["y"]) <= 2 * TOL
+    assert rel_err(grep, g.out["graph_rep"]) <= 2 * TOL
+    (y * g.cot["y"]).sum().backward()
+    scale = max(float(v.abs().max()) for v in g.grad.values())
+    for k, ref in g.grad.items():
+        got = sd[k].grad
+        assert got is not None, k
+        # 2e-4 of the tensor's own largest gradient, but never tighter than 5e-6 of the model's gradient scale (fp32
+        # reassociation noise through 2-3 stacked train-mode BatchNorms; d bias through a BatchNorm is noise around 0)
+        bound = max(2e-4 * float(ref.abs().max()), 5e-6 * scale)
+        if k.endswith("graph_conv.bias"):
+            bound = 2e-4 * scale
+        assert float((got - ref).abs().max()) <= bound, k
+
+
 def test_non_onehot_rejected():
     g = Golden("layer_train")
     adj, afm, *rels = g.dense()

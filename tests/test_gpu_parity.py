@@ -877,3 +877,41 @@ def test_padded_widths_hiv_config_vs_oracle():
         test_baseline_configs_forward_vs_oracle("config4 hiv widths 2-layer (padded)", "hiv", 12, 2, True)
     finally:
         EL.GraphConv_Layer.pad_widths = False
+
+
+@pytest.mark.skipif(not os.environ.get("EAGCN_EXPERIMENTAL"), reason="fixtures added after the round's last GPU visit (EAGCN_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("case", golden_cases("stack_"))
+@pytest.mark.parametrize("pad", [False, True])
+def test_stack_vs_golden(case, pad):
+    """BASELINE.json configs 3 / 4 against goldens from the reference itself: GraphConv_Layer stacked 3 / 2 deep +
+    the head of models.py:108-120 (EAGCNStack), forward and every gradient; ``pad``: widths that are not multiples of 4
+    through the padded layout (GraphConv_Layer.pad_widths)."""
+    from eagcn_b200 import layers as EL, models as EM
+    dev = _cuda()
+    g = Golden(case)
+    n_layers = int(g.meta["n_layers"])
+    widths = [tuple(g.sd[f"layer{l + 1}.block{v + 1}.graph_conv.weight"].shape[1] for v in range(5)) for l in range(n_layers)]
+    kb = g.sd["layer1.block1.att.weight"].shape[1]
+    d1, d2, nc = g.sd["den1.weight"].shape[1], g.sd["den2.weight"].shape[1], g.sd["den3.weight"].shape[1]
+    EL.GraphConv_Layer.pad_widths = pad
+    try:
+        model = EM.EAGCNStack(kb, 24, widths, d1, d2, nc, dropout=0.0).to(dev)
+        model.load_state_dict(g.sd, strict=True)
+        model.train()
+        ins = _to(dev, g.dense())
+        y, atom_rep, graph_rep = model(*ins, torch.from_numpy(g.batch.sizes).to(dev))
+        assert rel_err(atom_rep.materialize(), g.out["atom_rep"]) <= n_layers * TOL
+        assert rel_err(y.cpu(), g.out["y"]) <= 5 * TOL
+        assert rel_err(graph_rep.cpu(), g.out["graph_rep"]) <= 5 * TOL
+        (y * g.cot["y"].to(dev)).sum().backward()
+        scale = max(float(v.abs().max()) for v in g.grad.values())
+        named = dict(model.named_parameters())
+        for k, ref in g.grad.items():
+            got = named[k].grad
+            assert got is not None, k
+            bound = max(2e-4 * float(ref.abs().max()), 2e-5 * scale)
+            if k.endswith("graph_conv.bias"):
+                bound = 2e-4 * scale
+            assert float((got.cpu() - ref).abs().max()) <= bound, k
+    finally:
+        EL.GraphConv_Layer.pad_widths = False

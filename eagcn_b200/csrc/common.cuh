@@ -120,9 +120,14 @@ struct Philox {
   }
 };
 
-// keep decision for element idx (one philox call serves 4 consecutive elements)
+// keep decision for element idx (one philox call serves 4 consecutive elements).
+// Counter layout: low 64 bits = element group idx/4, high 64 bits = call-site stream id + generator offset.  The offset
+// advances by 2^20 per dropout call site and forward pass (eagcn_rng_fork) and stream ids are < 2^20, so the high word
+// is unique per (call site, pass) and the low word never overlaps it: masks of different passes / sites are disjoint
+// Philox streams for ANY tensor size (the round-1 layout added the offset to the low word, which made the masks of
+// consecutive passes shifted copies of each other beyond 2^22 elements per site).
 __device__ __forceinline__ bool dropout_keep(const Philox& ph, uint64_t offset, uint64_t stream, uint64_t idx, float p) {
-  uint4 r = ph((idx >> 2) + offset, stream);
+  uint4 r = ph(idx >> 2, stream + offset);
   uint32_t x = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
   // uniform in [0,1): keep iff u >= p
   return (float)(x >> 8) * (1.0f / 16777216.0f) >= p;
@@ -131,7 +136,7 @@ __device__ __forceinline__ bool dropout_keep(const Philox& ph, uint64_t offset, 
 // vector form: keep flags of the 4 consecutive elements idx4 .. idx4+3 (idx4 % 4 == 0), one philox call
 __device__ __forceinline__ void dropout_keep4(const Philox& ph, uint64_t offset, uint64_t stream, uint64_t idx4, float p,
                                               bool (&keep)[4]) {
-  const uint4 r = ph((idx4 >> 2) + offset, stream);
+  const uint4 r = ph(idx4 >> 2, stream + offset);
   keep[0] = (float)(r.x >> 8) * (1.0f / 16777216.0f) >= p;
   keep[1] = (float)(r.y >> 8) * (1.0f / 16777216.0f) >= p;
   keep[2] = (float)(r.z >> 8) * (1.0f / 16777216.0f) >= p;

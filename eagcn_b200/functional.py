@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import HeadStruct, LayerStruct, WorkStruct, check, lib, ptr
+from ._lib import EagcnError, HeadStruct, LayerStruct, WorkStruct, check, lib, ptr
 from .plan import GraphPlan, _stream
 
 _F32 = torch.float32
@@ -110,9 +110,23 @@ class Overlap:
 
     @staticmethod
     def fresh(params):
-        """True when autograd will adopt the returned gradient tensors as-is (no accumulate / copy kernel)."""
-        return Overlap.defer_param_grads and all(
-            p is None or not p.requires_grad or (p.is_leaf and p.grad is None and not p._backward_hooks) for p in params)
+        """True when autograd will adopt the returned gradient tensors as-is, i.e. when NOTHING launches a kernel on
+        them before the end of the backward pass: every parameter is a leaf without a gradient yet (AccumulateGrad
+        steals the tensor), carries no tensor hooks and no post-accumulate-grad hooks (optimizer-in-backward, FSDP),
+        and the backward pass is not itself being recorded (``create_graph=True`` keeps grad mode on and makes
+        AccumulateGrad clone).  Hooks on the AccumulateGrad NODES (torch DDP's bucket hooks) cannot be seen from here:
+        wrap the model in DDP only with ``Overlap.defer_param_grads = False`` -- the join then precedes the layer's
+        return (eagcn_b200.parallel's own FlatGradBucket reduces after backward() and needs nothing)."""
+        if not Overlap.defer_param_grads or torch.is_grad_enabled():
+            return False
+        for p in params:
+            if p is None or not p.requires_grad:
+                continue
+            if not p.is_leaf or p.grad is not None or p._backward_hooks:
+                return False
+            if getattr(p, "_post_accumulate_grad_hooks", None):
+                return False
+        return True
 
 
 @dataclass
@@ -223,6 +237,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
     def forward(ctx, plan, cfg, buffers, H, *params):
         L = lib()
         dev = plan.device
+        Overlap.join_pending(dev)           # a backward pass that aborted after forking: join before anything else
         if H.device != dev or H.dtype != _F32 or H.dim() != 2 or H.shape[0] != plan.t_cap or H.shape[1] != cfg.fin:
             raise ValueError(f"packed input must be float32 [{plan.t_cap}, {cfg.fin}] on {dev}, "
                              f"got {tuple(H.shape)} {H.dtype} on {H.device}")
@@ -717,7 +732,22 @@ def _ticket_buf(dev, lane, n):
     return t
 
 
-def _mm_tile(A, transA, B, transB, stream=None):
+def _mm_tile_bufs(A, transA, B, transB, lane):
+    """Output, split-K workspace and ticket array of one ``_mm_tile`` call, allocated (and, for a new ticket array,
+    zero-filled) on the CURRENT stream: a side-stream call gets them BEFORE its fork point, so the fork orders the
+    allocation / zero-fill ahead of the side-stream kernel."""
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    L = lib()
+    C = torch.empty(M, N, dtype=_F32, device=A.device)
+    nbytes = int(L.eagcn_mm_tile_workspace_bytes(M, N, K))
+    ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
+    tk = _ticket_buf(A.device, lane, int(L.eagcn_mm_tile_tickets(M, N))) if nbytes else None
+    return C, ws, tk, nbytes
+
+
+def _mm_tile(A, transA, B, transB, stream=None, bufs=None):
     """op(A) @ op(B) on the small-matrix tile kernel (split-K combined inside the launch; bit-reproducible)."""
     M = A.shape[1] if transA else A.shape[0]
     K = A.shape[0] if transA else A.shape[1]
@@ -725,10 +755,7 @@ def _mm_tile(A, transA, B, transB, stream=None):
     if (B.shape[1] if transB else B.shape[0]) != K:
         raise ValueError("mm: inner dimensions differ")
     L = lib()
-    C = torch.empty(M, N, dtype=_F32, device=A.device)
-    nbytes = int(L.eagcn_mm_tile_workspace_bytes(M, N, K))
-    ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
-    tk = _ticket_buf(A.device, 0 if stream is None else 1, int(L.eagcn_mm_tile_tickets(M, N))) if nbytes else None
+    C, ws, tk, nbytes = bufs if bufs is not None else _mm_tile_bufs(A, transA, B, transB, 0 if stream is None else 1)
     st = _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
     check(L.eagcn_mm_tile(ptr(A), A.shape[1], int(transA), ptr(B), B.shape[1], int(transB), ptr(C), M, N, K,
                           ptr(ws), nbytes, ptr(tk), st), "eagcn_mm_tile")
@@ -762,13 +789,16 @@ class _DenseMmFn(torch.autograd.Function):
             return dx, dW, None
         dx = dW = None
         if need_dw and need_dx and Overlap.enabled:
+            # every buffer the side-stream product touches exists (tickets zero-filled) before the branch point
+            side_bufs = _mm_tile_bufs(x, True, dy, False, lane=1)
             forked = Overlap.fork_point(dy.device)
-            dx = _mm_tile(dy, False, W, True)[0]          # first: the rest of the backward pass waits for it
+            dx, ws_dx = _mm_tile(dy, False, W, True)      # first: the rest of the backward pass waits for it
             side = Overlap.fork_from(dy.device, forked)
-            dW, ws = _mm_tile(x, True, dy, False, stream=side)
+            dW, ws = _mm_tile(x, True, dy, False, stream=side, bufs=side_bufs)
             if Overlap.fresh((ctx.w_ref,)):
-                # dW itself is NOT kept: an extra reference would make autograd copy it instead of adopting it
-                Overlap.defer_join(dy.device, (x, dy, ws))
+                # dW itself is NOT kept: an extra reference would make autograd copy it instead of adopting it.
+                # ws_dx stays referenced too: freed early, the allocator could hand it to a side-stream kernel
+                Overlap.defer_join(dy.device, (x, dy, ws, ws_dx))
             else:
                 Overlap.join(dy.device)
             return dx, dW, None

@@ -294,8 +294,12 @@ class GraphConv_Layer(nn.Module):
         packed_io = isinstance(afms, PackedRows)
         H = afms.rows if packed_io else EF.gather_rows(plan, afms)
         p_drop = float(self.block1.dropout)
+        bn1 = self.block1.batch_norm.bn                    # AFM_BatchNorm(eps=1e-5, momentum=0.1), layers.py:399-401
+        if any(b.batch_norm.bn.eps != bn1.eps or b.batch_norm.bn.momentum != bn1.momentum for b in self.blocks):
+            raise EagcnError("the five views of a GraphConv_Layer must share BatchNorm eps / momentum")
         cfg = EF.LayerConfig(fin=self.node_feature_in, fo=tuple(b.node_feature_out for b in self.blocks),
                              training=self.training, p_drop=p_drop, rng_stream=self.rng_stream,
+                             eps=float(bn1.eps), momentum=float(bn1.momentum if bn1.momentum is not None else 0.1),
                              stat_allreduce=self.stat_allreduce, want_pad=wsum, prep=prep)
         if wsum and self.stat_allreduce is not None:
             raise EagcnError("structure='Weighted_sum' with global-batch BatchNorm is not implemented")

@@ -150,14 +150,16 @@ def layer_forward(sd, pre, adj, afm, codes, training, p=0.0, keeps=None, structu
 
 
 def stack_forward(sd, adj, afm, codes, n_layers, training, p=0.0, keeps=None, structure="Concate",
-                  last_flags=None):
-    """EAGCN.forward chaining (models.py:96-100) for ``n_layers`` GraphConv_Layers ``layer1..``."""
+                  last_flags=None, relu_masks=None):
+    """EAGCN.forward chaining (models.py:96-100) for ``n_layers`` GraphConv_Layers ``layer1..``.
+    keeps / relu_masks: per layer, per view (see block_forward)."""
     h = afm
     outs = []
     for l in range(n_layers):
         last = bool(last_flags[l]) if last_flags is not None else False
         o = layer_forward(sd, f"layer{l + 1}.", adj, h, codes, training, p,
-                          None if keeps is None else keeps[l], structure, last)
+                          None if keeps is None else keeps[l], structure, last,
+                          relu_masks=None if relu_masks is None else relu_masks[l])
         outs.append(o)
         h = o["x"]
     return h, outs

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference (Luckick/EAGCN) for checking.
 
 Only tests/, tests/golden/make_golden.py, __graft_entry__ and bench.py's cpu/reference legs
-may import this.  /root/reference exists in the build container only (never on the GPU box);
-``available()`` says whether it can be used.
+may import this.  /root/reference exists in the build container only (never on the GPU box); there the same
+four modules are found in the git-ignored copy ``oracle/_ref/`` that ``tools/make_oracle_ref.sh`` produces in the
+build container (it travels with the gpurun snapshot, never with git).  ``available()`` says whether either exists.
 
 reference eagcn_pytorch/models.py:4 does ``from utils import *`` and utils.py:5,19-21,818 /
 neural_fp.py:4-11 import rdkit + matplotlib at module top although the model code never
@@ -14,7 +15,18 @@ import os
 import sys
 import types
 
-REF_DIR = os.environ.get("EAGCN_REFERENCE_DIR", "/root/reference/eagcn_pytorch")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("EAGCN_REFERENCE_DIR"), "/root/reference/eagcn_pytorch", os.path.join(_HERE, "_ref")]
+
+
+def _pick_dir():
+    for d in _CANDIDATES:
+        if d and os.path.isfile(os.path.join(d, "layers.py")):
+            return d
+    return _CANDIDATES[1]
+
+
+REF_DIR = _pick_dir()
 
 _STUBS = [
     "rdkit", "rdkit.Chem", "rdkit.Chem.AllChem", "rdkit.Chem.Descriptors", "rdkit.Chem.rdMolDescriptors",
@@ -38,6 +50,30 @@ class _Inert(types.ModuleType):
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_DIR, "layers.py"))
+
+
+def source() -> str:
+    """'reference' (/root/reference itself), '_ref' (the shipped copy oracle/_ref) or 'absent'."""
+    if not available():
+        return "absent"
+    return "_ref" if os.path.abspath(REF_DIR) == os.path.join(_HERE, "_ref") else "reference"
+
+
+class cpu_only:
+    """The reference picks its device from ``torch.cuda.is_available()`` at import AND at construction time
+    (layers.py:10-14, :67-71, :275).  Inside this context it sees no GPU, so modules loaded / built here are the
+    reference's CPU path even on the GPU box."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.is_available = self._orig
+        return False
 
 
 def _install_stubs():

@@ -867,7 +867,6 @@ def test_fused_bn_forward_bit_identical():
         assert torch.equal(g0[k], g1[k]), k
 
 
-@pytest.mark.skipif(not os.environ.get("EAGCN_EXPERIMENTAL"), reason="opt-in path, not yet timed on a B200 (EAGCN_EXPERIMENTAL=1)")
 def test_padded_widths_hiv_config_vs_oracle():
     """GraphConv_Layer.pad_widths: HIV widths (5 x 250 in layer 2: row stride 1 250 floats) on the padded layout --
     tensor-core GEMM + float4 kernels instead of the FFMA / scalar fallbacks; same parity bar."""
@@ -879,7 +878,6 @@ def test_padded_widths_hiv_config_vs_oracle():
         EL.GraphConv_Layer.pad_widths = False
 
 
-@pytest.mark.skipif(not os.environ.get("EAGCN_EXPERIMENTAL"), reason="fixtures added after the round's last GPU visit (EAGCN_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("case", golden_cases("stack_"))
 @pytest.mark.parametrize("pad", [False, True])
 def test_stack_vs_golden(case, pad):
@@ -915,3 +913,122 @@ def test_stack_vs_golden(case, pad):
             assert float((got.cpu() - ref).abs().max()) <= bound, k
     finally:
         EL.GraphConv_Layer.pad_widths = False
+
+
+# ------------------------------------------------------------------ the BENCHMARKED configuration vs the oracle
+def test_bench_config_vs_oracle():
+    """bench.py's own step -- Tox21 B = 256, 24 -> 400 -> 700 + head 256/64/12, TRAIN mode, dropout 0.3, tcgen05 engine,
+    side-stream branches on, captured into a CUDA graph and REPLAYED -- against the oracle on the same batch: the
+    dropout keep masks of the three sites are exported from the library's Philox stream, the ReLU decisions are taken
+    from the implementation under test (and bounded to the kink), everything else is the oracle's own arithmetic.
+    Outputs <= 1e-5 per layer, every gradient <= 5e-5 of the gradient scale."""
+    import bench
+    from eagcn_b200 import functional as EF
+    from eagcn_b200.plan import GraphPlan
+    dev = _cuda()
+    assert EF.Overlap.enabled
+    model = bench.build_model(dev)
+    hb, T, E = bench.host_batch(seed=3)
+    dense = [torch.from_numpy(a) for a in hb.dense()]
+    ins = _to(dev, dense)
+    size = torch.from_numpy(hb.sizes).to(dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    p_drop, widths, nl = bench.P_DROP, bench.WIDTHS, len(bench.WIDTHS)
+    rec = {}
+    orig_bn_act = EF.bn_act
+
+    def rec_bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):
+        y = orig_bn_act(x, bn, training, relu=relu, p_drop=p_drop, rng_stream=rng_stream)
+        rec.setdefault("bn_act", []).append(y)
+        return y
+
+    def step():
+        for p in params:
+            p.grad = None
+        rec.clear()
+        model.prefetch_params()
+        plan = GraphPlan.build(ins[0], ins[2:], t_cap=T, e_cap=E)
+        rec["plan"] = plan
+        hooks = [l.register_forward_hook(lambda m, i, o, k=k: rec.__setitem__(f"x{k}", o[0].rows)) for k, l in
+                 enumerate(model.conv_layers)]
+        try:
+            out, atom, grep = model(plan, ins[1], size=size)
+        finally:
+            for h in hooks:
+                h.remove()
+        out.sum().backward()
+        rec["out"], rec["grep"] = out, grep
+        return out
+
+    work = torch.cuda.Stream()
+    work.wait_stream(torch.cuda.current_stream())
+    EF.bn_act = rec_bn_act
+    try:
+        with torch.cuda.stream(work):
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            rng = EF.RngState.get(dev)
+            EF.manual_seed(4242, dev)
+            rng_before = rng.state.clone()
+            g.replay()
+            g.replay()                       # second replay: same static buffers, the generator has moved on
+            rng_used = rng_before.clone(); rng_used[1] += (nl + 1) << 20
+            torch.cuda.synchronize()
+    finally:
+        EF.bn_act = orig_bn_act
+    plan = rec["plan"].check()
+    inc = 1 << 20
+    snaps = [rng_used + torch.tensor([0, i * inc], device=dev) for i in range(nl + 1)]     # prefork: site i = offset + i*inc
+    keeps, relus = [], []
+    for l in range(nl):
+        C = sum(widths[l])
+        cfg = EF.LayerConfig(fin=0, fo=widths[l], training=True, p_drop=p_drop, rng_stream=l)
+        keep = plan.scatter(EF.dropout_keep_mask(plan, cfg, C, snaps[l]).float()).cpu()
+        xl = plan.scatter(rec[f"x{l}"].detach()).cpu()
+        assert abs(float(keep.sum()) / (T * C) - (1 - p_drop)) < 0.01
+        assert float((xl * (1 - keep)).abs().max()) == 0.0                  # dropped elements are exact zeros
+        kv, rv, off = [], [], 0
+        for w in widths[l]:
+            kv.append(keep[:, :, off:off + w]); rv.append((xl[:, :, off:off + w] > 0).float() + (1 - keep[:, :, off:off + w]))
+            off += w
+        keeps.append(kv); relus.append(rv)
+    D1 = bench.DEN[0]
+    keep_h = EF.dropout_keep_mask_flat(snaps[nl], 1000, p_drop, hb.B * D1).view(hb.B, D1).float().cpu()
+    a_gbn, a1, a2 = [t.detach().cpu() for t in rec["bn_act"]]
+    relu_h = ((a1 > 0).float() + (1 - keep_h), (a2 > 0).float())
+    sd = O.clone_sd(model.state_dict(), requires_grad=True)
+    for k, t in sd.items():
+        if "running" in k or "num_batches" in k:
+            t.requires_grad_(False) if t.is_floating_point() else None
+    codes = [O.codes_from_onehot(dense[0], r) for r in dense[2:]]
+    h, outs = O.stack_forward(sd, dense[0], dense[1], codes, nl, True, p=p_drop, keeps=keeps, relu_masks=relus)
+    y_ref, g_ref = O.head_forward(sd, h, torch.from_numpy(hb.sizes), True, p=p_drop, keep=keep_h, relu_masks=relu_h)
+    # ReLU decisions of the implementation differ from the oracle's own only at the kink
+    m = dense[0].max(2).values.unsqueeze(2)
+    for l in range(nl):
+        for v, Zv in enumerate(outs[l]["Z"]):
+            dis = ((Zv.detach() > 0).float() != relus[l][v].clamp(max=1)) & (m > 0) & (keeps[l][v] > 0)
+            if bool(dis.any()):
+                assert float(Zv.detach().abs()[dis].max()) <= 1e-4 * float(Zv.detach().abs().max())
+                assert int(dis.sum()) <= 1e-5 * dis.numel() + 8
+    for l in range(nl):
+        assert rel_err(plan.scatter(rec[f"x{l}"].detach()).cpu(), outs[l]["x"]) <= (l + 1) * TOL, f"layer {l + 1}"
+    assert rel_err(rec["grep"].cpu(), g_ref) <= 3 * TOL
+    assert rel_err(rec["out"].cpu(), y_ref) <= 3 * TOL
+    y_ref.sum().backward()
+    named = dict(model.named_parameters())
+    scale = max(float(t.grad.abs().max()) for t in sd.values() if t.grad is not None)
+    worst = 0.0
+    for k, t in sd.items():
+        if t.grad is None:
+            continue
+        got = named[k].grad
+        assert got is not None, k
+        err = float((got.cpu() - t.grad).abs().max()) / scale
+        worst = max(worst, err)
+        assert err <= 5e-5, (k, err)
+    print(f"[bench-config parity] worst gradient error {worst:.2e} of scale")

@@ -1,26 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- molecules/sec of the EAGCN forward+backward hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config tox21|lipo3|hiv2|sweep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], named in ``config.workload``): Tox21-shaped synthetic batches
+Headline workload (BASELINE.json configs[1], named in ``config.workload``): Tox21-shaped synthetic batches
 (sizes drawn from the Tox21 heavy-atom histogram, Kb = 30, 5 views), batch 256 per GPU, 2 GraphConv_Layers
 24 -> 400 -> 700 + sum read-out + the reference's dense head (256 / 64 / 12), training mode, dropout 0.3,
-forward + backward of ``out.sum()``.  A "step" = one such pass over one batch, including
-the per-batch graph-plan packing.  Weak scaling: every rank processes its own 256-molecule batches; for
-N > 1 the flat gradient buffer is all-reduced (NCCL) inside the timed step.
+forward + backward of ``out.sum()``.  A "step" = one such pass over one batch, including the per-batch graph-plan
+packing.  Weak scaling: every rank processes its own 256-molecule batches; for N > 1 the flat gradient buffer is
+all-reduced (NCCL) inside the timed step.
 
-  value      whole-job molecules/s, inputs (the dense fp32 tensors the reference's collate produces)
-             already resident in HBM; each step is one CUDA-graph replay; NB distinct batches are rotated
-             so the inputs touched between two uses of the same batch exceed L2 (config.l2).
-  e2e        same metric through the public module call with HOST (pinned) buffers: H2D of that step's
-             inputs + the step + D2H of the outputs inside the timed region.  ``e2e`` uses the reference-
-             facing dense layout; ``e2e_packed`` the uint8 edge-code layout of the packed data boundary.
-  roofline   dominant kernel of the step (per-kernel CUDA-event timing inside this run).
-  cpu_baseline  the oracle's reference-cost form (same ATen op sequence as the reference) on the host cores.
+  value        whole-job molecules/s, inputs (the dense fp32 tensors the reference's collate produces) already
+               resident in HBM; each step is one CUDA-graph replay; NB distinct batches are rotated so the inputs
+               touched between two uses of the same batch exceed L2 (config.l2).  Median of ``--passes`` timed passes
+               of ``--steps`` steps each.
+  e2e          same metric through the public module call with HOST (pinned) buffers: H2D of that step's inputs +
+               the step + D2H of the outputs inside the timed region.  ``e2e`` uses the reference-facing dense
+               layout; ``e2e_packed`` the uint8 edge-code layout of the packed data boundary.
+  roofline     dominant kernel of the step (per-kernel CUDA-event timing inside this run).
+  cpu_baseline the reference's CPU path on the host cores: the reference's OWN classes when its modules are present
+               (/root/reference in the build container, the shipped copy oracle/_ref on the GPU box: kind
+               "reference"), else the oracle's op-for-op port (kind "port").
+  configs      (N = 1) the other single-GPU BASELINE.json configurations -- Lipophilicity B = 512 3-layer + regression
+               head, HIV 256 per GPU 2-layer -- value + dominant-kernel roofline each.
 
---impl reference: times that CPU path alone (rank 0 only) and prints the same JSON shape.
+--impl reference: times that CPU path alone (rank 0 only) and prints the same JSON shape, identical ``config``.
+--config sweep: the synthetic N x K x B sweep (BASELINE.json configs[4]) -> profiles/r02_sweep.json.
 """
 import argparse
 import ctypes
@@ -38,13 +44,26 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "tox21_b256_2layer_5view_fwd_bwd"
-DATASET, BATCH, KB = "tox21", 256, 30
-WIDTHS = [(80,) * 5, (140,) * 5]            # train.py:62-63 (tox21): 24 -> 400 -> 700
-DEN = (256, 64)
-NCLASS = 12
+# BASELINE.json configs -> shapes (widths from train.py:61-114)
+WORKLOADS = {
+    "tox21": dict(name="tox21_b256_2layer_5view_fwd_bwd", dataset="tox21", batch=256, kb=30,
+                  widths=[(80,) * 5, (140,) * 5], den=(256, 64), nclass=12),                    # train.py:62-63
+    "lipo3": dict(name="lipo_b512_3layer_5view_reghead_fwd_bwd", dataset="lipo", batch=512, kb=18,
+                  widths=[(60,) * 5, (100,) * 5, (200,) * 5], den=(128, 64), nclass=1),         # train.py:88-89
+    "hiv2": dict(name="hiv_b256pergpu_2layer_5view_fwd_bwd", dataset="hiv", batch=256, kb=30,
+                 widths=[(100,) * 5, (250,) * 5], den=(512, 128), nclass=1),                    # train.py:70-71
+}
 P_DROP = 0.3                                 # train.py:48
 METRIC = "molecules/sec EAGCN fwd+bwd (Tox21 shape, 5 views)"
+
+# module-level aliases of the headline workload (tests import these)
+_H = WORKLOADS["tox21"]
+WORKLOAD, DATASET, BATCH, KB = _H["name"], _H["dataset"], _H["batch"], _H["kb"]
+WIDTHS, DEN, NCLASS = _H["widths"], _H["den"], _H["nclass"]
+
+
+def widths_str(wl):
+    return "->".join(["24"] + [str(sum(w)) for w in wl["widths"]])
 
 
 def peaks():
@@ -69,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -106,20 +125,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def host_batch(seed):
+def host_batch(seed, wl=None):
     from eagcn_b200.data import make_batch
-    b = make_batch(BATCH, DATASET, seed=seed, kb=KB)
+    wl = wl or _H
+    b = make_batch(wl["batch"], wl["dataset"], seed=seed, kb=wl["kb"])
     T = int((b.adj.sum(2) > 0).sum())
     E = int(b.adj.sum())
     return b, T, E
 
 
-def build_model(dev):
-    from eagcn_b200 import models as EM
-    torch.manual_seed(0)
-    m = EM.EAGCNStack(KB, 24, WIDTHS, DEN[0], DEN[1], NCLASS, dropout=P_DROP).to(dev)
-    # utils.weights_init (utils.py:702-708) as train.py:302 applies it
-    g = torch.Generator().manual_seed(0)
+def workload_config(wl, world, nb, n_pad_mean, rows_mean, dense_mb):
+    """The workload description.  Both arms (--impl b200 / reference) print EXACTLY this dict: same keys, same values
+    (the batches are generated from the same seeds), so the driver's same_config test compares like with like.
+    Everything about HOW this arm runs the workload lives under ``impl_detail`` instead."""
+    return {"workload": wl["name"], "dataset_shape": wl["dataset"], "batch_per_gpu": wl["batch"],
+            "global_batch": wl["batch"] * world, "views": 5, "kb": wl["kb"], "widths": widths_str(wl),
+            "head": "/".join(str(x) for x in wl["den"] + (wl["nclass"],)), "dropout": P_DROP, "mode": "train fwd+bwd",
+            "bn_sync": "local", "parallelism": f"dp{world}",
+            "l2": f"{nb} distinct input batches rotated ({nb * dense_mb:.0f} MB of dense fp32 inputs > 126 MB L2)",
+            "n_pad_mean": n_pad_mean, "active_rows_mean": rows_mean}
+
+
+def init_like_reference(m, seed=0):
+    """utils.weights_init (utils.py:702-708) as train.py:302 applies it, from a private generator."""
+    g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for mod in m.modules():
             name = mod.__class__.__name__
@@ -128,6 +157,15 @@ def build_model(dev):
             elif "BatchNorm" in name:
                 mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.02 + 1.0)
                 mod.bias.zero_()
+    return m
+
+
+def build_model(dev, wl=None):
+    from eagcn_b200 import models as EM
+    wl = wl or _H
+    torch.manual_seed(0)
+    m = EM.EAGCNStack(wl["kb"], 24, wl["widths"], wl["den"][0], wl["den"][1], wl["nclass"], dropout=P_DROP).to(dev)
+    init_like_reference(m)
     m.train()
     return m
 
@@ -137,30 +175,32 @@ class Slot:
     pass
 
 
-def algorithmic(T, E, B, N):
+def algorithmic(wl, T, E, B, N):
     """Per-kernel algorithmic (bytes, flops) of ONE step for this batch: each operand read once, each
     result written once (DESIGN.md 'kernels').  Row counts are the unpadded active rows T."""
     V = 5
     out = {}
     fin = 24
     acc = lambda k, b, f: out.__setitem__(k, (out.get(k, (0, 0))[0] + b, out.get(k, (0, 0))[1] + f))
-    sumC = KB + 10
+    sumC = wl["kb"] + 10
     acc("pack_count_kernel", 4 * B * N * N, 0)
     acc("pack_fill_kernel", 4 * B * N * N + E * sumC * 4 + E * (4 + V), 0)
     acc("pack_link_kernel", E * (4 + 4 + 4 + 2 * V), 0)
-    F, D1, D2 = sum(WIDTHS[-1]), DEN[0], DEN[1]
-    for (m, n, k) in ((B, D1, F), (B, D2, D1), (B, NCLASS, D2)):      # y = x W, dx = dy W^T, dW = x^T dy of den1..den3
+    F, D1, D2, NC = sum(wl["widths"][-1]), wl["den"][0], wl["den"][1], wl["nclass"]
+    for (m, n, k) in ((B, D1, F), (B, D2, D1), (B, NC, D2)):      # y = x W, dx = dy W^T, dW = x^T dy of den1..den3
         acc("mm_tile_kernel", 3 * 4 * (m * k + k * n + m * n), 3 * 2 * m * n * k)
     for c in (F, D1, D2):
         acc("bn_act_fwd_kernel", 8 * B * c, 0)
         acc("bn_act_bwd_kernel", 12 * B * c, 0)
     acc("readout_sum_kernel", 4 * (T + B) * F, 0)
     acc("readout_sum_bwd_kernel", 4 * (T + B) * F, 0)
-    for w in WIDTHS:
+    for w in wl["widths"]:
         C = sum(w)
         acc("gemm_nn", 4 * (T * fin + fin * C + T * C), 2 * T * fin * C)
         acc("gemm_nt", 4 * (T * C + fin * C + T * fin), 2 * T * fin * C)
         acc("gemm_tn", 4 * (T * fin + T * C + fin * C), 2 * T * fin * C)
+        # fused part A: H and the (pre-split) weights in, Y and the saved activation Z out, codes + CSR once
+        acc("layer_fwd_fused", 4 * (T * fin + 2 * fin * C + 2 * T * C) + E * (4 + V) + 4 * V * T, 2 * T * fin * C + 2 * (E + T) * C)
         acc("agg_fwd_kernel", 4 * 2 * T * C + E * (4 + V) + 4 * V * T, 2 * (E + T) * C)
         acc("agg_bwd_kernel", 4 * 4 * T * C + E * (4 + 2 * V) + 4 * V * T, 4 * (E + T) * C)
         acc("bn_apply_kernel", 8 * T * C, 0)
@@ -173,13 +213,248 @@ def algorithmic(T, E, B, N):
 
 KERNEL_ALIAS = {"gemm_simt_nn": "gemm_nn", "gemm_simt_nt": "gemm_nt", "gemm_simt_tn": "gemm_tn",
                 "gemm_tc_nn": "gemm_nn", "gemm_tc_nt": "gemm_nt", "gemm_tc_tn": "gemm_tn"}
+TENSOR_KERNELS = ("gemm_tc_kernel", "layer_fwd_fused")
 
 
+# ------------------------------------------------------------------------------------------------
+class Runner:
+    """Model + NB pre-staged batches of one workload on one device, the captured step graphs and the timers."""
+
+    def __init__(self, wl, dev, args, rank, world, nb, layouts=("dense",)):
+        from eagcn_b200.plan import GraphPlan
+        self.wl, self.dev, self.args, self.rank, self.world, self.nb = wl, dev, args, rank, world, nb
+        self.model = build_model(dev, wl)
+        self.slots = []
+        for i in range(nb):
+            hb, T, E = host_batch(seed=1000 * rank + i, wl=wl)
+            s = Slot()
+            s.hb, s.T, s.E = hb, T, E
+            s.t_cap, s.e_cap = T, E                      # exact capacities known on the host: no device sync
+            dense = hb.dense()
+            s.host_dense = [torch.from_numpy(a).pin_memory() for a in dense]
+            s.host_codes = torch.from_numpy(hb.codes).pin_memory()
+            s.host_afm = s.host_dense[1]
+            s.dev_dense = [t.to(dev, non_blocking=True) for t in s.host_dense]
+            s.dev_codes = s.host_codes.to(dev, non_blocking=True)
+            s.size = torch.from_numpy(hb.sizes).to(dev)
+            self.slots.append(s)
+        torch.cuda.synchronize()
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.GraphPlan = GraphPlan
+        self.layouts = layouts
+        self.dense_mb = float(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in self.slots])) / 1e6
+        self.launches_per_step = None
+
+    def config(self):
+        return workload_config(self.wl, self.world, self.nb, float(np.mean([s.hb.N for s in self.slots])),
+                               float(np.mean([s.T for s in self.slots])), self.dense_mb)
+
+    # ---- one step, three input layouts ----
+    def _run(self, plan, s):
+        if self.args.layers_only:
+            from eagcn_b200 import functional as EF
+            from eagcn_b200.layers import PackedRows
+            h = PackedRows(EF.gather_rows(plan, s.dev_dense[1]), plan)
+            for layer in self.model.conv_layers:
+                h, _ = layer(plan, h)
+            out = EF.readout_sum(plan, h.rows)
+            out.sum().backward()
+            return out[:, :self.wl["nclass"]]
+        out, _, _ = self.model(plan, s.dev_dense[1], size=s.size)
+        out.sum().backward()
+        return out
+
+    def _begin(self):
+        for p in self.params:
+            p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
+        if not self.args.layers_only:
+            self.model.prefetch_params()                      # parameter-only work on the side stream, beside the packing
+
+    def step_dense(self, s):
+        self._begin()
+        return self._run(self.GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap), s)
+
+    def step_zero_copy(self, s):
+        """dense reference layout left in PINNED HOST memory: only adj + atom features are copied, the one-hot
+        planes are gathered at bonded pairs by the packer straight from host memory (zero-copy over PCIe)."""
+        self._begin()
+        return self._run(self.GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap), s)
+
+    def step_codes(self, s):
+        self._begin()
+        return self._run(self.GraphPlan.from_codes(s.dev_codes, s.hb.channels, t_cap=s.t_cap, e_cap=s.e_cap), s)
+
+    # ---- gradient bucket (N > 1): ONE flat buffer, ONE collective per step ----
+    def make_bucket(self):
+        import torch.distributed as dist
+        self.step_dense(self.slots[0])
+        self.gparams = [p for p in self.params if p.grad is not None]
+        n_grad = sum(p.numel() for p in self.gparams)
+        self.flat = torch.zeros(n_grad, device=self.dev)
+        self.grad_bytes = n_grad * 4
+        world, flat = self.world, self.flat
+
+        def all_reduce():
+            if world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)   # mean over replicas in the collective itself
+        self.all_reduce = all_reduce
+
+    def capture(self):
+        from eagcn_b200 import _lib
+        fns = {"dense": self.step_dense, "codes": self.step_codes, "zc": self.step_zero_copy}
+        for _ in range(3):
+            for s in self.slots[:2]:
+                for name in self.layouts:
+                    fns[name](s)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        for s in self.slots:
+            for name in self.layouts:
+                if name == "zc":
+                    continue
+                g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g, pool=self.pool):
+                    out = fns[name](s)
+                    if self.world > 1:                         # pack this graph's gradients into the flat buffer
+                        torch.cat([p.grad.reshape(-1) for p in self.gparams], out=self.flat)
+                setattr(s, "g_" + name, g)
+                setattr(s, "g_" + name + "_out", out)
+                if name == "dense" and self.launches_per_step is None:
+                    self.launches_per_step = _lib.launch_count() - c0
+        if "zc" in self.layouts:
+            # zero-copy layout, software-pipelined across steps: the packing of batch i+1 (its own graph, replayed on
+            # the pack stream right after that batch's H2D) overlaps the layers / head of batch i.  Separate pools:
+            # the two graph families run concurrently.
+            pool_pack = torch.cuda.graph_pool_handle()
+            for s in self.slots:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, pool=pool_pack):
+                    s.zc_plan = self.GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=self.pool):
+                    self._begin()
+                    out = self._run(s.zc_plan, s)
+                    if self.world > 1:
+                        torch.cat([p.grad.reshape(-1) for p in self.gparams], out=self.flat)
+                s.g_zc_pack, s.g_zc_main, s.g_zc_main_out = g1, g2, out
+        torch.cuda.synchronize()
+
+    # ---- timers ----
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, run_step, K, W, local=0):
+        for i in range(W):
+            run_step(i)
+        self.barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            run_step(W + i)
+        e1.record()
+        self.barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), clocks
+
+    def step_value(self, i):
+        s = self.slots[i % self.nb]
+        s.g_dense.replay()
+        self.all_reduce()
+
+    def time_value(self, steps, warmup, passes, local=0):
+        """Median over ``passes`` timed passes of ``steps`` graph replays each (max over ranks per pass); a pass that
+        saw a thermal / hardware slowdown is rejected and repeated once."""
+        res = []
+        for k in range(passes):
+            ms, clocks = self.timed(self.step_value, steps, warmup if k == 0 else 3, local)
+            if {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", [])):
+                ms, clocks = self.timed(self.step_value, steps, 3, local)
+            res.append((ms / steps, clocks))
+        res.sort(key=lambda r: r[0])
+        ms_step, clocks = res[len(res) // 2]
+        return ms_step, clocks, [round(r[0], 5) for r in res]
+
+    def profile_kernels(self, nprof=3):
+        """Per-kernel CUDA-event timing of eager steps (a ~4 ms device-side delay is queued ahead of each step so the
+        host runs ahead and the event pairs bracket kernels, not launch latency) + the algorithmic bytes / flops."""
+        from eagcn_b200 import _lib
+        _lib.profile(True)
+        for i in range(nprof):
+            _lib.lib().eagcn_spin(4_000_000, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            self.step_dense(self.slots[i % self.nb])
+            torch.cuda.synchronize()
+        rep = _lib.profile_report()
+        _lib.profile(False)
+        alg = {}
+        for i in range(nprof):
+            s = self.slots[i % self.nb]
+            for k, (b, f) in algorithmic(self.wl, s.T, s.E, self.wl["batch"], s.hb.N).items():
+                a = alg.get(k, (0, 0)); alg[k] = (a[0] + b, a[1] + f)
+        return rep, alg, nprof
+
+    def roofline(self):
+        rep, alg, nprof = self.profile_kernels()
+        tot_ms = sum(v[1] for v in rep.values())
+        kern = {k: {"launches_per_step": n / nprof, "ms_per_step": ms / nprof, "share": ms / tot_ms if tot_ms else 0}
+                for k, (n, ms) in rep.items()}
+        # the dominant KERNEL: the three tags gemm_tc_nn / _nt / _tn are launches of one kernel (gemm_tc_kernel)
+        by_kernel = {}
+        for k, (n, ms) in rep.items():
+            name = "gemm_tc_kernel" if k.startswith("gemm_tc") else k
+            a = by_kernel.get(name, (0, 0.0)); by_kernel[name] = (a[0] + n, a[1] + ms)
+        if not by_kernel:
+            return None
+        top = max(by_kernel.items(), key=lambda kv: kv[1][1])[0]
+        pk = peaks()
+        tags = [k for k in rep if (k.startswith("gemm_tc") if top == "gemm_tc_kernel" else k == top)]
+        b = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[0] for k in tags)
+        f = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[1] for k in tags)
+        n, ms = by_kernel[top]
+        sec = ms * 1e-3
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp) and self.wl is _H:
+            traffic = json.load(open(tp)).get(top)
+        if top in TENSOR_KERNELS:
+            ach = f / sec / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_sus"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
+                    "launches": n, "avg_launch_us": 1e3 * ms / n,
+                    "note": "useful flops of the fp32-faithful projection products (2*T*K*N each; the fused forward kernel adds "
+                            "its aggregation flops); every product is three TF32 tensor-core passes (hi/lo error "
+                            "compensation), so the ceiling of `frac` against the bf16 peak is 1/6",
+                    "frac_of_3xtf32_ceiling": 6.0 * ach / pk["bf16_sus"]}
+        else:
+            ach = b / sec / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " copy",
+                    "launches": n, "avg_launch_us": 1e3 * ms / n}
+        roof["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 5), "share": round(v["share"], 4),
+                               "launches_per_step": v["launches_per_step"]} for k, v in
+                           sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        # whole step against both rooflines (algorithmic totals of every kernel that ran)
+        tot_b = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[0] for k in rep) / nprof
+        tot_f = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[1] for k in rep) / nprof
+        roof["step_algorithmic"] = {"bytes": tot_b, "flops": tot_f}
+        return roof
+
+
+# ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
     from eagcn_b200 import _lib
-    from eagcn_b200.parallel import FlatGradBucket
-    from eagcn_b200.plan import GraphPlan
+    from eagcn_b200 import functional as EF
+    from eagcn_b200 import models as _M2
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,121 +467,49 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    from eagcn_b200 import functional as EF
     EF.set_gemm_engine(args.gemm)
     EF.set_agg_engine(args.agg)
-    model = build_model(dev)
     EF.Overlap.enabled = bool(args.overlap)
-    _lib.lib().eagcn_set_bn_act_mode(0 if args.bn_act == "vec" else 1)
-    _lib.lib().eagcn_set_fuse_mode(0 if args.fuse_bn else 1)
-    _lib.lib().eagcn_set_tc_bk(args.tc_bk)
+    L = _lib.lib()
+    L.eagcn_set_bn_act_mode(0 if args.bn_act == "vec" else 1)
+    L.eagcn_set_fuse_mode(0 if args.fuse_bn else 1)
+    L.eagcn_set_fwd_fused(1 if args.fwd_fused else 0)
+    L.eagcn_set_tc_bk(args.tc_bk)
     if args.no_pdl:
-        _lib.lib().eagcn_set_pdl(0)
-    from eagcn_b200 import models as _M2
+        L.eagcn_set_pdl(0)
     _M2.Dense.mm_engine = args.dense_mm
+
+    wl = WORKLOADS[args.config]
+    NB = args.nbatches
+    headline = args.config == "tox21"
+    run = Runner(wl, dev, args, rank, world, NB, layouts=("dense", "codes", "zc") if headline else ("dense",))
+    model = run.model
     if args.head != "auto":
-        model.fused_head = args.head == "fused"
         model.head_bn = "torch" if args.head == "torch" else "cuda"
         if args.head == "torch":
-            from eagcn_b200 import models as _M
-            _M.Dense.mm_engine = "torch"
-    NB = args.nbatches
-    slots = []
-    for i in range(NB):
-        hb, T, E = host_batch(seed=1000 * rank + i)
-        s = Slot()
-        s.hb, s.T, s.E = hb, T, E
-        s.t_cap, s.e_cap = T, E                      # exact capacities known on the host: no device sync
-        dense = hb.dense()
-        s.host_dense = [torch.from_numpy(a).pin_memory() for a in dense]
-        s.host_codes = torch.from_numpy(hb.codes).pin_memory()
-        s.host_afm = s.host_dense[1]
-        s.dev_dense = [t.to(dev, non_blocking=True) for t in s.host_dense]
-        s.dev_codes = s.host_codes.to(dev, non_blocking=True)
-        s.size = torch.from_numpy(hb.sizes).to(dev)
-        slots.append(s)
-    torch.cuda.synchronize()
-
-    params = [p for p in model.parameters() if p.requires_grad]
-
-    def layers_only(plan, s):
-        from eagcn_b200 import functional as EF
-        from eagcn_b200.layers import PackedRows
-        h = PackedRows(EF.gather_rows(plan, s.dev_dense[1]), plan)
-        for layer in model.conv_layers:
-            h, _ = layer(plan, h)
-        out = EF.readout_sum(plan, h.rows)
-        out.sum().backward()
-        return out[:, :NCLASS]
-
-    def step_dense(s):
-        for p in params:
-            p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
-        if not args.layers_only:
-            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
-        plan = GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
-        if args.layers_only:
-            return layers_only(plan, s)
-        out, _, _ = model(plan, s.dev_dense[1], size=s.size)
-        out.sum().backward()
-        return out
-
-    def step_zero_copy(s):
-        """dense reference layout left in PINNED HOST memory: only adj + atom features are copied, the one-hot
-        planes are gathered at bonded pairs by the packer straight from host memory (zero-copy over PCIe)."""
-        for p in params:
-            p.grad = None
-        if not args.layers_only:
-            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
-        plan = GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
-        out, _, _ = model(plan, s.dev_dense[1], size=s.size)
-        out.sum().backward()
-        return out
-
-    def step_codes(s):
-        for p in params:
-            p.grad = None
-        if not args.layers_only:
-            model.prefetch_params()          # parameter-only work on the side stream, beside the packing
-        plan = GraphPlan.from_codes(s.dev_codes, s.hb.channels, t_cap=s.t_cap, e_cap=s.e_cap)
-        out, _, _ = model(plan, s.dev_dense[1], size=s.size)
-        out.sum().backward()
-        return out
+            _M2.Dense.mm_engine = "torch"
+    slots = run.slots
+    nclass = wl["nclass"]
 
     # everything from here on runs on ONE non-default stream: autograd bookkeeping created on the legacy
     # default stream must never be touched while a graph is being captured
     work_stream = torch.cuda.Stream()
     work_stream.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(work_stream)
-
-    # which parameters get gradients -> their gradients are packed into ONE flat buffer per step and that
-    # buffer is all-reduced (N > 1): a single collective per step
-    step_dense(slots[0])
-    gparams = [p for p in params if p.grad is not None]
-    n_grad = sum(p.numel() for p in gparams)
-    flat = torch.zeros(n_grad, device=dev)
-
-    class _Bucket:
-        nbytes = n_grad * 4
-
-        @staticmethod
-        def all_reduce():
-            if world > 1:
-                dist.all_reduce(flat)
-                flat.mul_(1.0 / world)
-    bucket = _Bucket()
+    run.make_bucket()
     torch.cuda.synchronize()
+
     if args.gemm_trace:
         # diagnostic: clock64 stamps of the tcgen05 GEMM pipeline (CTA 0 of each GEMM launch of one eager step)
         for i in range(3):
-            step_dense(slots[i % NB])
+            run.step_dense(slots[i % NB])
         torch.cuda.synchronize()
-        stride = int(_lib.lib().eagcn_gemm_trace_stride())
+        stride = int(L.eagcn_gemm_trace_stride())
         buf = torch.zeros(8 * stride, dtype=torch.int64, device=dev)
-        _lib.lib().eagcn_gemm_trace(buf.data_ptr(), 8)
-        step_dense(slots[0])
+        L.eagcn_gemm_trace(buf.data_ptr(), 8)
+        run.step_dense(slots[0])
         torch.cuda.synchronize()
-        _lib.lib().eagcn_gemm_trace(None, 0)
+        L.eagcn_gemm_trace(None, 0)
         tr = buf.cpu().view(8, stride)
         out = []
         for l in range(8):
@@ -323,54 +526,13 @@ def run_b200(args):
         return
     if args.profile_only:
         for i in range(args.warmup + args.steps):
-            step_dense(slots[i % NB])
+            run.step_dense(slots[i % NB])
         torch.cuda.synchronize()
         print(json.dumps({"profile_only": True, "steps": args.steps, "warmup": args.warmup}))
         return
 
-    # ---- capture one CUDA graph per (batch, layout) ----
-    for _ in range(3):
-        for s in slots[:2]:
-            step_dense(s); step_codes(s); step_zero_copy(s)
-    torch.cuda.synchronize()
-    pool = torch.cuda.graph_pool_handle()
-    launches_per_step = None
-    for s in slots:
-        for name, fn in (("g_dense", step_dense), ("g_codes", step_codes)):
-            g = torch.cuda.CUDAGraph()
-            c0 = _lib.launch_count()
-            with torch.cuda.graph(g, pool=pool):
-                out = fn(s)
-                if world > 1:                                  # pack this graph's gradients into the flat buffer
-                    torch.cat([p.grad.reshape(-1) for p in gparams], out=flat)
-            setattr(s, name, g)
-            setattr(s, name + "_out", out)
-            if name == "g_dense" and launches_per_step is None:
-                launches_per_step = _lib.launch_count() - c0
-    # zero-copy layout, software-pipelined across steps: the packing of batch i+1 (its own graph, replayed on the
-    # copy stream right after that batch's H2D) overlaps the layers / head of batch i.  Separate memory pools: the
-    # two graph families run concurrently.
-    pool_pack = torch.cuda.graph_pool_handle()
-    for s in slots:
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1, pool=pool_pack):
-            s.zc_plan = GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
-        g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g2, pool=pool):
-            for p in params:
-                p.grad = None
-            model.prefetch_params()
-            out, _, _ = model(s.zc_plan, s.dev_dense[1], size=s.size)
-            out.sum().backward()
-            if world > 1:
-                torch.cat([p.grad.reshape(-1) for p in gparams], out=flat)
-        s.g_zc_pack, s.g_zc_main, s.g_zc_main_out = g1, g2, out
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    run.capture()
+    launches_per_step = run.launches_per_step
 
     if args.trace:
         # diagnostic (never a bench value): per-kernel durations INSIDE the graph replays, via CUPTI activity records
@@ -404,222 +566,186 @@ def run_b200(args):
                           "last_step_sequence": seq}))
         return
 
-    def timed(run_step, K, W):
-        for i in range(W):
-            run_step(i)
-        barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            run_step(W + i)
-        e1.record()
-        barrier()
-        clocks = sampler.stop()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) , clocks
-
     # ---- value: HBM-resident inputs, graph replay (+ flat all-reduce for N>1) ----
-    def step_value(i):
-        s = slots[i % NB]
-        s.g_dense.replay()
-        bucket.all_reduce()
+    ms_step, clocks, passes = run.time_value(args.steps, args.warmup, args.passes, local)
+    B = wl["batch"]
+    value = B * world / (ms_step * 1e-3)
 
-    ms_total, clocks = timed(step_value, args.steps, args.warmup)
-    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
-    if bad:                                           # rejected run: re-measure once
-        ms_total, clocks = timed(step_value, args.steps, args.warmup)
-    ms_step = ms_total / args.steps
-    value = BATCH * world / (ms_step * 1e-3)
-
-    # ---- e2e: pinned host buffers -> H2D -> step -> D2H, every step ----
-    out_host = torch.empty(BATCH, NCLASS).pin_memory()
-
-    # A real input pipeline prefetches.  Three stages on three streams: the H2D copies of batch i+depth (copy stream), the
-    # packing of batch i+1 from host memory (zero-copy layout only; pack stream) and the step of batch i (work stream)
-    # overlap.  Every step still pays one full H2D + one D2H inside the timed region and ends with a host sync on its
-    # result.
-    copy_stream = torch.cuda.Stream()
-    pack_stream = torch.cuda.Stream()
-    copied = [torch.cuda.Event() for _ in range(NB)]
-    ready = [torch.cuda.Event() for _ in range(NB)]
-    depth = max(1, min(args.e2e_depth, NB - 1))
-
-    def make_e2e(layout):
-        state = {"copied": -1, "ready": -1, "first": True}
-
-        def copy(i):
-            s = slots[i % NB]
-            with torch.cuda.stream(copy_stream):
-                if layout == "dense":
-                    for d, h in zip(s.dev_dense, s.host_dense):
-                        d.copy_(h, non_blocking=True)
-                elif layout == "zc":
-                    s.dev_dense[0].copy_(s.host_dense[0], non_blocking=True)
-                    s.dev_dense[1].copy_(s.host_dense[1], non_blocking=True)
-                else:
-                    s.dev_codes.copy_(s.host_codes, non_blocking=True)
-                    s.dev_dense[1].copy_(s.host_afm, non_blocking=True)
-                copied[i % NB].record(copy_stream)
-            state["copied"] = i
-
-        def make_ready(i):
-            s = slots[i % NB]
-            if layout == "zc":
-                with torch.cuda.stream(pack_stream):
-                    pack_stream.wait_event(copied[i % NB])
-                    s.g_zc_pack.replay()                      # graph plan of this batch, gathered from host memory
-                    ready[i % NB].record(pack_stream)
-            state["ready"] = i
-
-        def advance(i_copy, i_ready):
-            for j in range(state["copied"] + 1, i_copy + 1):
-                copy(j)
-            for j in range(state["ready"] + 1, i_ready + 1):
-                make_ready(j)
-
-        def step(i):
-            s = slots[i % NB]
-            if state["first"]:                                # first step of a run: nothing prefetched yet
-                state["first"] = False
-                state["copied"] = state["ready"] = i - 1
-                copy_stream.wait_stream(torch.cuda.current_stream())
-                pack_stream.wait_stream(torch.cuda.current_stream())
-            advance(i, i)
-            torch.cuda.current_stream().wait_event(ready[i % NB] if layout == "zc" else copied[i % NB])
-            g, gout = {"dense": (s.g_dense, s.g_dense_out), "zc": (s.g_zc_main, s.g_zc_main_out),
-                       "codes": (s.g_codes, s.g_codes_out)}[layout]
-            g.replay()
-            bucket.all_reduce()
-            out_host.copy_(gout, non_blocking=True)
-            advance(i + depth, i + 1)                         # prefetch while this step runs
-            torch.cuda.current_stream().synchronize()         # the user reads this step's result
-        return step
-
-    k_e2e = max(5, min(args.steps, 30))
-    ms_e2e_full, _ = timed(make_e2e("dense"), k_e2e, 3)
-    torch.cuda.synchronize()
-    ms_e2e, _ = timed(make_e2e("zc"), k_e2e, 3)
-    torch.cuda.synchronize()
-    ms_e2e_p, _ = timed(make_e2e("codes"), k_e2e, 3)
-    torch.cuda.synchronize()
-    h2d_dense = int(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in slots]))
-    h2d_zc = int(np.mean([s.host_dense[0].numel() * 4 + s.host_dense[1].numel() * 4 for s in slots]))
-    zc_reads = int(np.mean([s.E * (KB + 10) * 32 for s in slots]))      # one 32-byte sector per (bonded pair, plane)
-    h2d_codes = int(np.mean([s.host_codes.numel() + s.host_afm.numel() * 4 for s in slots]))
-    d2h = out_host.numel() * 4
-
-    # ---- per-kernel CUDA-event profile of eager steps (roofline of the dominant kernel) ----
-    roof = None
-    cpu = None
-    if rank == 0:
-        _lib.profile(True)
-        nprof = 3
-        for i in range(nprof):
-            # ~4 ms of device-side delay first: the host queues the whole eager step behind it, so each kernel's event
-            # pair brackets the kernel and not the host's launch latency
-            _lib.lib().eagcn_spin(4_000_000, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-            step_dense(slots[i % NB])
-            torch.cuda.synchronize()
-        rep = _lib.profile_report()
-        _lib.profile(False)
-        alg = {}
-        for i in range(nprof):
-            s = slots[i % NB]
-            for k, (b, f) in algorithmic(s.T, s.E, BATCH, s.hb.N).items():
-                a = alg.get(k, (0, 0)); alg[k] = (a[0] + b, a[1] + f)
-        tot_ms = sum(v[1] for v in rep.values())
-        kern = {}
-        for k, (n, ms) in rep.items():
-            kern[k] = {"launches_per_step": n / nprof, "ms_per_step": ms / nprof, "share": ms / tot_ms if tot_ms else 0}
-        # the dominant KERNEL: the three tags gemm_tc_nn / _nt / _tn are launches of one kernel (gemm_tc_kernel)
-        by_kernel = {}
-        for k, (n, ms) in rep.items():
-            name = "gemm_tc_kernel" if k.startswith("gemm_tc") else k
-            a = by_kernel.get(name, (0, 0.0)); by_kernel[name] = (a[0] + n, a[1] + ms)
-        top = max(by_kernel.items(), key=lambda kv: kv[1][1])[0] if by_kernel else None
-        pk = peaks()
-        if top is not None:
-            tags = [k for k in rep if (k.startswith("gemm_tc") if top == "gemm_tc_kernel" else k == top)]
-            b = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[0] for k in tags)
-            f = sum(alg.get(KERNEL_ALIAS.get(k, k), (0, 0))[1] for k in tags)
-            n, ms = by_kernel[top]
-            sec = ms * 1e-3
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.isfile(tp):
-                traffic = json.load(open(tp)).get(top)
-            if top.startswith("gemm"):
-                ach = f / sec / 1e12
-                roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_sus"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
-                        "launches": n, "avg_launch_us": 1e3 * ms / n,
-                        "note": "useful 2*T*K*N flops of the fp32-faithful projection products (Z = H W, dH = Q W^T, dW = H^T Q); "
-                                "every product is three TF32 tensor-core passes (hi/lo error compensation), so the ceiling of "
-                                "`frac` against the bf16 peak is 1/6",
-                        "frac_of_3xtf32_ceiling": 6.0 * ach / pk["bf16_sus"]}
-            else:
-                ach = b / sec / 1e9
-                roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " copy",
-                        "launches": n, "avg_launch_us": 1e3 * ms / n}
-            roof["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 5), "share": round(v["share"], 4),
-                                   "launches_per_step": v["launches_per_step"]} for k, v in
-                               sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])}
-        if world == 1 and not args.no_cpu:
-            cpu = run_cpu_baseline(steps=3, warmup=1, budget_s=25.0)
-
-    if rank == 0:
-        if args.layers_only:
+    if args.layers_only:
+        if rank == 0:
             print(json.dumps({"diagnostic": "layers-only (no dense head)", "ms_per_step": ms_step, "value": value,
-                              "e2e_packed_ms": ms_e2e_p / k_e2e, "gpu_launches_per_step": int(launches_per_step)}))
-            return
-        line = {
-            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
-                       "views": 5, "kb": KB, "widths": "24->400->700", "head": "256/64/12", "dropout": P_DROP,
-                       "mode": "train fwd+bwd", "bn_sync": "local",
-                       "dense_head": "fused CUDA (1 kernel fwd + 1 bwd)" if model.fused_head else
-                       ({"tile": "CUDA tile GEMMs (mm_tile, split-K combined in-kernel)", "cuda": "CUDA FFMA GEMMs (eagcn_mm)",
-                         "torch": "library GEMMs"}[_M2.Dense.mm_engine] + " + fused CUDA BatchNorm/ReLU/dropout kernels ("
-                        + ("float4" if _lib.lib().eagcn_get_bn_act_mode() == 0 else "32-channel") + ")"
-                        if model.head_bn == "cuda" else "stock PyTorch ops"),
-                       "overlap": "side-stream graph branches: parameter prep || packing, dW || dH + next layer, head dW || dX"
-                       if EF.Overlap.enabled else "single stream",
-                       "e2e_pipeline": f"H2D {depth} batches ahead, packing 1 ahead, step: 3 streams",
-                       "gemm_engine": {0: "tcgen05 3xTF32 (Z=HW, dH=QW^T, dW=H^TQ)", 1: "FFMA",
-                                       2: "tcgen05 3xTF32 (Z=HW, dH=QW^T) + FFMA (dW)"}[_lib.lib().eagcn_get_gemm_mode()], "parallelism": f"dp{world}",
-                       "pdl": bool(_lib.lib().eagcn_get_pdl()), "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[_lib.lib().eagcn_get_agg_mode()],
-                       "l2": f"{NB} distinct dense input batches rotated ({NB * h2d_dense / 1e6:.0f} MB > 126 MB L2)",
-                       "n_pad_mean": float(np.mean([s.hb.N for s in slots])), "active_rows_mean": float(np.mean([s.T for s in slots])),
-                       "step": "cuda-graph replay of pack + 2 layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce" if world > 1 else ""),
-                       "grad_bytes": bucket.nbytes},
-            "clocks": clocks,
-            "e2e": {"value": BATCH * world / (ms_e2e / k_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_zc,
+                              "gpu_launches_per_step": int(launches_per_step)}))
+        return
+
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H, every step (headline workload) ----
+    e2e = {}
+    if headline:
+        out_host = torch.empty(B, nclass).pin_memory()
+        # A real input pipeline prefetches.  Three stages on three streams: the H2D copies of batch i+depth (copy stream),
+        # the packing of batch i+1 from host memory (zero-copy layout only; pack stream) and the step of batch i (work
+        # stream) overlap.  Every step still pays one full H2D + one D2H inside the timed region and ends with a host
+        # sync on its result.
+        copy_stream = torch.cuda.Stream()
+        pack_stream = torch.cuda.Stream()
+        copied = [torch.cuda.Event() for _ in range(NB)]
+        ready = [torch.cuda.Event() for _ in range(NB)]
+        depth = max(1, min(args.e2e_depth, NB - 1))
+
+        def make_e2e(layout):
+            state = {"copied": -1, "ready": -1, "first": True}
+
+            def copy(i):
+                s = slots[i % NB]
+                with torch.cuda.stream(copy_stream):
+                    if layout == "dense":
+                        for d, h in zip(s.dev_dense, s.host_dense):
+                            d.copy_(h, non_blocking=True)
+                    elif layout == "zc":
+                        s.dev_dense[0].copy_(s.host_dense[0], non_blocking=True)
+                        s.dev_dense[1].copy_(s.host_dense[1], non_blocking=True)
+                    else:
+                        s.dev_codes.copy_(s.host_codes, non_blocking=True)
+                        s.dev_dense[1].copy_(s.host_afm, non_blocking=True)
+                    copied[i % NB].record(copy_stream)
+                state["copied"] = i
+
+            def make_ready(i):
+                s = slots[i % NB]
+                if layout == "zc":
+                    with torch.cuda.stream(pack_stream):
+                        pack_stream.wait_event(copied[i % NB])
+                        s.g_zc_pack.replay()                      # graph plan of this batch, gathered from host memory
+                        ready[i % NB].record(pack_stream)
+                state["ready"] = i
+
+            def advance(i_copy, i_ready):
+                for j in range(state["copied"] + 1, i_copy + 1):
+                    copy(j)
+                for j in range(state["ready"] + 1, i_ready + 1):
+                    make_ready(j)
+
+            def step(i):
+                s = slots[i % NB]
+                if state["first"]:                                # first step of a run: nothing prefetched yet
+                    state["first"] = False
+                    state["copied"] = state["ready"] = i - 1
+                    copy_stream.wait_stream(torch.cuda.current_stream())
+                    pack_stream.wait_stream(torch.cuda.current_stream())
+                advance(i, i)
+                torch.cuda.current_stream().wait_event(ready[i % NB] if layout == "zc" else copied[i % NB])
+                g, gout = {"dense": (s.g_dense, s.g_dense_out), "zc": (s.g_zc_main, s.g_zc_main_out),
+                           "codes": (s.g_codes, s.g_codes_out)}[layout]
+                g.replay()
+                run.all_reduce()
+                out_host.copy_(gout, non_blocking=True)
+                advance(i + depth, i + 1)                         # prefetch while this step runs
+                torch.cuda.current_stream().synchronize()         # the user reads this step's result
+            return step
+
+        k_e2e = max(5, min(args.steps, 30))
+        ms_e2e_full, _ = run.timed(make_e2e("dense"), k_e2e, 3, local)
+        torch.cuda.synchronize()
+        ms_e2e, _ = run.timed(make_e2e("zc"), k_e2e, 3, local)
+        torch.cuda.synchronize()
+        ms_e2e_p, _ = run.timed(make_e2e("codes"), k_e2e, 3, local)
+        torch.cuda.synchronize()
+        h2d_dense = int(run.dense_mb * 1e6)
+        h2d_zc = int(np.mean([s.host_dense[0].numel() * 4 + s.host_dense[1].numel() * 4 for s in slots]))
+        zc_reads = int(np.mean([s.E * (wl["kb"] + 10) * 32 for s in slots]))   # one 32-byte sector per (bonded pair, plane)
+        h2d_codes = int(np.mean([s.host_codes.numel() + s.host_afm.numel() * 4 for s in slots]))
+        d2h = out_host.numel() * 4
+        e2e = {
+            "e2e": {"value": B * world / (ms_e2e / k_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_zc,
                     "d2h_bytes_per_step": d2h, "steps": k_e2e,
                     "layout": "dense fp32 one-hot tensors of the reference collate in pinned host memory; adj + atom "
                               "features copied, one-hot planes gathered at bonded pairs by the packer straight from "
                               "host memory (zero-copy)",
                     "zero_copy_host_read_bytes_per_step_est": zc_reads},
-            "e2e_full_copy": {"value": BATCH * world / (ms_e2e_full / k_e2e * 1e-3), "unit": "molecules/s",
+            "e2e_full_copy": {"value": B * world / (ms_e2e_full / k_e2e * 1e-3), "unit": "molecules/s",
                               "h2d_bytes_per_step": h2d_dense, "d2h_bytes_per_step": d2h, "steps": k_e2e,
                               "layout": "same host tensors, every one copied to the device first (what the reference's collate does)"},
-            "e2e_packed": {"value": BATCH * world / (ms_e2e_p / k_e2e * 1e-3), "unit": "molecules/s",
+            "e2e_packed": {"value": B * world / (ms_e2e_p / k_e2e * 1e-3), "unit": "molecules/s",
                            "h2d_bytes_per_step": h2d_codes, "d2h_bytes_per_step": d2h,
                            "layout": "uint8 edge codes + fp32 atom features", "steps": k_e2e},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roof,
-            "cpu_baseline": cpu,
         }
+
+    # ---- per-kernel CUDA-event profile of eager steps (roofline of the dominant kernel), CPU baseline ----
+    roof = cpu = None
+    extra = {}
+    if rank == 0:
+        roof = run.roofline()
+        if roof is not None:
+            pk = peaks()
+            sa = roof["step_algorithmic"]
+            roof["step_vs_rooflines"] = {"hbm_frac": sa["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm"],
+                                         "tensor_frac_bf16": sa["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_sus"]}
+    impl_detail = {
+        "dense_head": ({"tile": "CUDA tile GEMMs (mm_tile, split-K combined in-kernel)", "cuda": "CUDA FFMA GEMMs (eagcn_mm)",
+                        "torch": "library GEMMs"}[_M2.Dense.mm_engine] + " + fused CUDA BatchNorm/ReLU/dropout kernels ("
+                       + ("float4" if L.eagcn_get_bn_act_mode() == 0 else "32-channel") + ")"
+                       if model.head_bn == "cuda" else "stock PyTorch ops"),
+        "overlap": "side-stream graph branches: parameter prep || packing, dW || dH + next layer, head dW || dX"
+        if EF.Overlap.enabled else "single stream",
+        "layer_forward": "ONE fused kernel per layer for projection + score + normalise + aggregate + bias + statistics "
+                         "partials (layer_fused.cu), then BatchNorm/ReLU/dropout" if L.eagcn_get_fwd_fused() else
+                         "projection GEMM + aggregation kernel + BatchNorm/ReLU/dropout",
+        "gemm_engine": {0: "tcgen05 3xTF32", 1: "FFMA", 2: "tcgen05 3xTF32 (K-major products) + FFMA (dW)"}[L.eagcn_get_gemm_mode()],
+        "pdl": bool(L.eagcn_get_pdl()),
+        "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[L.eagcn_get_agg_mode()],
+        "step": "cuda-graph replay of pack + layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce (AVG)" if world > 1 else ""),
+        "grad_bytes": run.grad_bytes, "timed_passes_ms_per_step": passes,
+        "e2e_pipeline": "H2D 2 batches ahead, packing 1 ahead, step: 3 streams",
+    }
+    if rank == 0 and world == 1 and headline and not args.no_extra:
+        # the other single-GPU BASELINE.json configurations: value + dominant-kernel roofline each
+        cfg0 = run.config()
+        del run, slots
+        torch.cuda.empty_cache()
+        for key in ("lipo3", "hiv2"):
+            try:
+                extra[key] = measure_extra(key, dev, args, local)
+            except Exception as e:                              # a failed extra config must not cost the headline line
+                extra[key] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+    else:
+        cfg0 = run.config()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(wl, steps=3, warmup=1, budget_s=25.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg0, "impl_detail": impl_detail, "clocks": clocks,
+        }
+        line.update(e2e)
+        line.update({"gpu_launches": int(launches_per_step * args.steps * args.passes),
+                     "gpu_launches_per_step": int(launches_per_step), "roofline": roof, "cpu_baseline": cpu})
+        if extra:
+            line["configs"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_extra(key, dev, args, local):
+    """One of the other BASELINE.json single-GPU configurations: graph-replayed value (median of 3 passes) + roofline."""
+    wl = WORKLOADS[key]
+    r = Runner(wl, dev, args, 0, 1, 4)
+    r.make_bucket()
+    r.capture()
+    steps = max(20, min(args.steps, 50))
+    ms_step, clocks, passes = r.time_value(steps, 5, 3, local)
+    roof = r.roofline()
+    if roof is not None:
+        pk = peaks()
+        sa = roof["step_algorithmic"]
+        roof["step_vs_rooflines"] = {"hbm_frac": sa["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm"],
+                                     "tensor_frac_bf16": sa["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_sus"]}
+    return {"config": r.config(), "value": wl["batch"] / (ms_step * 1e-3), "unit": "molecules/s", "ms_per_step": ms_step,
+            "steps": steps, "timed_passes_ms_per_step": passes, "gpu_launches_per_step": int(r.launches_per_step),
+            "clocks": clocks, "roofline": roof}
 
 
 def usable_cores():
@@ -647,64 +773,86 @@ def usable_cores():
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cpu_baseline(steps, warmup, budget_s):
-    """The reference's CPU path (oracle reference-cost form: same ATen op sequence as layers.py / models.py)
-    on the host cores, fwd+bwd, train mode, dropout 0.3.  Bounded: the batch is cut down if one step at
-    B=256 would not fit the budget."""
-    from oracle import eagcn_oracle as O
+def run_cpu_baseline(wl, steps, warmup, budget_s, nbatches=1):
+    """The reference's CPU path on the host cores, fwd+bwd, train mode, dropout 0.3.
+
+    kind "reference": the reference's OWN unmodified classes (layers.GraphConv_Layer / layers.Dense stacked as
+    models.EAGCN wires them, oracle/ref_stack.py) -- /root/reference in the build container, its shipped copy
+    oracle/_ref on the GPU box.  kind "port": the oracle's op-for-op restatement (bit-identical outputs and gradients,
+    tests/test_reference_pins.py) when neither is present.  Bounded: the batch is cut down if one step at the full
+    batch would not fit the budget."""
+    from oracle import ref_loader
     cores = usable_cores()
     torch.set_num_threads(cores)
-    hb, _, _ = host_batch(seed=0)
-    model_sd = None
-    torch.manual_seed(0)
-    # parameters with the reference's shapes / names
-    sd = {}
-    fin = 24
-    g = torch.Generator().manual_seed(0)
-    chans = hb.channels
-    for l, w in enumerate(WIDTHS):
-        pre = f"layer{l + 1}."
-        for v in range(5):
-            bp = f"{pre}block{v + 1}."
-            sd[bp + "att.weight"] = (torch.randn(1, chans[v], 1, 1, generator=g) * 0.3).requires_grad_(True)
-            sd[bp + "self_r"] = (torch.randn(1, generator=g) * 0.01).requires_grad_(True)
-            sd[bp + "graph_conv.weight"] = (torch.randn(fin, w[v], generator=g) * 0.02).requires_grad_(True)
-            sd[bp + "graph_conv.bias"] = (torch.randn(w[v], generator=g) * 0.05).requires_grad_(True)
-            sd[bp + "batch_norm.bn.weight"] = torch.ones(w[v], requires_grad=True)
-            sd[bp + "batch_norm.bn.bias"] = torch.zeros(w[v], requires_grad=True)
-            sd[bp + "batch_norm.bn.running_mean"] = torch.zeros(w[v])
-            sd[bp + "batch_norm.bn.running_var"] = torch.ones(w[v])
-        fin = sum(w)
-    for name, n in (("Graph_BN.", fin), ("bn_den1.", DEN[0]), ("bn_den2.", DEN[1])):
-        sd[name + "weight"] = torch.ones(n, requires_grad=True); sd[name + "bias"] = torch.zeros(n, requires_grad=True)
-        sd[name + "running_mean"] = torch.zeros(n); sd[name + "running_var"] = torch.ones(n)
-    sd["den1.weight"] = (torch.randn(fin, DEN[0], generator=g) * 0.05).requires_grad_(True)
-    sd["den2.weight"] = (torch.randn(DEN[0], DEN[1], generator=g) * 0.05).requires_grad_(True)
-    sd["den3.weight"] = (torch.randn(DEN[1], NCLASS, generator=g) * 0.05).requires_grad_(True)
-    dense = [torch.from_numpy(a) for a in hb.dense()]
-    sizes = torch.from_numpy(hb.sizes)
+    batches = [host_batch(seed=i, wl=wl)[0] for i in range(nbatches)]
+    B = wl["batch"]
+    kind = "reference" if ref_loader.available() else "port"
+    if kind == "reference":
+        from oracle.ref_stack import make_ref_stack, seeded_init
+        with ref_loader.cpu_only():
+            Lr, _, _ = ref_loader.load()
+            torch.manual_seed(0)
+            model = seeded_init(make_ref_stack(Lr, wl["kb"], 24, wl["widths"], wl["den"][0], wl["den"][1], wl["nclass"],
+                                               dropout=P_DROP), seed=0)
+            model.train()
+        dense = [[torch.from_numpy(a) for a in hb.dense()] for hb in batches]
+        sizes = [torch.from_numpy(hb.sizes) for hb in batches]
 
-    def one(nmol):
-        d = [t[:nmol] for t in dense]
-        for t in sd.values():
-            if t.requires_grad:
-                t.grad = None
-        out = O.model_forward_conv(sd, d[0], d[1], d[2:], sizes[:nmol], len(WIDTHS), True, P_DROP)
-        out.sum().backward()
+        def one(nmol, i=0):
+            d = [t[:nmol] for t in dense[i % nbatches]]
+            for p in model.parameters():
+                p.grad = None
+            with ref_loader.cpu_only():
+                out, _, _ = model(*d, sizes[i % nbatches][:nmol])
+                out.sum().backward()
+    else:
+        from oracle import eagcn_oracle as O
+        g = torch.Generator().manual_seed(0)
+        sd, fin, chans = {}, 24, batches[0].channels
+        for l, w in enumerate(wl["widths"]):
+            pre = f"layer{l + 1}."
+            for v in range(5):
+                bp = f"{pre}block{v + 1}."
+                sd[bp + "att.weight"] = (torch.randn(1, chans[v], 1, 1, generator=g) * 0.3).requires_grad_(True)
+                sd[bp + "self_r"] = (torch.randn(1, generator=g) * 0.01).requires_grad_(True)
+                sd[bp + "graph_conv.weight"] = (torch.randn(fin, w[v], generator=g) * 0.02).requires_grad_(True)
+                sd[bp + "graph_conv.bias"] = (torch.randn(w[v], generator=g) * 0.05).requires_grad_(True)
+                sd[bp + "batch_norm.bn.weight"] = torch.ones(w[v], requires_grad=True)
+                sd[bp + "batch_norm.bn.bias"] = torch.zeros(w[v], requires_grad=True)
+                sd[bp + "batch_norm.bn.running_mean"] = torch.zeros(w[v])
+                sd[bp + "batch_norm.bn.running_var"] = torch.ones(w[v])
+            fin = sum(w)
+        for name, n in (("Graph_BN.", fin), ("bn_den1.", wl["den"][0]), ("bn_den2.", wl["den"][1])):
+            sd[name + "weight"] = torch.ones(n, requires_grad=True); sd[name + "bias"] = torch.zeros(n, requires_grad=True)
+            sd[name + "running_mean"] = torch.zeros(n); sd[name + "running_var"] = torch.ones(n)
+        sd["den1.weight"] = (torch.randn(fin, wl["den"][0], generator=g) * 0.05).requires_grad_(True)
+        sd["den2.weight"] = (torch.randn(wl["den"][0], wl["den"][1], generator=g) * 0.05).requires_grad_(True)
+        sd["den3.weight"] = (torch.randn(wl["den"][1], wl["nclass"], generator=g) * 0.05).requires_grad_(True)
+        dense = [[torch.from_numpy(a) for a in hb.dense()] for hb in batches]
+        sizes = [torch.from_numpy(hb.sizes) for hb in batches]
 
-    nmol = BATCH
+        def one(nmol, i=0):
+            d = [t[:nmol] for t in dense[i % nbatches]]
+            for t in sd.values():
+                if t.requires_grad:
+                    t.grad = None
+            out = O.model_forward_conv(sd, d[0], d[1], d[2:], sizes[i % nbatches][:nmol], len(wl["widths"]), True, P_DROP)
+            out.sum().backward()
+
+    nmol = B
     t0 = time.perf_counter(); one(nmol); t1 = time.perf_counter() - t0      # warm-up / calibration
     if t1 * (steps + warmup) > budget_s:
-        nmol = max(16, int(BATCH * budget_s / (t1 * (steps + warmup + 1))))
-    for _ in range(max(0, warmup - 1)):
-        one(nmol)
+        nmol = max(16, int(B * budget_s / (t1 * (steps + warmup + 1))))
+    for k in range(max(0, warmup - 1)):
+        one(nmol, k + 1)
     ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter(); one(nmol); ts.append(time.perf_counter() - t0)
+    for k in range(steps):
+        t0 = time.perf_counter(); one(nmol, warmup + k); ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    return {"value": nmol / sec, "unit": "molecules/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} fwd+bwd steps over the first {nmol} molecules of one {WORKLOAD} batch (N_pad={hb.N}), "
-                      f"{sec * 1e3:.0f} ms/step, torch {torch.__version__} CPU, {cores} threads",
+    src = {"reference": "the reference's own classes (" + ref_loader.source() + ")", "port": "oracle op-for-op port"}[kind]
+    return {"value": nmol / sec, "unit": "molecules/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} fwd+bwd steps over the first {nmol} molecules of {nbatches} rotated {wl['name']} batch(es) "
+                      f"(N_pad={batches[0].N}), {sec * 1e3:.0f} ms/step, {src}, torch {torch.__version__} CPU, {cores} threads",
             "ms_per_step": sec * 1e3}
 
 
@@ -712,20 +860,134 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.config if args.config in WORKLOADS else "tox21"]
+    nb = args.nbatches
     # a step here = fwd+bwd over a bounded sample of the workload; keep the whole run within a few minutes
-    budget = 150.0
-    cpu = run_cpu_baseline(steps=max(1, args.steps), warmup=max(1, args.warmup), budget_s=budget)
+    cpu = run_cpu_baseline(wl, steps=max(1, args.steps), warmup=max(1, args.warmup), budget_s=150.0, nbatches=nb)
+    # the same workload description our arm prints (same seeds -> same batches -> same numbers)
+    metas = [host_batch(seed=i, wl=wl) for i in range(nb)]
+    dense_mb = float(np.mean([hb.dense_bytes() for hb, _, _ in metas])) / 1e6
+    cfg = workload_config(wl, args.gpus, nb, float(np.mean([hb.N for hb, _, _ in metas])),
+                          float(np.mean([T for _, T, _ in metas])), dense_mb)
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "molecules/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dataset_shape": DATASET, "views": 5, "kb": KB, "widths": "24->400->700",
-                       "head": "256/64/12", "dropout": P_DROP, "mode": "train fwd+bwd",
-                       "device": "host CPU cores (the reference has no GPU kernels of its own to time; "
-                                 "/root/reference cannot travel to the GPU box, so its op sequence is restated in oracle/)"},
+            "config": cfg,
+            "impl_detail": {"device": "host CPU cores: the reference has no GPU kernels of its own to time; this arm runs its "
+                                      "CPU implementation of the path (" + cpu["kind"] + ")"},
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cpu["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_sweep(args):
+    """BASELINE.json configs[4]: N_atoms x K views x batch on one GPU, 2-layer stack at the Tox21 per-view widths
+    (80 / 140 per view), uint8-code boundary (the dense one-hot layout of a B = 4096, N = 256 batch would be 60 GB),
+    fwd+bwd in training mode; mol/s + the step's algorithmic bytes / flops against both measured rooflines."""
+    from eagcn_b200 import functional as EF, _lib
+    from eagcn_b200.data import make_batch
+    from eagcn_b200.layers import PackedRows
+    from eagcn_b200.plan import GraphPlan
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    out = []
+    work = torch.cuda.Stream()
+    torch.cuda.set_stream(work)
+    budget_elems = 1.5e9                                         # B * N * N * K bytes of codes per batch (two batches resident)
+    for N in (32, 64, 128, 256):
+        for K in (1, 5, 10):
+            for B in (64, 256, 1024, 4096):
+                if B * N * N * K > budget_elems:
+                    continue
+                fo1, fo2 = (80,) * K, (140,) * K
+                torch.manual_seed(0)
+                g = torch.Generator().manual_seed(0)
+                params, buffers = [], []
+                batches = [make_batch(B, "tox21", seed=s, kb=30, n_views=K, fixed_n=N) for s in range(2)]
+                chans = batches[0].channels
+                fin = 24
+                for fo in (fo1, fo2):
+                    pl, bl = [], []
+                    for v in range(K):
+                        pl += [torch.randn(1, chans[v], 1, 1, generator=g).to(dev).requires_grad_(True),
+                               (torch.randn(1, generator=g) * 0.01).to(dev).requires_grad_(True),
+                               (torch.randn(fin, fo[v], generator=g) * 0.02).to(dev).requires_grad_(True),
+                               (torch.randn(fo[v], generator=g) * 0.05).to(dev).requires_grad_(True),
+                               torch.ones(fo[v], device=dev, requires_grad=True), torch.zeros(fo[v], device=dev, requires_grad=True)]
+                        bl += [torch.zeros(fo[v], device=dev), torch.ones(fo[v], device=dev), torch.zeros(1, dtype=torch.int64, device=dev)]
+                    params.append(pl); buffers.append(bl)
+                    fin = sum(fo)
+                codes = [torch.from_numpy(b.codes).to(dev) for b in batches]
+                afm = [torch.from_numpy(b.afm).to(dev) for b in batches]
+                TE = [(int((b.adj.sum(2) > 0).sum()), int(b.adj.sum())) for b in batches]
+
+                def step(i):
+                    for pl in params:
+                        for t in pl:
+                            t.grad = None
+                    plan = GraphPlan.from_codes(codes[i % 2], chans, t_cap=TE[i % 2][0], e_cap=TE[i % 2][1])
+                    h = EF.gather_rows(plan, afm[i % 2])
+                    f = 24
+                    for l, fo in enumerate((fo1, fo2)):
+                        cfg = EF.LayerConfig(fin=f, fo=fo, training=True, p_drop=P_DROP, rng_stream=l)
+                        h = EF.graph_conv_layer(plan, cfg, h, params[l], buffers[l])
+                        f = sum(fo)
+                    EF.readout_sum(plan, h).sum().backward()
+
+                for i in range(3):
+                    step(i)
+                torch.cuda.synchronize()
+                graphs = []
+                c0 = _lib.launch_count()
+                for i in range(2):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        step(i)
+                    graphs.append(gr)
+                launches = (_lib.launch_count() - c0) // 2
+                for i in range(4):
+                    graphs[i % 2].replay()
+                torch.cuda.synchronize()
+                T, E = TE[0]
+                # ~20 ms of timed work per point, at least 10 steps
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); graphs[0].replay(); e1.record(); torch.cuda.synchronize()
+                steps = int(max(10, min(200, 20.0 / max(e0.elapsed_time(e1), 1e-3))))
+                res = []
+                for _ in range(3):
+                    e0.record()
+                    for i in range(steps):
+                        graphs[i % 2].replay()
+                    e1.record(); torch.cuda.synchronize()
+                    res.append(e0.elapsed_time(e1) / steps)
+                ms = sorted(res)[1]
+                # algorithmic totals of the two layers (packed definition, SURVEY 8(d)): fwd + bwd
+                by = fl = 0
+                f = 24
+                for fo in (fo1, fo2):
+                    C = sum(fo)
+                    by += (6 * E * K // 5) + 4 * T * (f + C) + (6 * E * K // 5) + 4 * T * (2 * C + 2 * f)
+                    fl += 3 * 2 * T * f * C + 6 * (E + T) * C
+                    f = C
+                rec = {"N": N, "K": K, "B": B, "active_rows": T, "edges": E, "ms_per_step": ms, "molecules_per_s": B / (ms * 1e-3),
+                       "gpu_launches_per_step": int(launches), "fused_forward": bool(N <= 128 and _lib.lib().eagcn_get_fwd_fused()),
+                       "hbm_frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "tensor_frac_bf16": fl / (ms * 1e-3) / 1e12 / pk["bf16_sus"],
+                       "tensor_frac_of_3xtf32_ceiling": 6.0 * fl / (ms * 1e-3) / 1e12 / pk["bf16_sus"]}
+                out.append(rec)
+                print(json.dumps(rec), file=sys.stderr)
+                del graphs, codes, afm, params, buffers
+                torch.cuda.empty_cache()
+    doc = {"sweep": "N_atoms x K views x batch, 2 GraphConv layers (80 / 140 channels per view) + sum read-out, train fwd+bwd, "
+                    "1 x B200, CUDA-graph replay, uint8-code boundary, median of 3 passes", "peaks": pk, "points": out}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "r02_sweep.json"), "w") as f:
+        json.dump(doc, f, indent=1)
+    best = max(out, key=lambda r: r["tensor_frac_bf16"]) if out else None
+    print(json.dumps({"sweep_points": len(out), "written": "gpurun_out/r02_sweep.json", "best_tensor_point": best}))
 
 
 def main():
@@ -733,11 +995,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--passes", type=int, default=3, help="timed passes of --steps steps each; the median is reported")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="tox21", choices=["tox21", "lipo3", "hiv2", "sweep"],
+                    help="workload: the headline Tox21 configuration (default; its line also carries lipo3 / hiv2 under "
+                         "`configs`), one of the other BASELINE.json configurations alone, or the synthetic sweep")
     ap.add_argument("--nbatches", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--head", default="auto", choices=["auto", "fused", "torch"],
-                    help="dense head: fused CUDA kernels or stock PyTorch ops (auto = the model's default)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the lipo3 / hiv2 configurations")
+    ap.add_argument("--head", default="auto", choices=["auto", "torch"],
+                    help="dense head: CUDA kernels (auto) or stock PyTorch ops")
     ap.add_argument("--layers-only", action="store_true",
                     help="diagnostic: loss = sum of the last layer's atom rows (no read-out / dense head); not a bench value")
     ap.add_argument("--gemm-trace", action="store_true", help="diagnostic: GEMM pipeline clock stamps of one eager step")
@@ -753,15 +1020,18 @@ def main():
                     help="k-block of the K-major tcgen05 products (0: pipeline model picks per shape)")
     ap.add_argument("--fuse-bn", type=int, default=1, choices=[0, 1],
                     help="1: statistics reduction fused into the forward BatchNorm apply kernel; 0: separate kernels")
+    ap.add_argument("--fwd-fused", type=int, default=1, choices=[0, 1],
+                    help="1: one fused kernel for projection + attention + aggregation per layer; 0: GEMM + aggregation kernels")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2],
-                    help="e2e input pipeline: H2D copies issued this many batches ahead (2: copy of batch i+2, packing of "
-                         "batch i+1 and the step of batch i overlap)")
+                    help="e2e input pipeline: H2D copies issued this many batches ahead")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "ffma", "tcgen05-nt"], help="projection GEMM engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "sweep":
+        run_sweep(args)
     else:
         run_b200(args)
 

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -35,7 +35,7 @@ class PlanStruct(ctypes.Structure):
                 ("chan", _IV),
                 ("counts", c_void_p), ("deg", c_void_p), ("blk", c_void_p), ("pos_row", c_void_p),
                 ("row_pos", c_void_p), ("row_ptr", c_void_p), ("mol_ptr", c_void_p), ("col", c_void_p),
-                ("colpos", c_void_p), ("rev", c_void_p), ("code", c_void_p), ("rcode", c_void_p)]
+                ("colpos", c_void_p), ("rev", c_void_p), ("code", c_void_p), ("rcode", c_void_p), ("tile_row", c_void_p)]
 
 
 class LayerStruct(ctypes.Structure):
@@ -115,6 +115,8 @@ _PROTOS = {
     "eagcn_gemm_trace_stride": (c_int64, []),
     "eagcn_rng_fork": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "eagcn_rng_fork_n": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "eagcn_set_fwd_fused": (c_int, [c_int]),
+    "eagcn_get_fwd_fused": (c_int, []),
     "eagcn_set_fuse_mode": (c_int, [c_int]),
     "eagcn_get_fuse_mode": (c_int, []),
     "eagcn_set_tc_bk": (c_int, [c_int]),

@@ -165,6 +165,7 @@ struct PlanDev {
   int* counts; int* deg; int* blk; int* pos_row; int* row_pos; int* row_ptr; int* mol_ptr;
   int* col; int* colpos; int* rev;
   uint8_t* code; uint8_t* rcode;
+  int* tile_row;
 };
 
 inline PlanDev to_dev(const eagcn_plan_t* p) {
@@ -175,6 +176,7 @@ inline PlanDev to_dev(const eagcn_plan_t* p) {
   d.row_pos = (int*)p->row_pos; d.row_ptr = (int*)p->row_ptr; d.mol_ptr = (int*)p->mol_ptr;
   d.col = (int*)p->col; d.colpos = (int*)p->colpos; d.rev = (int*)p->rev;
   d.code = (uint8_t*)p->code; d.rcode = (uint8_t*)p->rcode;
+  d.tile_row = (int*)p->tile_row;
   return d;
 }
 
@@ -197,7 +199,7 @@ inline bool plan_ok(const eagcn_plan_t* p) {
   return p && p->B > 0 && p->N > 0 && p->V > 0 && p->V <= EAGCN_MAX_VIEWS && p->t_cap > 0 &&
          (p->t_cap % EAGCN_ROW_TILE) == 0 && p->e_cap > 0 && p->counts && p->deg && p->blk && p->pos_row &&
          p->row_pos && p->row_ptr && p->mol_ptr && p->col && p->colpos && p->rev && p->code && p->rcode &&
-         p->B * p->N < (int64_t)2147483000;
+         p->tile_row && p->B * p->N < (int64_t)2147483000;
 }
 
 inline bool aligned16(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; }

@@ -4,6 +4,7 @@
 #include "pack.cu"
 #include "rows.cu"
 #include "layer_fwd.cu"
+#include "layer_fused.cu"
 #include "layer_bwd.cu"
 #include "attention.cu"
 #include "head.cu"

@@ -197,7 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   // 1024-byte aligned carve-up: per stage [A raw/hi | A lo | B raw/hi | B lo]
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned start (SWIZZLE_128B atoms) as an OFFSET into the __shared__ array: an integer round trip of the
+  // pointer would lose the address space and turn every access below into a generic LD.E / ST.E instead of LDS / STS
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t bytesA = BM * bk * 4, bytesB = (uint32_t)g.BN * bk * 4;
   const uint32_t stage_bytes = 2 * bytesA + 2 * bytesB;
   auto sA_hi = [&](int s) { return base + (size_t)s * stage_bytes; };

@@ -638,7 +638,9 @@ extern "C" int64_t eagcn_gemm_workspace_bytes(int64_t fin, int64_t fo_tot, int64
   return gemm_tn_workspace_floats((int)fin, (int)fo_tot, (int)t_cap) * (int64_t)sizeof(float);
 }
 extern "C" int64_t eagcn_partial_floats(int64_t t_cap, int64_t fo_tot, int64_t V) {
-  const int64_t tiles = eagcn_stat_tiles(t_cap);
+  // + 4 tiles: the fused forward kernel stores its per-row-tile sums as doubles for up to 2 * t_cap / 128 + 1
+  // molecule-aligned tiles (4 floats per tile and channel) in this buffer
+  const int64_t tiles = eagcn_stat_tiles(t_cap) + 4;
   const int64_t a = tiles * 2 * fo_tot, b = tiles * V * EAGCN_SIG_STRIDE;
   return a > b ? a : b;
 }
@@ -678,7 +680,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   StatEpilogue ep{2, (const float*)w->ball, nullptr, (float*)w->invstd, (float*)w->dvec,
                   (w->training & 1) ? 1 : 0, 0.0, 0.0, 0.0};
   EAGCN_PROF("stat_reduce_kernel", st);
-  EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->bsums, C, ep);
+  EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->bsums, C, ep, 0);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -26,6 +26,10 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
 inline int& gemm_mode() { static int m = 0; return m; }
 inline int& agg_mode() { static int m = 0; return m; }   // 0: shared-memory tile kernels when eligible, 1: generic
 inline int& fuse_mode() { static int m = 0; return m; }  // 0: statistics reduction fused into the BatchNorm apply kernel, 1: separate
+namespace fz {
+bool fwd_fused_ok(const eagcn_plan_t* plan, const eagcn_layer_t* l, const eagcn_work_t* w, int gemm_mode_, int agg_mode_);
+int layer_fwd_fused(const eagcn_plan_t* plan, const PlanDev& p, const LayerDev& L, const eagcn_work_t* w, cudaStream_t st);
+}
 
 // ---------------------------------------------------------------------------------------------
 // wallT: [2][fo_tot][fin] and wsplit: [2][fin][fo_tot] hold the exact TF32 split of every weight
@@ -430,19 +434,30 @@ struct StatEpilogue {             // what stat_reduce_kernel does with the reduc
 constexpr int kStatLanes = 32;
 __global__ void __launch_bounds__(32 * kStatLanes) stat_reduce_kernel(PlanDev p, LayerDev L,
                                                                       const float* __restrict__ partial,
-                                                                      double* __restrict__ sums, int C, StatEpilogue ep) {
+                                                                      double* __restrict__ sums, int C, StatEpilogue ep,
+                                                                      int aligned_tiles) {
   pdl_prologue();
   __shared__ double s[kStatLanes][2][32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
-  const int ntile = (T + kStatRows - 1) / kStatRows;
+  // partials per 32-row tile, or per molecule-aligned row tile when the fused forward kernel produced them
+  const int ntile = aligned_tiles ? p.counts[EAGCN_CNT_TILES] : (T + kStatRows - 1) / kStatRows;
   double a = 0.0, b = 0.0;
   if (c < C) {
+    if (aligned_tiles) {             // the fused forward kernel writes its (fewer, larger) tile partials in double
+      const double* pd = reinterpret_cast<const double*>(partial);
 #pragma unroll 4
-    for (int t = ty; t < ntile; t += kStatLanes) {
-      a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
-      b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
+      for (int t = ty; t < ntile; t += kStatLanes) {
+        a += __ldg(pd + ((size_t)t * 2 + 0) * C + c);
+        b += __ldg(pd + ((size_t)t * 2 + 1) * C + c);
+      }
+    } else {
+#pragma unroll 4
+      for (int t = ty; t < ntile; t += kStatLanes) {
+        a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
+        b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
+      }
     }
   }
   s[ty][0][cx] = a; s[ty][1][cx] = b;
@@ -475,14 +490,15 @@ __global__ void __launch_bounds__(32 * kStatLanes) stat_reduce_kernel(PlanDev p,
 __global__ void __launch_bounds__(32 * kStatLanes) bn_stat_apply_kernel(
     PlanDev p, LayerDev L, const float* __restrict__ partial, double* __restrict__ sums, const float* __restrict__ Y,
     const float* __restrict__ ball, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ X, int C,
-    double M, double eps, double momentum, float p_drop, const unsigned long long* rng, unsigned long long rng_stream) {
+    double M, double eps, double momentum, float p_drop, const unsigned long long* rng, unsigned long long rng_stream,
+    int aligned_tiles) {
   pdl_prologue();
   __shared__ double s[kStatLanes][2][32];
   __shared__ __align__(16) float s_mu[32], s_is[32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
-  const int ntile = (T + kStatRows - 1) / kStatRows;
+  const int ntile = aligned_tiles ? p.counts[EAGCN_CNT_TILES] : (T + kStatRows - 1) / kStatRows;
   // apply-phase mapping: 8 float4 channel lanes x 128 row lanes over this CTA's share of the rows.  The thread's first
   // kPre rows of Y are requested NOW, so that their memory latency runs under the reduction below.
   constexpr int kPre = 6;
@@ -499,10 +515,19 @@ __global__ void __launch_bounds__(32 * kStatLanes) bn_stat_apply_kernel(
   }
   double a = 0.0, b = 0.0;
   if (c < C) {
+    if (aligned_tiles) {             // the fused forward kernel writes its (fewer, larger) tile partials in double
+      const double* pd = reinterpret_cast<const double*>(partial);
 #pragma unroll 4
-    for (int t = ty; t < ntile; t += kStatLanes) {
-      a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
-      b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
+      for (int t = ty; t < ntile; t += kStatLanes) {
+        a += __ldg(pd + ((size_t)t * 2 + 0) * C + c);
+        b += __ldg(pd + ((size_t)t * 2 + 1) * C + c);
+      }
+    } else {
+#pragma unroll 4
+      for (int t = ty; t < ntile; t += kStatLanes) {
+        a += (double)__ldg(partial + ((size_t)t * 2 + 0) * C + c);
+        b += (double)__ldg(partial + ((size_t)t * 2 + 1) * C + c);
+      }
     }
   }
   s[ty][0][cx] = a; s[ty][1][cx] = b;
@@ -724,6 +749,20 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
     rc = launch_prep_params(L, w, st);
     if (rc) return rc;
   }
+  const int want = (w->training & 1) ? 1 : 0;
+  const bool host_allreduce = (w->training & 2) != 0;   // global-batch BatchNorm: host sums the partial sums over ranks
+  if (fz::fwd_fused_ok(plan, layer, w, gemm_mode(), agg_mode())) {
+    // projection + score + normalise + aggregate + bias + statistics partials in ONE launch (layer_fused.cu)
+    rc = fz::layer_fwd_fused(plan, p, L, w, st);
+    if (rc) return rc;
+    if (want && host_allreduce) {
+      StatEpilogue ep{0, nullptr, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0};
+      EAGCN_PROF("stat_reduce_kernel", st);
+      EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep, 1);
+      EAGCN_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   if (gemm_mode() != 1 && w->wallT && tc::tc_supported((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, L.fin))
     rc = tc::gemm_tc_nt((const float*)w->H, L.fin, (const float*)w->wallT, L.fin, (float*)w->Z, C, p.t_cap, C, L.fin,
                         p.counts + EAGCN_CNT_T, st, "gemm_tc_nn", (const float*)w->wallT + (size_t)L.fin * C);
@@ -733,8 +772,6 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (rc) return rc;
   dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), L.V);
   const int n_pad = (int)(w->n_pad > 0 ? w->n_pad : plan->N);
-  const int want = (w->training & 1) ? 1 : 0;
-  const bool host_allreduce = (w->training & 2) != 0;   // global-batch BatchNorm: host sums the partial sums over ranks
   int fo_max = 0;
   for (int v = 0; v < L.V; ++v) fo_max = L.fo[v] > fo_max ? L.fo[v] : fo_max;
   if (agg_mode() == 0 && vec4_ok(layer) && fo_max <= kTileMaxFo && aligned16(w->Z) && aligned16(w->Y) && aligned16(w->ball)) {
@@ -774,7 +811,7 @@ extern "C" int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer
   if (want && host_allreduce) {
     StatEpilogue ep{0, nullptr, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0};
     EAGCN_PROF("stat_reduce_kernel", st);
-    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep, 0);
     EAGCN_LAUNCH_CHECK();
   }
   return 0;
@@ -792,6 +829,8 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
   const int C = L.fo_tot;
   const double M = (double)(w->m_total > 0 ? w->m_total : plan->B * plan->N);
   const int training = (w->training & 1) ? 1 : 0;
+  // how part A indexed the statistics partials (same pure eligibility test as eagcn_layer_forward_a)
+  const int aligned = (w->H && w->Z && fz::fwd_fused_ok(plan, layer, w, gemm_mode(), agg_mode())) ? 1 : 0;
   if (training && !(w->training & 2) && fuse_mode() == 0 && (C & 3) == 0 && aligned16(w->Y) && aligned16(w->X) &&
       aligned16(w->ball)) {
     // per-replica statistics, float4 layout: reduction of the tile partials + finalize + normalise/ReLU/dropout in ONE launch
@@ -803,7 +842,7 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
     EAGCN_LAUNCH(bn_stat_apply_kernel, dim3(nblk, R), 32 * kStatLanes, 0, st)(
         p, L, (const float*)w->partial, (double*)w->sums, (const float*)w->Y, (const float*)w->ball, (float*)w->mean,
         (float*)w->invstd, (float*)w->X, C, M, w->eps, w->momentum, (float)w->p_drop, (const unsigned long long*)w->rng,
-        (unsigned long long)w->rng_stream);
+        (unsigned long long)w->rng_stream, aligned);
     EAGCN_LAUNCH_CHECK();
     return 0;
   }
@@ -812,7 +851,7 @@ extern "C" int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer
     if (!w->partial) return EAGCN_E_ARG;
     StatEpilogue ep{1, (const float*)w->ball, (float*)w->mean, (float*)w->invstd, nullptr, 1, M, w->eps, w->momentum};
     EAGCN_PROF("stat_reduce_kernel", st);
-    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep);
+    EAGCN_LAUNCH(stat_reduce_kernel, (C + 31) / 32, 32 * kStatLanes, 0, st)(p, L, (const float*)w->partial, (double*)w->sums, C, ep, aligned);
     EAGCN_LAUNCH_CHECK();
   } else {
     EAGCN_PROF("bn_finalize_kernel", st);

@@ -322,12 +322,63 @@ __global__ void __launch_bounds__(kPackThreads) pack_fill_kernel(PlanDev p, cons
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.counts[EAGCN_CNT_STATUS], EAGCN_ST_NOT_ONEHOT);
 }
 
-// one warp per active row: neighbour row ids, reverse edge (binary search), reverse codes
+// Molecule-aligned row tiles for the fused layer kernel (layer_fused.cu): greedy runs of WHOLE molecules with at most
+// EAGCN_ROW_TILE active rows, so that every neighbour of a row lies in the tile that holds its projection on-chip.
+// One warp: the 32 lanes test the next 32 molecule boundaries at once (a tile holds ~7 molecules at Tox21 sizes).
+// A molecule with more than EAGCN_ROW_TILE active rows is cut into plain 128-row tiles and flagged (counts[4]): the
+// fused kernel is not used for such a batch (the host knows from N > EAGCN_ROW_TILE that this can happen).
+constexpr int kTileMolCap = 8191;   // molecule pointers staged in shared memory (beyond: read through L2)
+__device__ void build_row_tiles(const PlanDev& p, int T, const int* __restrict__ s_mp) {
+  const int lane = threadIdx.x & 31;
+  const int cap = p.t_cap / 32 + 1;
+  const bool sm = p.B <= kTileMolCap;
+  auto mp = [&](int i) { return min(sm ? s_mp[i] : p.mol_ptr[i], T); };
+  int k = 0, b = 0, big = 0;
+  while (b < p.B && k < cap) {
+    const int s = mp(b);
+    if (s >= T) break;
+    int last = b;                                      // last boundary index with mol_ptr[last] - s <= 128 rows
+    for (int base = b + 1; base <= p.B; base += 32) {
+      const int i = base + lane;
+      const bool fits = i <= p.B && mp(i) - s <= EAGCN_ROW_TILE;
+      const unsigned m = __ballot_sync(0xffffffffu, fits);
+      const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;   // leading run of fitting boundaries
+      last = base + run - 1;
+      if (run < 32) break;
+    }
+    if (last == b) {                                   // the molecule alone exceeds one tile
+      big = 1;
+      const int e = mp(b + 1);
+      for (int r = s; r < e && k < cap; r += EAGCN_ROW_TILE) { if (lane == 0) p.tile_row[k] = r; ++k; }
+      b = b + 1;
+      continue;
+    }
+    if (mp(last) > s) { if (lane == 0) p.tile_row[k] = s; ++k; }   // skip runs of bond-less molecules
+    b = last;
+  }
+  if (lane == 0) {
+    p.tile_row[k] = T;
+    p.counts[EAGCN_CNT_TILES] = k;
+    p.counts[EAGCN_CNT_BIGMOL] = big;
+  }
+}
+
+// one warp per active row: neighbour row ids, reverse edge (binary search), reverse codes; the last CTA builds the
+// molecule-aligned row tiles
 __global__ void __launch_bounds__(256) pack_link_kernel(PlanDev p) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * 8 + warp;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
+  if (blockIdx.x == gridDim.x - 1) {
+    extern __shared__ int s_mp[];                      // [B + 1] molecule pointers (this CTA only)
+    if (p.B <= kTileMolCap) {
+      for (int i = threadIdx.x; i <= p.B; i += 256) s_mp[i] = p.mol_ptr[i];
+      __syncthreads();
+    }
+    if (warp == 0) build_row_tiles(p, T, s_mp);
+    return;
+  }
+  const int t = blockIdx.x * 8 + warp;
   if (t >= T) return;
   const int e0 = p.row_ptr[t], e1 = p.row_ptr[t + 1];
   if (e1 > p.e_cap) return;
@@ -423,7 +474,7 @@ static int pack_fill_impl(const eagcn_plan_t* plan, const void* src, const void*
                                                           kCodes ? (const uint8_t*)src : nullptr, rp, plane_lanes);
   EAGCN_LAUNCH_CHECK();
   EAGCN_PROF("pack_link_kernel", st);
-  EAGCN_LAUNCH(pack_link_kernel, (p.t_cap + 7) / 8, 256, 0, st)(p);
+  EAGCN_LAUNCH(pack_link_kernel, (p.t_cap + 7) / 8 + 1, 256, p.B <= kTileMolCap ? (size_t)(p.B + 1) * 4 : 0, st)(p);
   EAGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -275,8 +275,9 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.wallT, w.wsplit = ptr(wallT), ptr(wsplit)
         w.mean, w.invstd = ptr(mean), ptr(invstd)
         w.rng = ptr(rng_snapshot)
+        no_bwd = not any(ctx.needs_input_grad[3:])     # inference: the fused forward kernel then skips the store of Z
         w.training = ((1 if cfg.training else 0) | (2 if (cfg.training and cfg.stat_allreduce is not None) else 0) |
-                      (4 if prep is not None else 0))
+                      (4 if prep is not None else 0) | (16 if no_bwd else 0))
         w.rng_stream = int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)

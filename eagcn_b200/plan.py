@@ -66,6 +66,7 @@ class GraphPlan:
         self.rev = torch.empty(self.e_cap, **i32)
         self.code = torch.empty(self.V, self.e_cap, dtype=torch.uint8, device=self.device)
         self.rcode = torch.empty(self.V, self.e_cap, dtype=torch.uint8, device=self.device)
+        self.tile_row = torch.empty(self.t_cap // 32 + 2, **i32)      # molecule-aligned row tiles (fused layer kernel)
         self._fill_struct()
 
     def _fill_struct(self):
@@ -75,7 +76,7 @@ class GraphPlan:
             s.chan[v] = self.channels[v] if v < self.V else 0
         for name in ("counts", "deg", "blk", "pos_row", "mol_ptr"):
             setattr(s, name, getattr(self, name).data_ptr())
-        for name in ("row_pos", "row_ptr", "col", "colpos", "rev", "code", "rcode"):
+        for name in ("row_pos", "row_ptr", "col", "colpos", "rev", "code", "rcode", "tile_row"):
             t = getattr(self, name, None)
             setattr(s, name, t.data_ptr() if t is not None else None)
 

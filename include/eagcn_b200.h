@@ -8,8 +8,13 @@
  * torch tensors (tensor.data_ptr()) and torch's current CUDA stream.
  *
  * Conventions: every pointer is a DEVICE pointer to contiguous row-major memory unless it says
- * "host"; sizes are int64_t; functions are asynchronous with respect to the host, re-entrant,
- * keep no global mutable state, never synchronise the device, never throw and never exit.
+ * "host"; sizes are int64_t; functions are asynchronous with respect to the host, never synchronise
+ * the device, never throw and never exit.  The compute entry points keep no state between calls:
+ * everything they read or write is passed in.  Two exceptions, both documented where declared:
+ * the eagcn_set_* engine switches (process-wide, for A/B measurements: set them before the first
+ * compute call, not concurrently with one) and the diagnostics block at the end (launch counter,
+ * per-kernel profiler: not thread-safe).  One CUDA device per process (torch.distributed's
+ * one-process-per-GPU model): the kernels' shared-memory opt-ins are cached per process.
  * Return value: 0 = ok, negative = invalid argument (EAGCN_E_*), positive = cudaError_t of the
  * failing runtime call / launch.
  *
@@ -25,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 14
+#define EAGCN_ABI_VERSION 15
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -43,6 +48,8 @@ extern "C" {
 #define EAGCN_CNT_T 0               /* number of active atom rows (rows with >=1 bond)  */
 #define EAGCN_CNT_E 1               /* number of directed edges (nnz of adj)            */
 #define EAGCN_CNT_STATUS 2
+#define EAGCN_CNT_TILES 3           /* number of molecule-aligned row tiles (plan.tile_row)  */
+#define EAGCN_CNT_BIGMOL 4          /* 1: some molecule has more than EAGCN_ROW_TILE active rows (no fused layer kernel) */
 
 /*
  * Graph plan: the packed form of one padded batch (adj [B,N,N] + V one-hot relation tensors).
@@ -68,6 +75,10 @@ typedef struct eagcn_plan {
   void* rev;                        /* int32 [e_cap]      index of the reverse edge        */
   void* code;                       /* uint8 [V][e_cap]   type_v(i,j); C_v = all-zero vec  */
   void* rcode;                      /* uint8 [V][e_cap]   type_v(j,i)                      */
+  void* tile_row;                   /* int32 [t_cap/32+2] first row of each molecule-aligned row tile: whole molecules,
+                                     * <= EAGCN_ROW_TILE rows each (greedy), tile_row[n_tiles] = T.  The fused layer
+                                     * kernel runs one tensor-core row tile per entry, so every neighbour of a row is
+                                     * inside the tile whose projection it holds on-chip                            */
 } eagcn_plan_t;
 
 /*
@@ -106,7 +117,8 @@ typedef struct eagcn_work {
   void* mean;     /* f32 [fo_tot]                                                         */
   void* invstd;   /* f32 [fo_tot]                                                         */
   void* rng;      /* u64 [2]               philox seed, offset (device; graph-replay safe) */
-  int64_t training;     /* bit2: eagcn_layer_prepare was already called for wall / wallT / wsplit / ball / sig;
+  int64_t training;     /* bit4 (16): no backward pass will follow (the fused forward then skips the store of Z);
+                         * bit2: eagcn_layer_prepare was already called for wall / wallT / wsplit / ball / sig;
                          * bit0: training mode (batch statistics, dropout); bit1: the host all-reduces `sums`
                          * between forward_a and forward_b and `bsums` between backward_a and backward_b
                          * (global-batch BatchNorm); without bit1 the reductions are fused into fewer kernels */
@@ -176,6 +188,14 @@ int eagcn_readout_sum_bwd(const eagcn_plan_t* plan, const void* dout, void* dpac
  * it when bit2 of work.training is set.                                                                          */
 int eagcn_layer_prepare(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
 int eagcn_layer_forward_a(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);
+/* Part A is ONE kernel launch (layer_fused.cu) when the layout allows it -- padded width N <= EAGCN_ROW_TILE, every
+ * fo_v a multiple of 4, 16-byte aligned rows, tcgen05 engine: per molecule-aligned row tile the projection
+ * Z = H W_all runs on the tensor cores (TMA -> tcgen05 -> TMEM), the tile of Z goes TMEM -> shared memory and the
+ * attention score lookup, row normalisation, neighbour aggregation, bias and BatchNorm partial sums are the epilogue;
+ * Z is written once only as the activation backward needs (bit4 of work.training set: not at all).  Otherwise
+ * projection GEMM + aggregation kernel.  eagcn_set_fwd_fused(0) forces the two-kernel form (measurements).        */
+int eagcn_set_fwd_fused(int on);
+int eagcn_get_fwd_fused(void);
 /* part B: BatchNorm finalize (+ running stats, layers.py:408-412), ReLU, dropout
  * (layers.py:93-94), concat (layers.py:313) -> X                                              */
 int eagcn_layer_forward_b(const eagcn_plan_t* plan, const eagcn_layer_t* layer, const eagcn_work_t* w, void* stream);

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_header_symbols():
 def test_struct_layouts_match_header():
     """All ABI structs are made of 8-byte fields; sizes must equal the C side's."""
     from eagcn_b200 import _lib
-    assert ctypes.sizeof(_lib.PlanStruct) == 8 * (5 + 16 + 12)
+    assert ctypes.sizeof(_lib.PlanStruct) == 8 * (5 + 16 + 13)
     assert ctypes.sizeof(_lib.LayerStruct) == 8 * (3 + 16 + 17 + 9 * 16)
     assert ctypes.sizeof(_lib.WorkStruct) == 8 * 33
     L = _lib.lib()
@@ -43,7 +43,7 @@ def test_size_helpers():
     from eagcn_b200 import _lib
     L = _lib.lib()
     assert L.eagcn_stat_tiles(128) == 4
-    assert L.eagcn_partial_floats(128, 700, 5) == max(4 * 2 * 700, 4 * 5 * 257)
+    assert L.eagcn_partial_floats(128, 700, 5) == max(8 * 2 * 700, 8 * 5 * 257)
     assert L.eagcn_gemm_workspace_bytes(24, 400, 4864) > 0
 
 

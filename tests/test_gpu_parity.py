@@ -1032,3 +1032,82 @@ def test_bench_config_vs_oracle():
         worst = max(worst, err)
         assert err <= 5e-5, (k, err)
     print(f"[bench-config parity] worst gradient error {worst:.2e} of scale")
+
+
+# ------------------------------------------------------------------ fused layer kernel (layer_fused.cu)
+def test_row_tiles_are_whole_molecules():
+    """plan.tile_row: greedy runs of whole molecules, <= 128 active rows each, covering [0, T) in order."""
+    from eagcn_b200.plan import GraphPlan
+    from eagcn_b200.data import make_batch
+    dev = _cuda()
+    for seed, B, ds, fixed in ((0, 256, "tox21", None), (1, 64, "hiv", None), (2, 9, "tox21", 128), (3, 5, "tox21", 150)):
+        batch = make_batch(B, ds, seed=seed, fixed_n=fixed)
+        plan = GraphPlan.from_codes(torch.from_numpy(batch.codes).to(dev), batch.channels).check()
+        cnt = plan.counts.cpu().tolist()
+        T, nt, big = cnt[0], cnt[3], cnt[4]
+        tr = plan.tile_row[:nt + 1].cpu().tolist()
+        mp = plan.mol_ptr.cpu().tolist()
+        assert tr[0] == 0 and tr[nt] == T and all(b > a for a, b in zip(tr, tr[1:]))
+        assert all(b - a <= 128 for a, b in zip(tr, tr[1:]))
+        assert big == (1 if max(b - a for a, b in zip(mp, mp[1:])) > 128 else 0)
+        if not big:
+            starts = set(mp)
+            assert all(t in starts for t in tr)                       # every tile starts (and ends) at a molecule boundary
+            # greedy: a tile cannot take the next molecule as well
+            for k in range(nt - 1):
+                nxt = min(m for m in mp if m > tr[k + 1])
+                assert nxt - tr[k] > 128
+
+
+@pytest.mark.parametrize("B,dataset,fin,fo,training,fixed", [
+    (64, "tox21", 24, (80,) * 5, True, None),
+    (48, "tox21", 400, (140,) * 5, True, None),
+    (32, "lipo", 300, (100,) * 5, False, None),
+    (16, "hiv", 24, (100, 52, 36, 20, 12), True, None),
+    (6, "tox21", 24, (16, 12, 8, 8, 4), True, 128),          # every molecule fills a whole tile
+    (300, "freesolv", 40, (260, 8, 8, 8, 4), True, None),    # a view wider than one 256-column chunk
+])
+def test_fused_forward_equals_two_kernel_form(B, dataset, fin, fo, training, fixed):
+    """eagcn_layer_forward_a as ONE launch (tcgen05 projection with the attention / aggregation epilogue) against the
+    projection GEMM + aggregation kernel pair: same arithmetic per element (Z tile identical, weights and row order
+    identical), so the outputs agree to rounding of the statistics reduction order (<= 1e-6) and gradients likewise."""
+    from eagcn_b200 import functional as EF, layers as EL, _lib
+    from eagcn_b200.data import make_batch, DATASETS
+    dev = _cuda()
+    kb = DATASETS[dataset]["kb"]
+    batch = make_batch(B, dataset=dataset, seed=B, kb=kb, n_afeat=fin, fixed_n=fixed)
+    assert batch.N <= 128
+    torch.manual_seed(B)
+    layer = EL.GraphConv_Layer(fin, kb, *fo, dropout=0.3 if training else 0.0, structure="Concate").to(dev)
+    layer.train(training)
+    ins = _to(dev, [torch.from_numpy(a) for a in batch.dense()])
+    res = []
+    L = _lib.lib()
+    with torch.no_grad():
+        layer(*ins)                                                  # builds (and caches) the graph plan of this batch
+    for fused in (1, 0):
+        L.eagcn_set_fwd_fused(fused)
+        try:
+            c0 = _lib.launch_count()
+            EF.manual_seed(7, dev)
+            for prm in layer.parameters():
+                prm.grad = None
+            sd0 = {k: v.clone() for k, v in layer.state_dict().items()}
+            afm = ins[1].clone().requires_grad_(True)
+            x, _ = layer(ins[0], afm, *ins[2:])
+            x.square().sum().backward()
+            torch.cuda.synchronize()
+            res.append((x.detach().clone(), afm.grad.clone(), {n: q.grad.clone() for n, q in layer.named_parameters() if q.grad is not None},
+                        {k: v.clone() for k, v in layer.state_dict().items()}, _lib.launch_count() - c0))
+            layer.load_state_dict(sd0)
+        finally:
+            L.eagcn_set_fwd_fused(1)
+    (x1, g1, pg1, sd1, n1), (x0, g0, pg0, sd0_, n0) = res
+    assert n1 == n0 - 1                                              # one launch less per layer call
+    assert rel_err(x1, x0) <= 5e-6
+    assert rel_err(g1, g0) <= 2e-5
+    for k in pg0:
+        assert rel_err(pg1[k], pg0[k]) <= 5e-5 or float((pg1[k] - pg0[k]).abs().max()) <= 1e-6 * float(x0.abs().max()), k
+    for k in sd0_:
+        if sd0_[k].is_floating_point():
+            assert rel_err(sd1[k], sd0_[k]) <= 1e-6, k

@@ -225,8 +225,17 @@ class Runner:
         self.wl, self.dev, self.args, self.rank, self.world, self.nb = wl, dev, args, rank, world, nb
         self.model = build_model(dev, wl)
         self.slots = []
+        self.gen_meta = []                                # (N, T) of the batches as generated (workload description)
         for i in range(nb):
-            hb, T, E = host_batch(seed=1000 * rank + i, wl=wl)
+            if world > 1 and getattr(args, "shard", "balanced") == "balanced":
+                # the step's GLOBAL batch = the per-rank batches of all ranks; dealt out by size so that every rank gets
+                # the same number of molecules and nearly the same number of atom rows (parallel.shard_balanced)
+                from eagcn_b200.parallel import shard_balanced
+                glob = [host_batch(seed=1000 * q + i, wl=wl)[0] for q in range(world)]
+                hb = shard_balanced(glob, rank, world)
+                T, E = int((hb.adj.sum(2) > 0).sum()), int(hb.adj.sum())
+            else:
+                hb, T, E = host_batch(seed=1000 * rank + i, wl=wl)
             s = Slot()
             s.hb, s.T, s.E = hb, T, E
             s.t_cap, s.e_cap = T, E                      # exact capacities known on the host: no device sync
@@ -244,10 +253,16 @@ class Runner:
         self.layouts = layouts
         self.dense_mb = float(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in self.slots])) / 1e6
         self.launches_per_step = None
+        self.ar = None
+        self.ar_mode = getattr(args, "allreduce", "graph") if world > 1 else "none"
 
     def config(self):
-        return workload_config(self.wl, self.world, self.nb, float(np.mean([s.hb.N for s in self.slots])),
-                               float(np.mean([s.T for s in self.slots])), self.dense_mb)
+        # described from the batches AS GENERATED for rank 0 (seeds 0..nb-1): the same numbers the reference arm prints
+        metas = [host_batch(seed=i, wl=self.wl) for i in range(self.nb)] if self.world > 1 or self.rank != 0 else \
+            [(s.hb, s.T, s.E) for s in self.slots]
+        dense_mb = float(np.mean([hb.dense_bytes() for hb, _, _ in metas])) / 1e6
+        return workload_config(self.wl, self.world, self.nb, float(np.mean([hb.N for hb, _, _ in metas])),
+                               float(np.mean([T for _, T, _ in metas])), dense_mb)
 
     # ---- one step, three input layouts ----
     def _run(self, plan, s):
@@ -262,11 +277,15 @@ class Runner:
             return out[:, :self.wl["nclass"]]
         out, _, _ = self.model(plan, s.dev_dense[1], size=s.size)
         out.sum().backward()
+        if self.ar is not None and self.ar_mode == "graph":
+            self.ar.finish()                                  # remainder of the gradient exchange + join (inside the step / graph)
         return out
 
     def _begin(self):
         for p in self.params:
             p.grad = None                                     # fresh gradients: no zero-fill / accumulate kernels
+        if self.ar is not None:
+            self.ar.begin()                                   # gradient arena back to offset 0
         if not self.args.layers_only:
             self.model.prefetch_params()                      # parameter-only work on the side stream, beside the packing
 
@@ -286,17 +305,32 @@ class Runner:
 
     # ---- gradient bucket (N > 1): ONE flat buffer, ONE collective per step ----
     def make_bucket(self):
-        import torch.distributed as dist
+        """Gradient arena: every parameter gradient of the step is written by the kernels into ONE flat buffer (no
+        packing copy); for N > 1 that buffer is all-reduced (AVG) in two pieces on a communication stream -- the head's
+        and the upper layers' gradients while layer 1's backward still runs -- either inside the captured step graph
+        (--allreduce graph) or as one collective after the replay (--allreduce eager)."""
+        from eagcn_b200 import functional as EF
+        from eagcn_b200.parallel import ArenaAllReduce
+        EF.GradArena.current = None                            # (a previous Runner's arena)
         self.step_dense(self.slots[0])
         self.gparams = [p for p in self.params if p.grad is not None]
-        n_grad = sum(p.numel() for p in self.gparams)
-        self.flat = torch.zeros(n_grad, device=self.dev)
-        self.grad_bytes = n_grad * 4
-        world, flat = self.world, self.flat
+        n = EF.GradArena.measure(lambda: self.step_dense(self.slots[0]), self.dev)
+        self.arena = EF.GradArena(n, self.dev)
+        EF.GradArena.current = self.arena
+        self.ar = ArenaAllReduce(self.arena, overlap=(self.ar_mode == "graph"))
+        if self.world > 1 and self.ar_mode == "graph":
+            first = self.model.conv_layers[0]
+            first.register_forward_hook(lambda m, i, o: self.ar.watch(o[0].rows if hasattr(o[0], "rows") else o[0]))
+        self.step_dense(self.slots[0])
+        torch.cuda.synchronize()
+        assert all(self.arena.holds(p.grad) for p in self.gparams), "a parameter gradient was produced outside the arena"
+        self.grad_bytes = self.arena.off * 4
+        ar, mode = self.ar, self.ar_mode
 
-        def all_reduce():
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)   # mean over replicas in the collective itself
+        def all_reduce():                                     # after the replay: only the eager mode has work left
+            if mode == "eager":
+                ar.done = 0
+                ar.finish()
         self.all_reduce = all_reduce
 
     def capture(self):
@@ -314,10 +348,8 @@ class Runner:
                     continue
                 g = torch.cuda.CUDAGraph()
                 c0 = _lib.launch_count()
-                with torch.cuda.graph(g, pool=self.pool):
+                with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
                     out = fns[name](s)
-                    if self.world > 1:                         # pack this graph's gradients into the flat buffer
-                        torch.cat([p.grad.reshape(-1) for p in self.gparams], out=self.flat)
                 setattr(s, "g_" + name, g)
                 setattr(s, "g_" + name + "_out", out)
                 if name == "dense" and self.launches_per_step is None:
@@ -332,11 +364,9 @@ class Runner:
                 with torch.cuda.graph(g1, pool=pool_pack):
                     s.zc_plan = self.GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, pool=self.pool):
+                with torch.cuda.graph(g2, pool=self.pool, capture_error_mode="thread_local"):
                     self._begin()
                     out = self._run(s.zc_plan, s)
-                    if self.world > 1:
-                        torch.cat([p.grad.reshape(-1) for p in self.gparams], out=self.flat)
                 s.g_zc_pack, s.g_zc_main, s.g_zc_main_out = g1, g2, out
         torch.cuda.synchronize()
 
@@ -464,7 +494,15 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the single JSON line
+        # collectives are captured into the step's CUDA graph: the process group's watchdog must not poll CUDA events of
+        # captured work (PyTorch CUDA-graphs notes: disable NCCL async error handling before init_process_group)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
+        warm = torch.ones(1024, device=dev)
+        for _ in range(3):                                    # communicator + AVG kernels warm before any capture
+            dist.all_reduce(warm, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     EF.set_gemm_engine(args.gemm)
@@ -478,6 +516,18 @@ def run_b200(args):
     if args.no_pdl:
         L.eagcn_set_pdl(0)
     _M2.Dense.mm_engine = args.dense_mm
+
+    dp_parity = None
+    if world > 1:
+        # multi-rank parity travels with the scaling numbers: one small N-rank step with global-batch BatchNorm against
+        # the single process on the concatenated batch, before anything is timed
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            import dp_parity as _dp
+            dp_parity = _dp.check(dev, rank, world)
+        except Exception as e:
+            dp_parity = {"error": repr(e)[:300]}
+        torch.cuda.synchronize()
 
     wl = WORKLOADS[args.config]
     NB = args.nbatches
@@ -680,7 +730,7 @@ def run_b200(args):
             roof["step_vs_rooflines"] = {"hbm_frac": sa["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm"],
                                          "tensor_frac_bf16": sa["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_sus"]}
     impl_detail = {
-        "dense_head": ({"tile": "CUDA tile GEMMs (mm_tile, split-K combined in-kernel)", "cuda": "CUDA FFMA GEMMs (eagcn_mm)",
+        "dense_head": ({"tile": "CUDA tile GEMMs (mm_tile, split-K combined in-kernel)",
                         "torch": "library GEMMs"}[_M2.Dense.mm_engine] + " + fused CUDA BatchNorm/ReLU/dropout kernels ("
                        + ("float4" if L.eagcn_get_bn_act_mode() == 0 else "32-channel") + ")"
                        if model.head_bn == "cuda" else "stock PyTorch ops"),
@@ -692,7 +742,11 @@ def run_b200(args):
         "gemm_engine": {0: "tcgen05 3xTF32", 1: "FFMA", 2: "tcgen05 3xTF32 (K-major products) + FFMA (dW)"}[L.eagcn_get_gemm_mode()],
         "pdl": bool(L.eagcn_get_pdl()),
         "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[L.eagcn_get_agg_mode()],
-        "step": "cuda-graph replay of pack + layers + head fwd/bwd" + (" + NCCL flat-grad all-reduce (AVG)" if world > 1 else ""),
+        "step": "cuda-graph replay of pack + layers + head fwd/bwd" + ({
+            "graph": " with the NCCL gradient all-reduce (AVG over the gradient arena, two pieces on a communication stream: "
+                     "head + upper layers under layer 1's backward) captured inside the graph",
+            "eager": " + one NCCL all-reduce (AVG) over the gradient arena after the replay", "none": ""}[run.ar_mode]),
+        "sharding": getattr(args, "shard", "balanced") if world > 1 else "single rank",
         "grad_bytes": run.grad_bytes, "timed_passes_ms_per_step": passes,
         "e2e_pipeline": "H2D 2 batches ahead, packing 1 ahead, step: 3 streams",
     }
@@ -724,6 +778,8 @@ def run_b200(args):
                      "gpu_launches_per_step": int(launches_per_step), "roofline": roof, "cpu_baseline": cpu})
         if extra:
             line["configs"] = extra
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -1001,6 +1057,12 @@ def main():
                     help="workload: the headline Tox21 configuration (default; its line also carries lipo3 / hiv2 under "
                          "`configs`), one of the other BASELINE.json configurations alone, or the synthetic sweep")
     ap.add_argument("--nbatches", type=int, default=8)
+    ap.add_argument("--allreduce", default="graph", choices=["graph", "eager"],
+                    help="N > 1: gradient all-reduce captured inside the step graph and overlapped with layer 1's backward "
+                         "(graph) or one collective after each replay (eager)")
+    ap.add_argument("--shard", default="balanced", choices=["balanced", "contiguous"],
+                    help="N > 1: molecules of the global batch dealt to the ranks by size (equal molecules, near-equal atoms) "
+                         "or every rank its own generated batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the lipo3 / hiv2 configurations")
     ap.add_argument("--head", default="auto", choices=["auto", "torch"],
@@ -1012,7 +1074,7 @@ def main():
     ap.add_argument("--profile-only", action="store_true",
                     help="eager steps only, no graphs / e2e / cpu (for `ncu`: never a bench value)")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
-    ap.add_argument("--dense-mm", default="tile", choices=["tile", "cuda", "torch"], help="GEMM of the head's dense layers")
+    ap.add_argument("--dense-mm", default="tile", choices=["tile", "torch"], help="GEMM of the head's dense layers")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="1: independent branches of a step on a side stream (parallel graph branches); 0: one stream")
     ap.add_argument("--bn-act", default="vec", choices=["vec", "c32"], help="head BatchNorm kernels: float4 or 32-channel")

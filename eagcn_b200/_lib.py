@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -56,20 +56,6 @@ class WorkStruct(ctypes.Structure):
                 ("gemm_ws_bytes", c_int64), ("wallT", c_void_p), ("wsplit", c_void_p), ("phase", c_int64)]
 
 
-_P3 = c_void_p * 3
-
-
-class HeadStruct(ctypes.Structure):
-    _fields_ = [("B", c_int64), ("F", c_int64), ("D1", c_int64), ("D2", c_int64), ("NC", c_int64),
-                ("training", c_int64), ("rng_stream", c_int64),
-                ("p_drop", c_double), ("eps", c_double), ("momentum", c_double),
-                ("x0", c_void_p), ("W", _P3), ("bn_w", _P3), ("bn_b", _P3), ("bn_rm", _P3), ("bn_rv", _P3),
-                ("bn_nbt", _P3), ("rng", c_void_p), ("a1", c_void_p), ("a2", c_void_p), ("out", c_void_p),
-                ("mean", _P3), ("invstd", _P3), ("part", c_void_p), ("bar", c_void_p),
-                ("d_out", c_void_p), ("d_a2", c_void_p), ("g2buf", c_void_p), ("g1buf", c_void_p), ("dh0", c_void_p),
-                ("dx0", c_void_p), ("dW", _P3), ("dbn_w", _P3), ("dbn_b", _P3)]
-
-
 _PROTOS = {
     "eagcn_version": (c_int, []),
     "eagcn_sizeof": (c_int64, [c_int]),
@@ -93,9 +79,6 @@ _PROTOS = {
     "eagcn_attention_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_attention_dense_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eagcn_dropout_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
-    "eagcn_head_part_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
-    "eagcn_head_forward": (c_int, [c_void_p, c_void_p]),
-    "eagcn_head_backward": (c_int, [c_void_p, c_void_p]),
     "eagcn_set_gemm_mode": (c_int, [c_int]),
     "eagcn_get_gemm_mode": (c_int, []),
     "eagcn_bn_act_forward": (c_int, [c_void_p] * 9 + [c_int64, c_int64, c_int, c_int, c_double, c_void_p, c_int64,
@@ -104,9 +87,6 @@ _PROTOS = {
                                       c_void_p]),
     "eagcn_set_bn_act_mode": (c_int, [c_int]),
     "eagcn_get_bn_act_mode": (c_int, []),
-    "eagcn_mm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
-    "eagcn_mm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                         c_int64, c_void_p]),
     "eagcn_mm_tile_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "eagcn_mm_tile_tickets": (c_int64, [c_int64, c_int64]),
     "eagcn_mm_tile": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
@@ -159,7 +139,7 @@ def lib():
         v = L.eagcn_version()
         if v != ABI_VERSION:
             raise EagcnError(f"libeagcn_sm100.so ABI {v} != python binding {ABI_VERSION}: rebuild")
-        for which, cls in enumerate((PlanStruct, LayerStruct, WorkStruct, HeadStruct)):
+        for which, cls in enumerate((PlanStruct, LayerStruct, WorkStruct)):
             if L.eagcn_sizeof(which) != ctypes.sizeof(cls):
                 raise EagcnError(f"{cls.__name__}: ctypes mirror is {ctypes.sizeof(cls)} bytes, the library's struct "
                                  f"{L.eagcn_sizeof(which)}: rebuild")

@@ -7,7 +7,6 @@
 #include "layer_fused.cu"
 #include "layer_bwd.cu"
 #include "attention.cu"
-#include "head.cu"
 #include "bn_act.cu"
 #include "mm_tile.cu"
 
@@ -17,7 +16,6 @@ extern "C" int64_t eagcn_sizeof(int which) {
     case 0: return (int64_t)sizeof(eagcn_plan_t);
     case 1: return (int64_t)sizeof(eagcn_layer_t);
     case 2: return (int64_t)sizeof(eagcn_work_t);
-    case 3: return (int64_t)sizeof(eagcn_head_t);
     default: return -1;
   }
 }
@@ -79,18 +77,6 @@ extern "C" int eagcn_gemm_tn(const void* A, int64_t lda, const void* B, int64_t 
     return eagcn::gemm_tn((const float*)A, (int)lda, (const float*)B, (int)ldb, (float*)C, (int)M, (int)N, (int)k_cap,
                           (const int*)k_dev, (float*)ws, ws_bytes / 4, st);
   return EAGCN_E_ARG;
-}
-
-extern "C" int64_t eagcn_mm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  if (M <= 0 || N <= 0 || K <= 0) return 0;
-  return eagcn::mm_workspace_floats((int)M, (int)N, (int)K) * (int64_t)sizeof(float);
-}
-extern "C" int eagcn_mm(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C, int64_t M,
-                        int64_t N, int64_t K, void* ws, int64_t ws_bytes, void* stream) {
-  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || M > (1 << 24) || N > (1 << 24) || K > (1 << 24)) return EAGCN_E_ARG;
-  if (lda < (transA ? M : K) || ldb < (transB ? K : N)) return EAGCN_E_ARG;
-  return eagcn::mm((const float*)A, (int)lda, transA != 0, (const float*)B, (int)ldb, transB != 0, (float*)C, (int)M, (int)N,
-                   (int)K, (float*)ws, ws_bytes / 4, (cudaStream_t)stream);
 }
 
 // ---- diagnostics -----------------------------------------------------------------------------------

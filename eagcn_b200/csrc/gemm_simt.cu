@@ -164,41 +164,4 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int M, i
 }
 
 
-// ---- general strict-fp32 product for the small dense layers of the head (reference layers.py:382-388) ----
-// C[M,N] = op(A) . op(B), row-major operands, split-K over ~2 CTAs per SM with a fixed-order reduction.  The library
-// GEMM picks an un-split 32x32 tile kernel for these shapes (M = 256: 64 CTAs walking K = 1400 serially).
-int mm_splits(int M, int N, int K) {
-  // a reduce launch costs ~4 us on the dependent chain of a CUDA graph: split only when few tiles would otherwise walk a
-  // long K serially (den1 forward: 8 tiles x K = 1400)
-  const int tiles = ((M + GBM - 1) / GBM) * ((N + GBN - 1) / GBN);
-  if (tiles >= 40 || K < 512) return 1;
-  int ns = 148 / tiles;
-  const int kmax = K / 128;
-  if (ns > kmax) ns = kmax;
-  if (ns > 32) ns = 32;
-  return ns < 1 ? 1 : ns;
-}
-long long mm_workspace_floats(int M, int N, int K) {
-  const int ns = mm_splits(M, N, K);
-  return ns > 1 ? (long long)ns * M * N : 0;
-}
-int mm(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int M, int N, int K,
-       float* ws, long long ws_floats, cudaStream_t st) {
-  const int ns = mm_splits(M, N, K);
-  if (ns > 1 && (!ws || ws_floats < (long long)ns * M * N)) return EAGCN_E_ARG;
-  int kchunk = (K + ns - 1) / ns;
-  kchunk = ((kchunk + GBK - 1) / GBK) * GBK;
-  GemmArgs g{A, B, ns > 1 ? ws : C, transA ? 1 : lda, transA ? lda : 1, transB ? 1 : ldb, transB ? ldb : 1, N, M, N, K,
-             nullptr, nullptr, kchunk, (long long)M * N};
-  dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, ns);
-  EAGCN_PROF("mm_simt", st);
-  if (!transA && !transB) EAGCN_LAUNCH((gemm_simt_kernel<true, false>), grid, GTHREADS, 0, st)(g);
-  else if (!transA && transB) EAGCN_LAUNCH((gemm_simt_kernel<true, true>), grid, GTHREADS, 0, st)(g);
-  else if (transA && !transB) EAGCN_LAUNCH((gemm_simt_kernel<false, false>), grid, GTHREADS, 0, st)(g);
-  else EAGCN_LAUNCH((gemm_simt_kernel<false, true>), grid, GTHREADS, 0, st)(g);
-  EAGCN_LAUNCH_CHECK();
-  if (ns > 1) return splitk_reduce(ws, C, (long long)M * N, ns, st);
-  return 0;
-}
-
 }  // namespace eagcn

@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import EagcnError, HeadStruct, LayerStruct, WorkStruct, check, lib, ptr
+from ._lib import EagcnError, LayerStruct, WorkStruct, check, lib, ptr
 from .plan import GraphPlan, _stream
 
 _F32 = torch.float32
@@ -127,6 +127,64 @@ class Overlap:
             if getattr(p, "_post_accumulate_grad_hooks", None):
                 return False
         return True
+
+
+class GradArena:
+    """All parameter gradients of a backward pass in ONE flat fp32 buffer, written there by the kernels themselves.
+
+    The layer / dense / BatchNorm backward functions allocate their gradient outputs (dW_all, d bias / gamma / beta,
+    d att / d self_r, head dW, dgamma, dbeta) through ``GradArena.empty``; with an arena installed (``GradArena.current``)
+    those are consecutive 64-byte aligned slices of ``flat`` in backward order (head first, layer 1 last) and autograd
+    hands the parameters views of it -- so the data-parallel gradient exchange is ONE collective over ``flat[:off]``
+    with no packing copy, and ``flat[:mark]`` -- everything above layer 1 -- can be reduced while
+    layer 1's backward still runs (eagcn_b200.parallel.ArenaAllReduce).  Offsets are a pure function of the model, so a
+    captured CUDA graph replays onto the same addresses; call ``reset()`` at the start of every step."""
+    current = None
+
+    def __init__(self, nfloats, device):
+        self.flat = torch.zeros(int(nfloats), dtype=_F32, device=device)
+        self.off = 0
+        self.device = torch.device(device)
+
+    def reset(self):
+        self.off = 0
+
+    def take(self, n):
+        n = int(n)
+        if self.off + n > self.flat.numel():
+            raise EagcnError(f"GradArena of {self.flat.numel()} floats is too small (need {self.off + n}); size it with GradArena.measure")
+        t = self.flat[self.off:self.off + n]
+        self.off += (n + 15) & ~15
+        return t
+
+    @staticmethod
+    def empty(n, device):
+        a = GradArena.current
+        if a is not None and a.device == torch.device(device):
+            return a.take(n)
+        return torch.empty(int(n), dtype=_F32, device=device)
+
+    @classmethod
+    def measure(cls, run_backward, device):
+        """Floats one backward pass allocates (run under a counting arena)."""
+        class _Count:
+            def __init__(self):
+                self.off, self.device = 0, torch.device(device)
+
+            def take(self, n):
+                self.off += (int(n) + 15) & ~15
+                return torch.empty(int(n), dtype=_F32, device=device)
+        prev, cls.current = cls.current, _Count()
+        try:
+            run_backward()
+            return cls.current.off
+        finally:
+            cls.current = prev
+
+    def holds(self, t):
+        """True when tensor ``t`` lives inside the arena (its gradient needs no separate exchange)."""
+        lo = self.flat.data_ptr()
+        return t is not None and lo <= t.data_ptr() < lo + self.flat.numel() * 4
 
 
 @dataclass
@@ -316,9 +374,9 @@ class _GraphConvLayerFn(torch.autograd.Function):
         Q = torch.empty(T, C, **f32)
         need_dH = ctx.needs_input_grad[3]
         dH = torch.empty(T, cfg.fin, **f32) if need_dH else None
-        dwall = torch.empty(cfg.fin * C, **f32)        # view-blocked: each view's [fin, fo_v] block contiguous
-        dvec = torch.empty(3, C, **f32)
-        datt = torch.empty(plan.V, _lib.SIG_STRIDE, **f32)
+        dwall = GradArena.empty(cfg.fin * C, dev)      # view-blocked: each view's [fin, fo_v] block contiguous
+        dvec = GradArena.empty(3 * C, dev).view(3, C)
+        datt = GradArena.empty(plan.V * _lib.SIG_STRIDE, dev).view(plan.V, _lib.SIG_STRIDE)
         bsums = torch.empty(2, C, dtype=torch.float64, device=dev)
         partial = torch.empty(int(L.eagcn_partial_floats(T, C, plan.V)), **f32)
         ws_bytes = int(L.eagcn_gemm_workspace_bytes(cfg.fin, C, T))
@@ -568,101 +626,6 @@ def dropout_keep_mask(plan, cfg: LayerConfig, fo_tot, rng_state):
 
 
 # ------------------------------------------------------------------------------------------------
-_head_bars = {}
-
-
-def _head_bar(dev):
-    key = torch.device(dev).index or 0
-    if key not in _head_bars:
-        _head_bars[key] = torch.zeros(2, dtype=torch.int32, device=dev)     # grid-barrier state, lives forever
-    return _head_bars[key]
-
-
-class _HeadFn(torch.autograd.Function):
-    """Graph_BN -> den1 -> bn_den1 -> ReLU -> dropout -> den2 -> bn_den2 -> ReLU -> den3 (models.py:112-120)
-    in one kernel per direction.  Inputs: x0, then (W1, W2, W3, g0, b0, g1, b1, g2, b2)."""
-
-    @staticmethod
-    def forward(ctx, cfg, bufs, x0, *params):
-        training, p_drop, rng_stream, eps, momentum = cfg
-        dev = x0.device
-        x0 = x0.contiguous()
-        params = tuple(p.detach().contiguous() for p in params)
-        W1, W2, W3, g0, b0, g1, b1, g2, b2 = params
-        B, F = x0.shape
-        D1, D2, NC = W1.shape[1], W2.shape[1], W3.shape[1]
-        if W1.shape[0] != F or W2.shape[0] != D1 or W3.shape[0] != D2:
-            raise ValueError("dense head: inconsistent weight shapes")
-        f32 = dict(dtype=_F32, device=dev)
-        a1 = torch.empty(B, D1, **f32); a2 = torch.empty(B, D2, **f32); out = torch.empty(B, NC, **f32)
-        stats = [torch.empty(n, **f32) for n in (F, F, D1, D1, D2, D2)]
-        L = lib()
-        part = torch.empty(int(L.eagcn_head_part_floats(B, F, D1, D2)), **f32)
-        rng = RngState.get(dev)
-        snap = rng.fork() if (training and p_drop > 0.0) else None
-        h = HeadStruct()
-        h.B, h.F, h.D1, h.D2, h.NC = B, F, D1, D2, NC
-        h.training, h.rng_stream = int(training), int(rng_stream)
-        h.p_drop, h.eps, h.momentum = float(p_drop), float(eps), float(momentum)
-        h.x0 = x0.data_ptr()
-        for i, t in enumerate((W1, W2, W3)):
-            h.W[i] = t.data_ptr()
-        for i, (g, b) in enumerate(((g0, b0), (g1, b1), (g2, b2))):
-            h.bn_w[i], h.bn_b[i] = g.data_ptr(), b.data_ptr()
-            rm, rv, nbt = bufs[3 * i: 3 * i + 3]
-            h.bn_rm[i], h.bn_rv[i] = rm.data_ptr(), rv.data_ptr()
-            h.bn_nbt[i] = nbt.data_ptr() if nbt is not None else None
-            h.mean[i], h.invstd[i] = stats[2 * i].data_ptr(), stats[2 * i + 1].data_ptr()
-        h.rng = snap.data_ptr() if snap is not None else None
-        h.a1, h.a2, h.out = a1.data_ptr(), a2.data_ptr(), out.data_ptr()
-        h.part, h.bar = part.data_ptr(), _head_bar(dev).data_ptr()
-        check(L.eagcn_head_forward(ctypes.byref(h), _stream()), "eagcn_head_forward")
-        ctx.cfg, ctx.bufs = cfg, bufs
-        ctx.saved = (x0, params, a1, a2, stats, snap)
-        return out, a2
-
-    @staticmethod
-    def backward(ctx, d_out, d_a2):
-        training, p_drop, rng_stream, eps, momentum = ctx.cfg
-        x0, params, a1, a2, stats, snap = ctx.saved
-        W1, W2, W3, g0, b0, g1, b1, g2, b2 = params
-        dev = x0.device
-        B, F = x0.shape
-        D1, D2, NC = W1.shape[1], W2.shape[1], W3.shape[1]
-        f32 = dict(dtype=_F32, device=dev)
-        L = lib()
-        d_out = d_out.contiguous() if d_out is not None else torch.zeros(B, NC, **f32)
-        d_a2 = d_a2.contiguous() if d_a2 is not None else None
-        g2buf = torch.empty(B, D2, **f32); g1buf = torch.empty(B, D1, **f32); dh0 = torch.empty(B, F, **f32)
-        dx0 = torch.empty(B, F, **f32)
-        dW = [torch.empty_like(W1), torch.empty_like(W2), torch.empty_like(W3)]
-        dg = [torch.empty_like(g0), torch.empty_like(g1), torch.empty_like(g2)]
-        db = [torch.empty_like(b0), torch.empty_like(b1), torch.empty_like(b2)]
-        part = torch.empty(int(L.eagcn_head_part_floats(B, F, D1, D2)), **f32)
-        h = HeadStruct()
-        h.B, h.F, h.D1, h.D2, h.NC = B, F, D1, D2, NC
-        h.training, h.rng_stream = int(training), int(rng_stream)
-        h.p_drop, h.eps, h.momentum = float(p_drop), float(eps), float(momentum)
-        h.x0 = x0.data_ptr()
-        for i, t in enumerate((W1, W2, W3)):
-            h.W[i] = t.data_ptr()
-            h.dW[i] = dW[i].data_ptr()
-        for i, (g, b) in enumerate(((g0, b0), (g1, b1), (g2, b2))):
-            h.bn_w[i], h.bn_b[i] = g.data_ptr(), b.data_ptr()
-            rm, rv, nbt = ctx.bufs[3 * i: 3 * i + 3]
-            h.bn_rm[i], h.bn_rv[i] = rm.data_ptr(), rv.data_ptr()
-            h.mean[i], h.invstd[i] = stats[2 * i].data_ptr(), stats[2 * i + 1].data_ptr()
-            h.dbn_w[i], h.dbn_b[i] = dg[i].data_ptr(), db[i].data_ptr()
-        h.rng = snap.data_ptr() if snap is not None else None
-        h.a1, h.a2 = a1.data_ptr(), a2.data_ptr()
-        h.part, h.bar = part.data_ptr(), _head_bar(dev).data_ptr()
-        h.d_out = d_out.data_ptr()
-        h.d_a2 = d_a2.data_ptr() if d_a2 is not None else None
-        h.g2buf, h.g1buf, h.dh0, h.dx0 = g2buf.data_ptr(), g1buf.data_ptr(), dh0.data_ptr(), dx0.data_ptr()
-        check(L.eagcn_head_backward(ctypes.byref(h), _stream()), "eagcn_head_backward")
-        return (None, None, dx0, dW[0], dW[1], dW[2], dg[0], db[0], dg[1], db[1], dg[2], db[2])
-
-
 class _BnActFn(torch.autograd.Function):
     """dropout(relu(BatchNorm1d(x))) in one kernel per direction (models.py:112, 114-116, 119)."""
 
@@ -695,27 +658,12 @@ class _BnActFn(torch.autograd.Function):
         B, C = x.shape
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dg, db = torch.empty_like(g), torch.empty_like(b)
+        dg, db = GradArena.empty(C, x.device), GradArena.empty(C, x.device)
         check(lib().eagcn_bn_act_backward(ptr(x), ptr(dy), ptr(g), ptr(b), ptr(mean), ptr(invstd), ptr(dx), ptr(dg),
                                           ptr(db), B, C, int(training), int(relu), float(p_drop),
                                           ptr(snap) if snap is not None else None, int(rng_stream), _stream()),
               "eagcn_bn_act_backward")
         return None, None, dx, dg, db
-
-
-def _mm(A, transA, B, transB):
-    """op(A) @ op(B) through eagcn_mm (strict fp32, split-K with fixed-order reduction)."""
-    M = A.shape[1] if transA else A.shape[0]
-    K = A.shape[0] if transA else A.shape[1]
-    N = B.shape[0] if transB else B.shape[1]
-    if (B.shape[1] if transB else B.shape[0]) != K:
-        raise ValueError("mm: inner dimensions differ")
-    C = torch.empty(M, N, dtype=_F32, device=A.device)
-    nbytes = int(lib().eagcn_mm_workspace_bytes(M, N, K))
-    ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
-    check(lib().eagcn_mm(ptr(A), A.shape[1], int(transA), ptr(B), B.shape[1], int(transB), ptr(C), M, N, K,
-                         ptr(ws) if ws is not None else None, nbytes, _stream()), "eagcn_mm")
-    return C
 
 
 _tickets = {}
@@ -733,7 +681,7 @@ def _ticket_buf(dev, lane, n):
     return t
 
 
-def _mm_tile_bufs(A, transA, B, transB, lane):
+def _mm_tile_bufs(A, transA, B, transB, lane, grad=False):
     """Output, split-K workspace and ticket array of one ``_mm_tile`` call, allocated (and, for a new ticket array,
     zero-filled) on the CURRENT stream: a side-stream call gets them BEFORE its fork point, so the fork orders the
     allocation / zero-fill ahead of the side-stream kernel."""
@@ -741,7 +689,8 @@ def _mm_tile_bufs(A, transA, B, transB, lane):
     K = A.shape[0] if transA else A.shape[1]
     N = B.shape[0] if transB else B.shape[1]
     L = lib()
-    C = torch.empty(M, N, dtype=_F32, device=A.device)
+    # a weight gradient goes to the gradient arena when one is installed
+    C = GradArena.empty(M * N, A.device).view(M, N) if grad else torch.empty(M, N, dtype=_F32, device=A.device)
     nbytes = int(L.eagcn_mm_tile_workspace_bytes(M, N, K))
     ws = torch.empty(nbytes // 4, dtype=_F32, device=A.device) if nbytes else None
     tk = _ticket_buf(A.device, lane, int(L.eagcn_mm_tile_tickets(M, N))) if nbytes else None
@@ -764,8 +713,8 @@ def _mm_tile(A, transA, B, transB, stream=None, bufs=None):
 
 
 class _DenseMmFn(torch.autograd.Function):
-    """y = x @ W (layers.py:382-388) with dX = dY @ W^T and dW = x^T @ dY.  engine 'tile': mm_tile.cu, the weight
-    gradient on the side stream beside dX (Overlap); engine 'cuda': the split-K FFMA kernel of gemm_simt.cu."""
+    """y = x @ W (layers.py:382-388) with dX = dY @ W^T and dW = x^T @ dY on mm_tile.cu, the weight gradient on the
+    side stream beside dX (Overlap)."""
 
     @staticmethod
     def forward(ctx, x, W, engine):
@@ -774,24 +723,19 @@ class _DenseMmFn(torch.autograd.Function):
         ctx.w_ref = W
         x, W = x.contiguous(), W.detach().contiguous()
         ctx.save_for_backward(x, W)
-        ctx.engine = engine
-        if engine == "tile":
-            return _mm_tile(x, False, W, False)[0]
-        return _mm(x, False, W, False)
+        if engine != "tile":
+            raise ValueError("dense_mm engines: 'tile' (mm_tile.cu)")
+        return _mm_tile(x, False, W, False)[0]
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if ctx.engine != "tile":
-            dx = _mm(dy, False, W, True) if need_dx else None
-            dW = _mm(x, True, dy, False) if need_dw else None
-            return dx, dW, None
         dx = dW = None
         if need_dw and need_dx and Overlap.enabled:
             # every buffer the side-stream product touches exists (tickets zero-filled) before the branch point
-            side_bufs = _mm_tile_bufs(x, True, dy, False, lane=1)
+            side_bufs = _mm_tile_bufs(x, True, dy, False, lane=1, grad=True)
             forked = Overlap.fork_point(dy.device)
             dx, ws_dx = _mm_tile(dy, False, W, True)      # first: the rest of the backward pass waits for it
             side = Overlap.fork_from(dy.device, forked)
@@ -806,7 +750,7 @@ class _DenseMmFn(torch.autograd.Function):
         if need_dx:
             dx = _mm_tile(dy, False, W, True)[0]
         if need_dw:
-            dW = _mm_tile(x, True, dy, False)[0]
+            dW = _mm_tile(x, True, dy, False, bufs=_mm_tile_bufs(x, True, dy, False, lane=0, grad=True))[0]
         return dx, dW, None
 
 
@@ -819,14 +763,6 @@ def bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):
     momentum = bn.momentum if bn.momentum is not None else 0.1
     cfg = (bool(training), bool(relu), float(p_drop), int(rng_stream), float(bn.eps), float(momentum))
     return _BnActFn.apply(cfg, (bn.running_mean, bn.running_var, bn.num_batches_tracked), x, bn.weight, bn.bias)
-
-
-def dense_head(x0, weights, bns, training, p_drop, rng_stream=1000):
-    """weights: (W1, W2, W3); bns: three nn.BatchNorm1d.  Returns (out, graph_representation)."""
-    params = tuple(weights) + tuple(t for bn in bns for t in (bn.weight, bn.bias))
-    bufs = tuple(t for bn in bns for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked))
-    cfg = (bool(training), float(p_drop), int(rng_stream), float(bns[0].eps), float(bns[0].momentum))
-    return _HeadFn.apply(cfg, bufs, x0, *params)
 
 
 def dropout_keep_mask_flat(rng_state, rng_stream, p_drop, total):

@@ -193,11 +193,12 @@ class GraphConv_Layer(nn.Module):
     """All bond relations of one layer (layers.py:262-325), CUDA path."""
 
     _plan_cache = None          # (key, weakref to adjs, plan): the 4 layers of a model share one plan
-    # True: a layer whose widths are not multiples of 4 floats (HIV layer 2: 5 x 250) runs on widths rounded up to 4
-    # (EF.pad_layer_args: zero-padded parameters, real channels cut out afterwards) and so stays on the tensor-core GEMM
-    # and the float4 kernels instead of the FFMA / scalar fallbacks.  The padding algebra is CPU-tested
-    # (tests/test_pad_widths.py); it is opt-in until the padded shapes have been timed on a B200.
-    pad_widths = False
+    # True (default): a layer whose widths are not multiples of 4 floats (HIV layer 2: 5 x 250, train.py:70-71) runs on
+    # widths rounded up to 4 (EF.pad_layer_args: zero-padded parameters, real channels cut out afterwards) and so stays
+    # on the tensor-core GEMM and the float4 kernels instead of the FFMA / scalar fallbacks.  The padding algebra is
+    # CPU-tested (tests/test_pad_widths.py) and checked on the GPU against the reference-generated golden of that
+    # configuration (tests/test_gpu_parity.py); False keeps the un-padded fallback engines.
+    pad_widths = True
 
     def __init__(self, node_feature_in, bond_feature_num, node_out_1, node_out_2, node_out_3, node_out_4,
                  node_out_5, dropout, structure, last=False, adj_size=0):

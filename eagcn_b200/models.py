@@ -49,12 +49,11 @@ class Dense(nn.Module):
 
     # 'tile' : eagcn_mm_tile (mm_tile.cu: 32x32 tiles, whole K range staged at once, split-K combined inside the launch,
     #          weight gradient on the side stream) -- strict fp32, bit-reproducible;
-    # 'torch': library GEMM (un-split 32x32x16 SIMT kernel on these skinny shapes: 63 us per step over 9 products);
-    # 'cuda' : eagcn_mm (128x64 tiles of the projection FFMA kernel: 197 us per step)
+    # 'torch': library GEMM (un-split 32x32x16 SIMT kernel on these skinny shapes: 63 us per step over 9 products)
     mm_engine = "tile"
 
     def forward(self, input):
-        if self.mm_engine in ("tile", "cuda") and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:
+        if self.mm_engine == "tile" and input.is_cuda and input.dim() == 2 and input.dtype == torch.float32:
             out = EF.dense_mm(input, self.weight, self.mm_engine)                   # layers.py:382-388
         else:
             out = torch.mm(input, self.weight)
@@ -99,10 +98,6 @@ class EAGCNStack(nn.Module):
         if molfp_mode not in ("sum", "ave", "pool"):
             raise EagcnError("read-out modes: 'sum' / 'ave' / 'pool' (models.py:104-111)")
         self.molfp_mode, self.dropout = molfp_mode, dropout
-        # True: one CUDA kernel per direction for the dense head (eagcn_b200/csrc/head.cu, parity-tested).  Measured
-        # slower than the ~35 stock PyTorch launches it replaces at B = 256 (un-pipelined operand loads), so it is
-        # opt-in until its tile loop is software-pipelined.
-        self.fused_head = False
         self.head_bn = "cuda"          # 'cuda': fused BatchNorm/ReLU/dropout kernels; 'torch': stock modules
         fin = n_afeat
         self.n_layers = len(widths)
@@ -180,12 +175,6 @@ class EAGCNStack(nn.Module):
                 x = EF.readout_sum(plan, h.rows)                                    # models.py:108
         if self.molfp_mode == "ave":                                                # models.py:109-111
             x = x / size.view(-1, 1).to(x.dtype)
-        if self.fused_head and all(bn.momentum is not None and bn.affine and bn.track_running_stats
-                                   for bn in (self.Graph_BN, self.bn_den1, self.bn_den2)):
-            x, graph_representation = EF.dense_head(x, (self.den1.weight, self.den2.weight, self.den3.weight),
-                                                    (self.Graph_BN, self.bn_den1, self.bn_den2), self.training,
-                                                    float(self.dropout))              # models.py:112-120
-            return x, atom_representations, graph_representation
         bns = (self.Graph_BN, self.bn_den1, self.bn_den2)
         if self.head_bn == "cuda" and all(bn.affine and bn.track_running_stats and bn.momentum is not None for bn in bns):
             # library GEMMs between fused BatchNorm(+ReLU)(+dropout) kernels: 3 + 3 launches instead of ~25

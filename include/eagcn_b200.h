@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 15
+#define EAGCN_ABI_VERSION 16
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -149,7 +149,7 @@ typedef struct eagcn_work {
 } eagcn_work_t;
 
 int eagcn_version(void);
-/* sizeof of the ABI structs as compiled (0: eagcn_plan_t, 1: eagcn_layer_t, 2: eagcn_work_t, 3: eagcn_head_t): lets a
+/* sizeof of the ABI structs as compiled (0: eagcn_plan_t, 1: eagcn_layer_t, 2: eagcn_work_t): lets a
  * foreign-function binding verify its mirror of the layouts at load time                                          */
 int64_t eagcn_sizeof(int which);
 /* number of CTAs/tiles the statistics partial buffer must hold for a given t_cap */
@@ -216,36 +216,9 @@ int eagcn_dropout_mask(const eagcn_plan_t* plan, const eagcn_work_t* w, int64_t 
 int eagcn_rng_fork(void* state, void* snapshot, int64_t increment, void* stream);
 /* n call sites in one launch: snapshots u64 [n][2], snapshot i = (seed, offset + i*increment); offset += n*increment */
 int eagcn_rng_fork_n(void* state, void* snapshots, int64_t n, int64_t increment, void* stream);
-/* same generator over a flat index range (the fused head draws element m*D1+k of stream rng_stream):
+/* same generator over a flat index range (eagcn_bn_act_forward draws element b*C+c of stream rng_stream):
  * keep_out u8 [total]                                                                          */
 int eagcn_dropout_mask_flat(const void* rng, int64_t rng_stream, double p_drop, int64_t total, void* keep_out, void* stream);
-
-/* --- fused read-out head (models.py:112-120): Graph_BN -> den1 -> bn_den1 -> ReLU -> dropout -> den2 ->
- * bn_den2 -> ReLU -> den3, three bias-free Dense layers (layers.py:360-392) and three BatchNorm1d over the B
- * molecules.  ONE kernel forward, ONE kernel backward (single resident grid with a software grid barrier;
- * `bar` is a persistent uint32[2] that must be zero when first used).                                     */
-typedef struct eagcn_head {
-  int64_t B, F, D1, D2, NC;         /* molecules, read-out width, den1 / den2 widths, classes           */
-  int64_t training, rng_stream;
-  double p_drop, eps, momentum;
-  void* x0;                         /* f32 [B, F]   read-out (sum / mean over atoms)                    */
-  void* W[3];                       /* f32 [F,D1] [D1,D2] [D2,NC]  den1..den3 weights                   */
-  void* bn_w[3]; void* bn_b[3];     /* Graph_BN, bn_den1, bn_den2 affine                                 */
-  void* bn_rm[3]; void* bn_rv[3]; void* bn_nbt[3];   /* running mean / var (updated in training), i64 counters */
-  void* rng;                        /* u64 [2] philox seed, offset (device)                              */
-  void* a1; void* a2; void* out;    /* f32 [B,D1] [B,D2] (= graph_representation) [B,NC]                 */
-  void* mean[3]; void* invstd[3];   /* saved statistics [F] [D1] [D2]                                    */
-  void* part;                       /* f32 eagcn_head_part_floats() workspace                            */
-  void* bar;                        /* u32 [2] grid barrier state                                        */
-  /* backward */
-  void* d_out; void* d_a2;          /* f32 [B,NC]; optional [B,D2] gradient of graph_representation     */
-  void* g2buf; void* g1buf; void* dh0;   /* f32 [B,D2] [B,D1] [B,F] workspaces                           */
-  void* dx0;                        /* f32 [B,F] out                                                    */
-  void* dW[3]; void* dbn_w[3]; void* dbn_b[3];   /* out: parameter gradients                            */
-} eagcn_head_t;
-int64_t eagcn_head_part_floats(int64_t B, int64_t F, int64_t D1, int64_t D2);
-int eagcn_head_forward(const eagcn_head_t* args, void* stream);
-int eagcn_head_backward(const eagcn_head_t* args, void* stream);
 
 /* --- fused BatchNorm1d (+ReLU)(+dropout) of the read-out head ---------------------------------- */
 /* y[B,C] = dropout(relu(BatchNorm1d(x)))  -- reference models.py:112 (Graph_BN: relu = 0, p_drop = 0), :114-116
@@ -267,15 +240,9 @@ int eagcn_set_bn_act_mode(int mode);
 int eagcn_get_bn_act_mode(void);
 
 /* --- dense layers of the head ------------------------------------------------------------------ */
-/* C[M,N] = op(A) . op(B) in strict fp32 (FFMA), row-major; transX != 0: the operand is stored transposed (A as [K,M],
- * B as [N,K]); lda / ldb = row strides in elements; C is dense (ldc = N).  Split-K with a fixed-order reduction
- * through ws (eagcn_mm_workspace_bytes(M,N,K) bytes; may be NULL when that is 0).  This is `torch.mm(input, weight)`
- * of reference layers.py:382-388 (Dense.forward) and its two autograd products.                                  */
-int64_t eagcn_mm_workspace_bytes(int64_t M, int64_t N, int64_t K);
-int eagcn_mm(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C, int64_t M, int64_t N,
-             int64_t K, void* ws, int64_t ws_bytes, void* stream);
-
-/* Same product on the small-matrix tile kernel (mm_tile.cu): 32x32 tiles, split-K combined INSIDE the launch (the last
+/* C[M,N] = op(A) . op(B) in strict fp32, row-major; transX != 0: the operand is stored transposed (A as [K,M], B as
+ * [N,K]); lda / ldb = row strides in elements; C is dense (ldc = N).  This is `torch.mm(input, weight)` of reference
+ * layers.py:382-388 (Dense.forward) and its two autograd products, on the small-matrix tile kernel (mm_tile.cu): 32x32 tiles, split-K combined INSIDE the launch (the last
  * CTA to reach a tile sums the partials in z order: bit-reproducible, no second kernel).  `tickets`: device int32
  * [eagcn_mm_tile_tickets(M,N)], zero when first used; the kernel leaves it zero, so one array can serve every call that
  * is ordered after the previous one (calls that may run concurrently need separate arrays).  ws:

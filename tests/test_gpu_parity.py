@@ -470,14 +470,15 @@ def test_view_count_sweep_vs_oracle(V, fixed_n, B):
         assert float((dsd[k].grad.cpu() - t.grad).abs().max()) / denom <= 5 * TOL, k
 
 
-# ------------------------------------------------------------------ fused dense head
+# ------------------------------------------------------------------ dense head
 @pytest.mark.parametrize("B,F,D1,D2,NC,training,p", [
     (64, 100, 48, 24, 5, True, 0.0), (256, 700, 256, 64, 12, True, 0.0), (37, 70, 33, 17, 1, False, 0.0),
     (128, 300, 128, 64, 3, True, 0.3),
 ])
-def test_fused_head_vs_oracle(B, F, D1, D2, NC, training, p):
-    """models.py:112-120 in one kernel per direction vs the oracle (ReLU decisions / dropout mask taken from the
-    implementation under test, the former bounded to the kink)."""
+def test_head_vs_oracle(B, F, D1, D2, NC, training, p):
+    """models.py:112-120 on the library's kernels (fused BatchNorm/ReLU/dropout launches between mm_tile products) vs the
+    oracle: the dropout mask is exported from the library's stream, the ReLU decisions are taken from the
+    implementation under test."""
     import torch.nn as nn
     from eagcn_b200 import functional as EF
     dev = _cuda()
@@ -498,16 +499,20 @@ def test_fused_head_vs_oracle(B, F, D1, D2, NC, training, p):
     xg = x0.to(dev).requires_grad_(True)
     EF.manual_seed(77, dev)
     rng_before = EF.RngState.get(dev).state.clone()
-    out, a2 = EF.dense_head(xg, Ws, bns, training, p)
+    x = EF.bn_act(xg, bns[0], training)                                           # models.py:112
+    a1 = EF.bn_act(EF.dense_mm(x, Ws[0]), bns[1], training, relu=True, p_drop=p)  # models.py:114-116
+    a2 = EF.dense_mm(a1, Ws[1])                                                   # models.py:117 (graph_representation)
+    a3 = EF.bn_act(a2, bns[2], training, relu=True)                               # models.py:119
+    out = EF.dense_mm(a3, Ws[2])                                                  # models.py:120
     keep = None
     if training and p > 0:
         keep = EF.dropout_keep_mask_flat(rng_before, 1000, p, B * D1).view(B, D1).float().cpu()
         assert abs(float(keep.mean()) - (1 - p)) < 0.03
-    # ReLU decisions of the implementation: recompute its pre-activations from its own saved stats is not exposed,
-    # so take them from a float64 oracle pass and only allow kink-level disagreement via the output check below
+    one = torch.ones(B, D1)
+    relu_masks = ((a1.detach().cpu() > 0).float() + (one - (keep if keep is not None else one)), (a3.detach().cpu() > 0).float())
     ref_sd = O.clone_sd(sd, requires_grad=True)
     x_ref = x0.clone().requires_grad_(True)
-    y_ref, g_ref = O.head_forward(ref_sd, None, None, training, p=p, keep=keep, x0=x_ref)
+    y_ref, g_ref = O.head_forward(ref_sd, None, None, training, p=p, keep=keep, x0=x_ref, relu_masks=relu_masks)
     assert rel_err(out.cpu(), y_ref) <= 2 * TOL
     assert rel_err(a2.cpu(), g_ref) <= 2 * TOL
     gen2 = torch.Generator().manual_seed(3)
@@ -520,7 +525,9 @@ def test_fused_head_vs_oracle(B, F, D1, D2, NC, training, p):
         checks += [(bn.weight.grad, ref_sd[name + ".weight"].grad, name + ".w"), (bn.bias.grad, ref_sd[name + ".bias"].grad, name + ".b")]
     for got, ref, name in checks:
         denom = max(float(ref.abs().max()), 1e-3 * scale)
-        assert float((got.cpu() - ref).abs().max()) / denom <= 1e-4, name      # a rare ReLU-kink flip costs ~1/sqrt(width)
+        if name == "Graph_BN.b" and training:
+            denom = scale         # a constant shift ahead of den1 -> bn_den1 is removed by that BatchNorm: analytically 0, noise
+        assert float((got.cpu() - ref).abs().max()) / denom <= 5 * TOL, name
     if training:
         for bn, name in zip(bns, ("Graph_BN", "bn_den1", "bn_den2")):
             assert int(bn.num_batches_tracked) == 1
@@ -871,11 +878,13 @@ def test_padded_widths_hiv_config_vs_oracle():
     """GraphConv_Layer.pad_widths: HIV widths (5 x 250 in layer 2: row stride 1 250 floats) on the padded layout --
     tensor-core GEMM + float4 kernels instead of the FFMA / scalar fallbacks; same parity bar."""
     from eagcn_b200 import layers as EL
-    EL.GraphConv_Layer.pad_widths = True
+    assert EL.GraphConv_Layer.pad_widths                      # the default
+    test_baseline_configs_forward_vs_oracle("config4 hiv widths 2-layer (padded)", "hiv", 12, 2, True)
+    EL.GraphConv_Layer.pad_widths = False                     # and the un-padded fallback engines (FFMA GEMM, scalar kernels)
     try:
-        test_baseline_configs_forward_vs_oracle("config4 hiv widths 2-layer (padded)", "hiv", 12, 2, True)
+        test_baseline_configs_forward_vs_oracle("config4 hiv widths 2-layer (fallback engines)", "hiv", 12, 2, True)
     finally:
-        EL.GraphConv_Layer.pad_widths = False
+        EL.GraphConv_Layer.pad_widths = True
 
 
 @pytest.mark.parametrize("case", golden_cases("stack_"))
@@ -912,7 +921,7 @@ def test_stack_vs_golden(case, pad):
                 bound = 2e-4 * scale
             assert float((got.cpu() - ref).abs().max()) <= bound, k
     finally:
-        EL.GraphConv_Layer.pad_widths = False
+        EL.GraphConv_Layer.pad_widths = True
 
 
 # ------------------------------------------------------------------ the BENCHMARKED configuration vs the oracle

@@ -113,3 +113,72 @@ def test_shard_partitions_batch():
     assert sum(p.B for p in parts) == 10
     assert np.array_equal(np.concatenate([p.adj for p in parts]), b.adj)
     assert all(p.N == b.N for p in parts)
+
+
+# ---------------------------------------------------------------- gradient arena + two-piece all-reduce
+def _arena_allreduce(rank, world):
+    from eagcn_b200.functional import GradArena
+    arena = GradArena(200, "cpu")
+    ar = PAR.ArenaAllReduce(arena, overlap=True)
+    out = []
+    for step in range(2):                                          # offsets repeat every step
+        ar.begin()
+        a = arena.take(10); a.fill_(float(rank + 1))               # "head + upper layers"
+        b = arena.take(33); b.copy_(torch.arange(33.0) * (rank + 1))
+        assert a.data_ptr() == arena.flat.data_ptr() and b.data_ptr() == arena.flat[16:].data_ptr()   # 64-byte aligned slices
+        ar.flush_async()                                           # first piece goes out while "layer 1" still computes
+        c = arena.take(5); c.fill_(10.0 * (rank + 1))
+        ar.finish()
+        assert arena.holds(a) and arena.holds(c) and not arena.holds(torch.zeros(3))
+        out.append((a.clone().numpy(), b.clone().numpy(), c.clone().numpy()))
+    return out
+
+
+def test_arena_allreduce_is_replica_mean():
+    out = _spawn(_arena_allreduce)
+    for r in (0, 1):
+        for a, b, c in out[r]:
+            np.testing.assert_allclose(a, np.full(10, 1.5))
+            np.testing.assert_allclose(b, np.arange(33.0) * 1.5)
+            np.testing.assert_allclose(c, np.full(5, 15.0))
+
+
+def test_grad_arena_measure_and_overflow():
+    from eagcn_b200.functional import GradArena
+    from eagcn_b200._lib import EagcnError
+    n = GradArena.measure(lambda: (GradArena.empty(10, "cpu"), GradArena.empty(20, "cpu")), "cpu")
+    assert n == 16 + 32 and GradArena.current is None
+    arena = GradArena(n, "cpu")
+    GradArena.current = arena
+    try:
+        x, y = GradArena.empty(10, "cpu"), GradArena.empty(20, "cpu")
+        assert arena.holds(x) and arena.holds(y) and arena.off == 48
+        with pytest.raises(EagcnError):
+            GradArena.empty(1, "cpu")
+    finally:
+        GradArena.current = None
+
+
+def test_shard_balanced_same_molecules_even_atoms():
+    world = 4
+    batches = [make_batch(32, "tox21", seed=10 + r) for r in range(world)]
+    parts = [PAR.shard_balanced(batches, r, world) for r in range(world)]
+    assert all(p.B == 32 for p in parts)
+    all_sizes = np.sort(np.concatenate([b.sizes for b in batches]))
+    assert np.array_equal(np.sort(np.concatenate([p.sizes for p in parts])), all_sizes)      # same multiset of molecules
+    atoms = [int(p.sizes.sum()) for p in parts]
+    contiguous = [int(b.sizes.sum()) for b in batches]
+    assert max(atoms) - min(atoms) <= max(8, (max(contiguous) - min(contiguous)) // 4)
+    # a molecule keeps its graph, features and codes
+    p0 = parts[0]
+    n = int(p0.sizes[0])
+    found = False
+    for b in batches:
+        for m in range(b.B):
+            if int(b.sizes[m]) == n and np.array_equal(b.adj[m, :n, :n], p0.adj[0, :n, :n]) and \
+                    np.array_equal(b.afm[m, :n], p0.afm[0, :n]) and np.array_equal(b.codes[m, :, :n, :n], p0.codes[0, :, :n, :n]):
+                found = True
+    assert found
+    # one rank: the identity
+    one = PAR.shard_balanced(batches[:1], 0, 1)
+    assert np.array_equal(one.adj, batches[0].adj) and np.array_equal(one.codes, batches[0].codes)

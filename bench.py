@@ -254,7 +254,7 @@ class Runner:
         self.dense_mb = float(np.mean([sum(t.numel() * t.element_size() for t in s.host_dense) for s in self.slots])) / 1e6
         self.launches_per_step = None
         self.ar = None
-        self.ar_mode = getattr(args, "allreduce", "graph") if world > 1 else "none"
+        self.ar_mode = getattr(args, "allreduce", "eager") if world > 1 else "none"
 
     def config(self):
         # described from the batches AS GENERATED for rank 0 (seeds 0..nb-1): the same numbers the reference arm prints
@@ -327,10 +327,12 @@ class Runner:
         self.grad_bytes = self.arena.off * 4
         ar, mode = self.ar, self.ar_mode
 
+        import torch.distributed as dist
+        arena = self.arena
+
         def all_reduce():                                     # after the replay: only the eager mode has work left
-            if mode == "eager":
-                ar.done = 0
-                ar.finish()
+            if mode == "eager":                               # ONE collective, replica mean taken by NCCL itself, same stream
+                dist.all_reduce(arena.flat[:arena.off], op=dist.ReduceOp.AVG)
         self.all_reduce = all_reduce
 
     def capture(self):
@@ -354,6 +356,21 @@ class Runner:
                 setattr(s, "g_" + name + "_out", out)
                 if name == "dense" and self.launches_per_step is None:
                     self.launches_per_step = _lib.launch_count() - c0
+        if self.world > 1 and self.ar_mode == "eager":
+            # N > 1: the step as TWO graphs -- packing of the batch (no parameter dependency) and everything else -- so that
+            # the previous step's gradient all-reduce, issued on a communication stream, overlaps the packing of this
+            # batch exactly as in a training loop: [pack(i+1) || all-reduce(i)] -> (optimiser) -> layers + head (i+1)
+            pool_pack2 = torch.cuda.graph_pool_handle()
+            for s in self.slots:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, pool=pool_pack2):
+                    s.dp_plan = self.GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=self.pool):
+                    self._begin()
+                    out = self._run(s.dp_plan, s)
+                s.g_dp_pack, s.g_dp_main, s.g_dp_out = g1, g2, out
+            self.comm = torch.cuda.Stream()
         if "zc" in self.layouts:
             # zero-copy layout, software-pipelined across steps: the packing of batch i+1 (its own graph, replayed on
             # the pack stream right after that batch's H2D) overlaps the layers / head of batch i.  Separate pools:
@@ -398,6 +415,16 @@ class Runner:
 
     def step_value(self, i):
         s = self.slots[i % self.nb]
+        if self.world > 1 and self.ar_mode == "eager":
+            import torch.distributed as dist
+            work = torch.cuda.current_stream()
+            s.g_dp_pack.replay()                              # beside the previous step's all-reduce (communication stream)
+            work.wait_stream(self.comm)                       # gradients of the previous step reduced (-> optimiser step)
+            s.g_dp_main.replay()
+            self.comm.wait_stream(work)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.arena.flat[:self.arena.off], op=dist.ReduceOp.AVG)
+            return
         s.g_dense.replay()
         self.all_reduce()
 
@@ -494,10 +521,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the single JSON line
-        # collectives are captured into the step's CUDA graph: the process group's watchdog must not poll CUDA events of
-        # captured work (PyTorch CUDA-graphs notes: disable NCCL async error handling before init_process_group)
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
+        if args.allreduce == "graph":
+            # collectives captured into the step's CUDA graph: the process group's watchdog must not poll CUDA events of
+            # captured work (PyTorch CUDA-graphs notes: disable NCCL async error handling before init_process_group)
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
         warm = torch.ones(1024, device=dev)
         for _ in range(3):                                    # communicator + AVG kernels warm before any capture
@@ -745,7 +772,9 @@ def run_b200(args):
         "step": "cuda-graph replay of pack + layers + head fwd/bwd" + ({
             "graph": " with the NCCL gradient all-reduce (AVG over the gradient arena, two pieces on a communication stream: "
                      "head + upper layers under layer 1's backward) captured inside the graph",
-            "eager": " + one NCCL all-reduce (AVG) over the gradient arena after the replay", "none": ""}[run.ar_mode]),
+            "eager": " as two graphs (packing | layers + head) + ONE NCCL all-reduce (AVG) over the gradient arena (kernels write "
+                     "gradients into one flat buffer: no packing copy) on a communication stream: the all-reduce of step i "
+                     "overlaps the packing of batch i+1, the layers of step i+1 wait for it", "none": ""}[run.ar_mode]),
         "sharding": getattr(args, "shard", "balanced") if world > 1 else "single rank",
         "grad_bytes": run.grad_bytes, "timed_passes_ms_per_step": passes,
         "e2e_pipeline": "H2D 2 batches ahead, packing 1 ahead, step: 3 streams",
@@ -1057,9 +1086,11 @@ def main():
                     help="workload: the headline Tox21 configuration (default; its line also carries lipo3 / hiv2 under "
                          "`configs`), one of the other BASELINE.json configurations alone, or the synthetic sweep")
     ap.add_argument("--nbatches", type=int, default=8)
-    ap.add_argument("--allreduce", default="graph", choices=["graph", "eager"],
-                    help="N > 1: gradient all-reduce captured inside the step graph and overlapped with layer 1's backward "
-                         "(graph) or one collective after each replay (eager)")
+    ap.add_argument("--allreduce", default="eager", choices=["graph", "eager"],
+                    help="N > 1: ONE NCCL all-reduce (AVG) over the gradient arena after each graph replay, on the step's own "
+                         "stream (eager, default: 24 us at 2 ranks) or captured inside the step graph in two pieces on a "
+                         "communication stream under layer 1's backward (graph: EXPERIMENTAL -- the capture hangs with "
+                         "torch 2.11 / NCCL 2.28 on the 2-GPU box, profiles/r02_dp2_notes.md)")
     ap.add_argument("--shard", default="balanced", choices=["balanced", "contiguous"],
                     help="N > 1: molecules of the global batch dealt to the ranks by size (equal molecules, near-equal atoms) "
                          "or every rank its own generated batch")

@@ -188,7 +188,8 @@ def algorithmic(wl, T, E, B, N):
     acc("pack_link_kernel", E * (4 + 4 + 4 + 2 * V), 0)
     F, D1, D2, NC = sum(wl["widths"][-1]), wl["den"][0], wl["den"][1], wl["nclass"]
     for (m, n, k) in ((B, D1, F), (B, D2, D1), (B, NC, D2)):      # y = x W, dx = dy W^T, dW = x^T dy of den1..den3
-        acc("mm_tile_kernel", 3 * 4 * (m * k + k * n + m * n), 3 * 2 * m * n * k)
+        for tag in ("mm_tile_nn", "mm_tile_nt", "mm_tile_tn"):    # one template instantiation (= kernel) per product kind
+            acc(tag, 4 * (m * k + k * n + m * n), 2 * m * n * k)
     for c in (F, D1, D2):
         acc("bn_act_fwd_kernel", 8 * B * c, 0)
         acc("bn_act_bwd_kernel", 12 * B * c, 0)
@@ -557,8 +558,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     wl = WORKLOADS[args.config]
+    if args.batch:                                               # diagnostic: the same workload at another batch size
+        wl = dict(wl, batch=args.batch, name=wl["name"].replace("_b%d" % wl["batch"], "_b%d" % args.batch) + "_diagnostic")
     NB = args.nbatches
-    headline = args.config == "tox21"
+    headline = args.config == "tox21" and not args.batch
     run = Runner(wl, dev, args, rank, world, NB, layouts=("dense", "codes", "zc") if headline else ("dense",))
     model = run.model
     if args.head != "auto":
@@ -1086,6 +1089,9 @@ def main():
                     help="workload: the headline Tox21 configuration (default; its line also carries lipo3 / hiv2 under "
                          "`configs`), one of the other BASELINE.json configurations alone, or the synthetic sweep")
     ap.add_argument("--nbatches", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=0,
+                    help="diagnostic (never a bench value): run the chosen workload at this batch size per GPU -- per-kernel "
+                         "table of a FILLED GPU, no e2e / extra configurations")
     ap.add_argument("--allreduce", default="eager", choices=["graph", "eager"],
                     help="N > 1: ONE NCCL all-reduce (AVG) over the gradient arena after each graph replay, on the step's own "
                          "stream (eager, default: 24 us at 2 ranks) or captured inside the step graph in two pieces on a "

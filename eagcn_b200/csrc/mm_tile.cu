@@ -312,7 +312,8 @@ extern "C" int eagcn_mm_tile(const void* A, int64_t lda, int transA, const void*
     }
     attr_set = true;
   }
-  EAGCN_PROF("mm_tile_kernel", stream);
+  // four template instantiations = four kernels (as the profilers list them): tag them apart
+  EAGCN_PROF(transA ? (transB ? "mm_tile_tt" : "mm_tile_tn") : (transB ? "mm_tile_nt" : "mm_tile_nn"), stream);
   EAGCN_LAUNCH(kern, dim3(gx, gy, (unsigned)ns), kMmThreads, kMmSmemBytes, (cudaStream_t)stream)(g);
   EAGCN_LAUNCH_CHECK();
   return 0;

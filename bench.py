@@ -292,7 +292,44 @@ class Runner:
 
     def step_dense(self, s):
         self._begin()
-        return self._run(self.GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap), s)
+        plan = self.GraphPlan.build(s.dev_dense[0], s.dev_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
+        if getattr(self, "global_bn", False):                 # BatchNorm population / padded width of the GLOBAL batch
+            plan.m_total, plan.n_pad = s.m_total_g, s.n_pad_g
+        return self._run(plan, s)
+
+    def measure_global_bn(self, steps, local=0):
+        """bn_sync = 'global' (SURVEY 8(e)): BatchNorm statistics of the graph-conv layers and of the head all-reduced over
+        the ranks, population and padded width of the global batch -- the reference's single-process big-batch semantics
+        (checked by dp_parity).  Eager launches: the per-layer statistic all-reduces are NCCL calls between kernels."""
+        import torch.distributed as dist
+        from eagcn_b200 import parallel as PAR
+        for s in self.slots:
+            t = torch.tensor([s.hb.B, s.hb.N], dtype=torch.int64, device=self.dev)
+            tb = t.clone()
+            dist.all_reduce(tb[:1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
+            s.n_pad_g = int(t[1]); s.m_total_g = int(tb[0]) * s.n_pad_g
+        PAR.set_bn_sync(self.model, "global")
+        self.global_bn = True
+        try:
+            flat = torch.zeros(sum(p.numel() for p in self.gparams), device=self.dev)
+
+            def step(i):                                      # (the head's SyncBatchNorm gradients are torch-made: pack)
+                self.step_dense(self.slots[i % self.nb])
+                torch.cat([p.grad.reshape(-1) for p in self.gparams], out=flat)
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            pipe, self.pack_stream, comm, self.comm = getattr(self, "pack_stream", None), None, getattr(self, "comm", None), None
+            try:
+                ms, _ = self.timed(step, steps, 5, local)
+            finally:
+                self.pack_stream, self.comm = pipe, comm
+        finally:
+            self.global_bn = False
+            PAR.set_bn_sync(self.model, "local")
+        ms_step = ms / steps
+        return {"value": self.wl["batch"] * self.world / (ms_step * 1e-3), "unit": "molecules/s", "ms_per_step": ms_step,
+                "steps": steps, "mode": "eager launches (not a CUDA graph): 2 statistic all-reduces per layer and direction + "
+                                        "SyncBatchNorm in the head + the gradient all-reduce"}
 
     def step_zero_copy(self, s):
         """dense reference layout left in PINNED HOST memory: only adj + atom features are copied, the one-hot
@@ -691,6 +728,13 @@ def run_b200(args):
     B = wl["batch"]
     value = B * world / (ms_step * 1e-3)
 
+    global_bn = None
+    if world > 1 and not args.layers_only and not args.no_global_bn:
+        try:
+            global_bn = run.measure_global_bn(max(10, min(args.steps, 30)), local)
+        except Exception as e:
+            global_bn = {"error": repr(e)[:300]}
+
     if args.layers_only:
         if rank == 0:
             print(json.dumps({"diagnostic": "layers-only (no dense head)", "ms_per_step": ms_step, "value": value,
@@ -853,6 +897,8 @@ def run_b200(args):
             line["configs"] = extra
         if dp_parity is not None:
             line["dp_parity"] = dp_parity
+        if global_bn is not None:
+            line["bn_sync_global"] = global_bn
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -1143,6 +1189,7 @@ def main():
                          "or every rank its own generated batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the lipo3 / hiv2 configurations")
+    ap.add_argument("--no-global-bn", action="store_true", help="N > 1: skip the bn_sync = 'global' throughput leg")
     ap.add_argument("--head", default="auto", choices=["auto", "torch"],
                     help="dense head: CUDA kernels (auto) or stock PyTorch ops")
     ap.add_argument("--layers-only", action="store_true",

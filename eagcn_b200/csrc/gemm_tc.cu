@@ -235,9 +235,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      int s = 0, ph = 0;                               // running stage / phase: no integer division per k-block
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % g.stages, it = kb / g.stages;
-        if (it > 0) mbar_wait(&bar_empty[s], (it - 1) & 1);
+        if (kb >= g.stages) mbar_wait(&bar_empty[s], ph ^ 1);
         if (tr && kb < kTraceKb) g.trace[8 + kb * kTracePer + 0] = clock64();
         if (!tn) {
           mbar_expect_tx(&bar_full[s], bytesA + (g.b_split ? 2 : 1) * bytesB);
@@ -250,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int i = 0; i < nboxA; ++i) tma_load_2d(&mapA, &bar_full[s], sA_hi(s) + i * box_bytes, m0 + 32 * i, krow);
           for (int i = 0; i < nboxB; ++i) tma_load_2d(&mapB, &bar_full[s], sB_hi(s) + i * box_bytes, n0 + 32 * i, krow);
         }
+        if (++s == g.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -294,9 +295,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ===================== transform (hi/lo split), then epilogue =====================
     const int xt = threadIdx.x - 64;                              // 0..255
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % g.stages, it = kb / g.stages;
-      mbar_wait(&bar_full[s], it & 1);
+    int s = 0, ph = 0;                                            // running stage / phase (the kb % stages, kb / stages pair
+                                                                  // was 10 % of this kernel's executed instructions)
+    for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == g.stages ? 0 : s + 1), ph ^= (s == 0)) {
+      mbar_wait(&bar_full[s], ph);
       if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * kTracePer + 1] = clock64();
       if (tn) {                                                    // boxes outside the tensors were not loaded
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);

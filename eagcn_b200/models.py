@@ -186,15 +186,34 @@ class EAGCNStack(nn.Module):
             x = EF.bn_act(x, self.bn_den2, self.training, relu=True)                # models.py:119
             x = self.den3(x)
             return x, atom_representations, graph_representation
-        x = self.Graph_BN(x)                                                        # models.py:112
+        if self.head_bn == "sync":
+            # global-batch BatchNorm across data-parallel ranks (eagcn_b200.parallel.set_bn_sync): the head's three
+            # BatchNorm1d see the GLOBAL batch like the reference's single process does (models.py:112,115,119)
+            gbn, bn1, bn2 = (self._sync_bn(bn) for bn in bns)
+        else:
+            gbn, bn1, bn2 = bns
+        x = gbn(x)                                                                  # models.py:112
         x = self.den1(x)
-        x = F.relu(self.bn_den1(x))
+        x = F.relu(bn1(x))
         x = F.dropout(x, p=self.dropout, training=self.training)
         x = self.den2(x)
         graph_representation = x
-        x = F.relu(self.bn_den2(x))
+        x = F.relu(bn2(x))
         x = self.den3(x)
         return x, atom_representations, graph_representation
+
+    def _sync_bn(self, bn):
+        """torch.nn.SyncBatchNorm over the SAME parameter / buffer tensors as ``bn`` (state_dict keys unchanged); the
+        wrappers live outside the module tree."""
+        cache = self.__dict__.setdefault("_sync_bn_cache", {})
+        sbn = cache.get(id(bn))
+        if sbn is None:
+            sbn = nn.SyncBatchNorm(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats)
+            sbn.weight, sbn.bias = bn.weight, bn.bias
+            sbn.running_mean, sbn.running_var, sbn.num_batches_tracked = bn.running_mean, bn.running_var, bn.num_batches_tracked
+            cache[id(bn)] = sbn
+        sbn.train(self.training)
+        return sbn
 
 
 class EAGCN(EAGCNStack):

@@ -187,6 +187,14 @@ def set_bn_sync(model, mode: str, group=None):
     for m in model.modules():
         if isinstance(m, GraphConv_Layer):
             m.stat_allreduce = hook
+    # the read-out head's three BatchNorm1d (models.py:112,115,119): SyncBatchNorm over the same parameters / buffers
+    if hasattr(model, "head_bn"):
+        if mode == "global":
+            if model.head_bn != "sync":
+                model._head_bn_local = model.head_bn
+            model.head_bn = "sync"
+        elif model.head_bn == "sync":
+            model.head_bn = getattr(model, "_head_bn_local", "cuda")
 
 
 def global_population(local_B: int, n_pad: int, group=None, device=None):

@@ -14,15 +14,6 @@ from eagcn_b200.data import make_batch, shard
 from eagcn_b200.plan import GraphPlan
 
 
-def run(model, mb, dev, m_total=None, n_pad=None):
-    dense = [torch.from_numpy(a).to(dev) for a in mb.dense()]
-    plan = GraphPlan.build(dense[0], dense[2:]).check()
-    if m_total is not None:
-        plan.m_total, plan.n_pad = m_total, n_pad
-    out, _, _ = model(plan, dense[1], size=torch.from_numpy(mb.sizes).to(dev))
-    return out
-
-
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -31,88 +22,74 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     res = check(dev, rank, world)
     if rank == 0:
-        print(f"DP-{world} global-BN vs single process: atoms {res['atoms']:.2e}  layer grads {res['layer_grads']:.2e}  "
-              f"running stats {res['running_stats']:.2e}")
+        print(f"DP-{world} global-BN vs single process: atoms {res['atoms']:.2e}  outputs {res['outputs']:.2e}  all grads "
+              f"{res['all_grads']:.2e}  running stats {res['running_stats']:.2e}  {res['mismatches']}")
         assert res["ok"], "data-parallel parity failed"
         print("DP PARITY OK")
     dist.destroy_process_group()
 
 
 def check(dev, rank, world):
-    """N-rank data parallel (contiguous shards, global-batch BatchNorm, ONE flat gradient all-reduce) against the single
-    process on the concatenated batch, on this process group.  Returns max relative deviations (max over ranks)."""
+    """N-rank data parallel (contiguous shards, global-batch BatchNorm in the graph-conv layers AND the read-out head, ONE
+    flat gradient all-reduce) against the single process on the concatenated batch, on this process group: the FULL model
+    (layers + read-out + head), loss = sum of the outputs.  Returns max relative deviations (max over ranks)."""
     full = make_batch(32 * world, "tox21", seed=7)
     torch.manual_seed(0)
     model = EM.EAGCNStack(30, 24, [(16,) * 5, (24,) * 5], 32, 16, 3, dropout=0.0).to(dev)
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     model.train()
 
-    # (b) single process, whole batch (head BatchNorms see the whole batch)
-    for p in model.parameters(): p.grad = None
-    out_full = run(model, full, dev)
-    out_full.sum().backward()
-    g_full = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
-    rs_full = {k: v.clone() for k, v in model.state_dict().items() if "running" in k and "layer" in k}
+    def fwd_bwd(mb, m_total=None, n_pad=None):
+        for p in model.parameters():
+            p.grad = None
+        dense = [torch.from_numpy(a).to(dev) for a in mb.dense()]
+        plan = GraphPlan.build(dense[0], dense[2:]).check()
+        if m_total is not None:
+            plan.m_total, plan.n_pad = m_total, n_pad
+        out, atoms, _ = model(plan, dense[1], size=torch.from_numpy(mb.sizes).to(dev))
+        out.sum().backward()
+        named = [(n, p) for n, p in model.named_parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for _, p in named])
+        rs = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
+        return out.detach(), atoms.materialize().to(dev), flat, rs, named
 
-    # (a) data parallel: shard + global-batch statistics in the graph-conv layers.  The dense head's
-    # nn.BatchNorm1d would need SyncBatchNorm for exact equality, so compare the atom representations
-    # (pure hot-path output) and the hot-path parameter gradients driven by a sum-of-atoms loss.
+    # (b) single process, whole batch
+    out_full, atoms_full, flat_full, rs_one, named = fwd_bwd(full)
+
+    # (a) data parallel: shard + global-batch statistics everywhere + ONE flat gradient all-reduce (sum over shards)
     model.load_state_dict(sd0)
     PAR.set_bn_sync(model, "global")
     mb = shard(full, rank, world)
     M, Npad = PAR.global_population(mb.B, mb.N, device=dev)
     lo = rank * ((full.B + world - 1) // world)
-
-    def atoms_loss(m, batch, m_total=None, n_pad=None):
-        from eagcn_b200 import functional as EF
-        from eagcn_b200.layers import PackedRows
-        dense = [torch.from_numpy(a).to(dev) for a in batch.dense()]
-        plan = GraphPlan.build(dense[0], dense[2:]).check()
-        if m_total is not None:
-            plan.m_total, plan.n_pad = m_total, n_pad
-        h = PackedRows(EF.gather_rows(plan, dense[1]), plan)
-        for layer in m.conv_layers:
-            h, _ = layer(plan, h)
-        return h.dense()
-
-    for p in model.parameters(): p.grad = None
-    x_dp = atoms_loss(model, mb, M, Npad)
-    w = torch.linspace(0.5, 1.5, x_dp.shape[2], device=dev)
-    (x_dp * w).sum().backward()
-    params = [p for n, p in model.named_parameters() if n.startswith("layer") and p.grad is not None]
-    bucket_flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(bucket_flat)                                  # ONE flat gradient all-reduce (sum over shards)
-    rs_dp = {k: v.clone() for k, v in model.state_dict().items() if "running" in k and "layer" in k}
-
-    model.load_state_dict(sd0)
+    out_dp, atoms_dp, flat_dp, rs_dp, _ = fwd_bwd(mb, M, Npad)
+    dist.all_reduce(flat_dp)
     PAR.set_bn_sync(model, "local")
-    for p in model.parameters(): p.grad = None
-    x_full = atoms_loss(model, full)
-    (x_full * w).sum().backward()
-    flat_full = torch.cat([p.grad.reshape(-1) for n, p in model.named_parameters() if n.startswith("layer") and p.grad is not None])
-    rs_one = {k: v.clone() for k, v in model.state_dict().items() if "running" in k and "layer" in k}
+    model.load_state_dict(sd0)
 
-    ex = float((x_dp - x_full[lo:lo + mb.B]).abs().max() / x_full.abs().max())
-    eg = float((bucket_flat - flat_full).abs().max() / flat_full.abs().max())
-    er = max(float((rs_dp[k] - rs_one[k]).abs().max() / rs_one[k].abs().max().clamp_min(1e-12)) for k in rs_one)
-    res = torch.tensor([ex, eg, er], device=dev)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    eo = rel(out_dp, out_full[lo:lo + mb.B])
+    ex = rel(atoms_dp, atoms_full[lo:lo + mb.B])
+    eg = rel(flat_dp, flat_full)
+    er = max(rel(rs_dp[k], rs_one[k]) for k in rs_one)
+    res = torch.tensor([ex, eg, er, eo], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     worst = []
     if rank == 0:
-        names = [n for n, p in model.named_parameters() if n.startswith("layer") and p.grad is not None]
         off = 0
-        for n, p in zip(names, params):
+        for n, p in named:
             k = p.numel()
-            e = float((bucket_flat[off:off + k] - flat_full[off:off + k]).abs().max() / flat_full.abs().max())
+            e = float((flat_dp[off:off + k] - flat_full[off:off + k]).abs().max() / flat_full.abs().max())
             if e > 5e-5:
                 worst.append((n, e))
             off += k
-    PAR.set_bn_sync(model, "local")
-    a, g, r = float(res[0]), float(res[1]), float(res[2])
-    return {"ranks": world, "global_batch": full.B, "bn_sync": "global", "atoms": a, "layer_grads": g, "running_stats": r,
-            "ok": bool(a <= 1e-5 and g <= 5e-5 and r <= 1e-5), "mismatches": worst[:4],
-            "what": "N-rank shards + global-batch BatchNorm + one flat gradient all-reduce vs the single process on the "
-                    "concatenated batch (max relative deviation over ranks)"}
+    a, g, r, o = (float(x) for x in res)
+    return {"ranks": world, "global_batch": full.B, "bn_sync": "global (layers + head)", "atoms": a, "outputs": o,
+            "all_grads": g, "layer_grads": g, "running_stats": r,
+            "ok": bool(a <= 1e-5 and o <= 5e-5 and g <= 5e-5 and r <= 1e-5), "mismatches": worst[:4],
+            "what": "N-rank shards + global-batch BatchNorm (graph-conv layers and the head's three BatchNorm1d) + one flat "
+                    "gradient all-reduce vs the single process on the concatenated batch: full model, loss = sum of outputs "
+                    "(max relative deviation over ranks)"}
 
 
 if __name__ == "__main__":

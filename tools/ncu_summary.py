@@ -5,7 +5,8 @@ profiles/traffic.json (DRAM read + write bytes per launch and kernel: bench.py's
     ncu -i gpurun_out/<tag>_prof.ncu-rep --page raw --csv > /tmp/raw.csv
     python tools/ncu_summary.py /tmp/raw.csv profiles/<tag>_ncu_full_summary.csv [profiles/traffic.json]
 
-The launch order of the tcgen05 GEMM inside one eager step of bench.py is: Z1 (nn), Z2 (nn), dH2 (nt), dW2 (tn), dW1 (tn).
+Round 2: the forward projections live inside layer_fwd_fused_kernel; the launch order of gemm_tc_kernel inside one eager
+step of bench.py is dH2 (nt), dW2 (tn), dW1 (tn).  mm_tile_kernel<..> instantiations are tagged nn / nt / tn / tt.
 """
 import collections
 import csv
@@ -42,7 +43,14 @@ def main():
     mr, mw = mult[units[ir]], mult[units[iw]]
     by = collections.defaultdict(list)
     for r in rows[2:]:
-        k = re.match(r"(?:void )?(?:eagcn::)?(?:tc::)?(\w+)", r[iname]).group(1)
+        k = re.match(r"(?:void )?(?:eagcn::)?(?:tc::|fz::)?(\w+)", r[iname]).group(1)
+        if k == "layer_fwd_fused_kernel":
+            k = "layer_fwd_fused"
+        if k == "mm_tile_kernel":
+            m = re.search(r"mm_tile_kernel<\(bool\)(\d), \(bool\)(\d)>|mm_tile_kernel<(true|false), (true|false)>", r[iname])
+            if m:
+                a, b = (m.group(1), m.group(2)) if m.group(1) is not None else (str(int(m.group(3) == "true")), str(int(m.group(4) == "true")))
+                k = "mm_tile_" + ("n" if a == "1" else "t") + ("t" if b == "1" else "n")
         by[TAGS.get(k, k)].append(float(r[ir]) * mr + float(r[iw]) * mw)
     out = {"_source": f"{sys.argv[2]} (ncu --set full --clock-control none, eager steps, cold caches): dram__bytes_read.sum + "
                       "dram__bytes_write.sum per launch, averaged over the captured launches of each kernel"}

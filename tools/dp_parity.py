@@ -71,7 +71,9 @@ def check(dev, rank, world):
     eo = rel(out_dp, out_full[lo:lo + mb.B])
     ex = rel(atoms_dp, atoms_full[lo:lo + mb.B])
     eg = rel(flat_dp, flat_full)
-    er = max(rel(rs_dp[k], rs_one[k]) for k in rs_one)
+    ers = {k: rel(rs_dp[k], rs_one[k]) for k in rs_one}
+    er = max(ers.values())
+    worst_rs = sorted(ers.items(), key=lambda kv: -kv[1])[:3]
     res = torch.tensor([ex, eg, er, eo], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     worst = []
@@ -87,6 +89,7 @@ def check(dev, rank, world):
     return {"ranks": world, "global_batch": full.B, "bn_sync": "global (layers + head)", "atoms": a, "outputs": o,
             "all_grads": g, "layer_grads": g, "running_stats": r,
             "ok": bool(a <= 1e-5 and o <= 5e-5 and g <= 5e-5 and r <= 1e-5), "mismatches": worst[:4],
+            "worst_running_stats": [(k, float(v)) for k, v in worst_rs],
             "what": "N-rank shards + global-batch BatchNorm (graph-conv layers and the head's three BatchNorm1d) + one flat "
                     "gradient all-reduce vs the single process on the concatenated batch: full model, loss = sum of outputs "
                     "(max relative deviation over ranks)"}

@@ -429,10 +429,10 @@ class Runner:
             # zero-copy layout, software-pipelined across steps: the packing of batch i+1 (its own graph, replayed on
             # the pack stream right after that batch's H2D) overlaps the layers / head of batch i.  Separate pools:
             # the two graph families run concurrently.
-            pool_pack = torch.cuda.graph_pool_handle()
-            for s in self.slots:
+            pools_pack = [torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle()]    # neighbours may pack concurrently
+            for si, s in enumerate(self.slots):
                 g1 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1, pool=pool_pack):
+                with torch.cuda.graph(g1, pool=pools_pack[si % 2]):
                     s.zc_plan = self.GraphPlan.build(s.dev_dense[0], s.host_dense[2:], t_cap=s.t_cap, e_cap=s.e_cap)
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, pool=self.pool, capture_error_mode="thread_local"):
@@ -750,10 +750,11 @@ def run_b200(args):
         # stream) overlap.  Every step still pays one full H2D + one D2H inside the timed region and ends with a host
         # sync on its result.
         copy_stream = torch.cuda.Stream()
-        pack_stream = torch.cuda.Stream()
+        npk = max(1, min(args.e2e_pack_streams, 2))
+        pack_streams = [torch.cuda.Stream() for _ in range(npk)]
         copied = [torch.cuda.Event() for _ in range(NB)]
         ready = [torch.cuda.Event() for _ in range(NB)]
-        depth = max(1, min(args.e2e_depth, NB - 1))
+        depth = max(1, min(args.e2e_depth + (npk - 1), NB - 2))
 
         def make_e2e(layout):
             state = {"copied": -1, "ready": -1, "first": True}
@@ -776,10 +777,11 @@ def run_b200(args):
             def make_ready(i):
                 s = slots[i % NB]
                 if layout == "zc":
-                    with torch.cuda.stream(pack_stream):
-                        pack_stream.wait_event(copied[i % NB])
+                    pk = pack_streams[i % npk]                    # with two pack streams the gathers of batches i+1, i+2 overlap
+                    with torch.cuda.stream(pk):
+                        pk.wait_event(copied[i % NB])
                         s.g_zc_pack.replay()                      # graph plan of this batch, gathered from host memory
-                        ready[i % NB].record(pack_stream)
+                        ready[i % NB].record(pk)
                 state["ready"] = i
 
             def advance(i_copy, i_ready):
@@ -794,7 +796,8 @@ def run_b200(args):
                     state["first"] = False
                     state["copied"] = state["ready"] = i - 1
                     copy_stream.wait_stream(torch.cuda.current_stream())
-                    pack_stream.wait_stream(torch.cuda.current_stream())
+                    for pk in pack_streams:
+                        pk.wait_stream(torch.cuda.current_stream())
                 advance(i, i)
                 torch.cuda.current_stream().wait_event(ready[i % NB] if layout == "zc" else copied[i % NB])
                 g, gout = {"dense": (s.g_dense, s.g_dense_out), "zc": (s.g_zc_main, s.g_zc_main_out),
@@ -802,7 +805,7 @@ def run_b200(args):
                 g.replay()
                 run.all_reduce()
                 out_host.copy_(gout, non_blocking=True)
-                advance(i + depth, i + 1)                         # prefetch while this step runs
+                advance(i + depth, i + npk)                       # prefetch while this step runs
                 torch.cuda.current_stream().synchronize()         # the user reads this step's result
             return step
 
@@ -865,7 +868,8 @@ def run_b200(args):
                      "layers of step i+1 wait for it", "none": ""}[run.ar_mode]),
         "sharding": getattr(args, "shard", "balanced") if world > 1 else "single rank",
         "grad_bytes": run.grad_bytes, "timed_passes_ms_per_step": passes,
-        "e2e_pipeline": "H2D 2 batches ahead, packing 1 ahead, step: 3 streams",
+        "e2e_pipeline": f"H2D {args.e2e_depth + args.e2e_pack_streams - 1} batches ahead, packing {args.e2e_pack_streams} ahead "
+                        f"({args.e2e_pack_streams} pack stream(s)), step",
     }
     if rank == 0 and world == 1 and headline and not args.no_extra:
         # the other single-GPU BASELINE.json configurations: value + dominant-kernel roofline each
@@ -1209,6 +1213,8 @@ def main():
                     help="1: statistics reduction fused into the forward BatchNorm apply kernel; 0: separate kernels")
     ap.add_argument("--fwd-fused", type=int, default=1, choices=[0, 1],
                     help="1: one fused kernel for projection + attention + aggregation per layer; 0: GEMM + aggregation kernels")
+    ap.add_argument("--e2e-pack-streams", type=int, default=1, choices=[1, 2],
+                    help="e2e (zero-copy layout): graph plans of this many upcoming batches gathered concurrently")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2],
                     help="e2e input pipeline: H2D copies issued this many batches ahead")
     ap.add_argument("--agg", default="tile", choices=["tile", "generic"], help="aggregation kernels")

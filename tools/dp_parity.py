@@ -72,8 +72,8 @@ def check(dev, rank, world):
     ex = rel(atoms_dp, atoms_full[lo:lo + mb.B])
     eg = rel(flat_dp, flat_full)
     # running means that are analytically 0 (bn_den1: its input is a linear map of Graph_BN's zero-mean output) hold
-    # rounding noise ~1e-9: measure running statistics against a floor of 1e-3 (running variances start at 1)
-    ers = {k: float((rs_dp[k] - rs_one[k]).abs().max() / rs_one[k].abs().max().clamp_min(1e-3)) for k in rs_one}
+    # rounding noise ~1e-8: measure running statistics against a floor of 1e-2 (running variances start at 1)
+    ers = {k: float((rs_dp[k] - rs_one[k]).abs().max() / rs_one[k].abs().max().clamp_min(1e-2)) for k in rs_one}
     er = max(ers.values())
     worst_rs = sorted(ers.items(), key=lambda kv: -kv[1])[:3]
     res = torch.tensor([ex, eg, er, eo], device=dev)

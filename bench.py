@@ -882,6 +882,24 @@ def run_b200(args):
             except Exception as e:                              # a failed extra config must not cost the headline line
                 extra[key] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
+        # BASELINE.json configs[1] names a reduced-precision ("bf16") forward+backward: the headline workload once more
+        # with ONE TF32 tensor-core pass instead of the fp32-faithful three -- ~1e-3 relative error, OUTSIDE the parity bar,
+        # reported beside the strict mode, never as `value`
+        try:
+            EF.set_tc_precision("tf32")
+            v = measure_extra("tox21", dev, args, local, wl=dict(wl, name=wl["name"] + "_tf32_single_pass"))
+            v["precision"] = ("ONE TF32 pass (10-bit mantissa operands, fp32 accumulate): ~1e-3 relative error, not within the "
+                              "1e-5 parity bar; the headline `value` is the fp32-faithful 3xTF32 mode")
+            if v.get("roofline") and "frac_of_3xtf32_ceiling" in v["roofline"]:
+                r = v["roofline"]
+                r["frac_of_tf32_ceiling"] = r.pop("frac_of_3xtf32_ceiling") / 3.0      # one pass: the ceiling is 1/2 of bf16
+                r["note"] = "single TF32 pass: the ceiling of `frac` against the bf16 peak is 1/2"
+            extra["tox21_tf32_single_pass"] = v
+        except Exception as e:
+            extra["tox21_tf32_single_pass"] = {"error": repr(e)[:300]}
+        finally:
+            EF.set_tc_precision("fp32x3")
+        torch.cuda.empty_cache()
     else:
         cfg0 = run.config()
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -908,9 +926,9 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def measure_extra(key, dev, args, local):
+def measure_extra(key, dev, args, local, wl=None):
     """One of the other BASELINE.json single-GPU configurations: graph-replayed value (median of 3 passes) + roofline."""
-    wl = WORKLOADS[key]
+    wl = wl or WORKLOADS[key]
     r = Runner(wl, dev, args, 0, 1, 4)
     r.make_bucket()
     r.capture()

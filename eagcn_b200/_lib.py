@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -100,6 +100,8 @@ _PROTOS = {
     "eagcn_set_fuse_mode": (c_int, [c_int]),
     "eagcn_get_fuse_mode": (c_int, []),
     "eagcn_set_tc_bk": (c_int, [c_int]),
+    "eagcn_set_tc_passes": (c_int, [c_int]),
+    "eagcn_get_tc_passes": (c_int, []),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

@@ -42,6 +42,12 @@ extern "C" int eagcn_set_tc_bk(int bk) {
   eagcn::tc::nt_bk_override() = bk;
   return 0;
 }
+extern "C" int eagcn_set_tc_passes(int passes) {
+  if (passes != 1 && passes != 3) return EAGCN_E_ARG;
+  eagcn::tc::tc_passes() = passes;
+  return 0;
+}
+extern "C" int eagcn_get_tc_passes(void) { return eagcn::tc::tc_passes(); }
 extern "C" int eagcn_set_pdl(int on) { eagcn::pdl_mode() = on ? 1 : 0; return 0; }
 extern "C" int eagcn_get_pdl(void) { return eagcn::pdl_mode(); }
 extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,

@@ -35,6 +35,7 @@ struct FusedArgs {
   uint32_t tmem_cols;
   int n_pad, want_stats, save_z;
   int nv_max;                        // most views any column chunk overlaps (sizes the per-view edge-weight staging)
+  int passes;                        // 3: fp32-faithful 3xTF32 (default); 1: single TF32 pass (tc::tc_passes())
   uint32_t graph_off;                // byte offset of the graph warps' staging region in dynamic shared memory
   const float* ball;
   const float* sig;
@@ -85,10 +86,11 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   // pointer would lose the address space and turn every access below into a generic LD.E / ST.E instead of LDS / STS
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t bytesA = BM * bk * 4, bytesB = (uint32_t)g.BN * bk * 4;
-  const uint32_t stage_bytes = 2 * bytesA + 2 * bytesB;
+  const bool one = g.passes == 1;                       // single TF32 pass: [A | B] per stage, no lo copies
+  const uint32_t stage_bytes = one ? bytesA + bytesB : 2 * bytesA + 2 * bytesB;
   auto sA_hi = [&](int s) { return base + (size_t)s * stage_bytes; };
   auto sA_lo = [&](int s) { return base + (size_t)s * stage_bytes + bytesA; };
-  auto sB_hi = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA; };
+  auto sB_hi = [&](int s) { return base + (size_t)s * stage_bytes + (one ? bytesA : 2 * bytesA); };
   auto sB_lo = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA + bytesB; };
   // graph warps' region (NOT overlapping the pipeline stages: filled while the main loop runs)
   int* s_col = reinterpret_cast<int*>(base + g.graph_off);                      // [kEdgeCap] neighbour row inside the tile
@@ -134,10 +136,10 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       int s = 0, ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (kb >= g.stages) mbar_wait(&bar_empty[s], ph ^ 1);
-        mbar_expect_tx(&bar_full[s], bytesA + 2 * bytesB);
+        mbar_expect_tx(&bar_full[s], bytesA + (one ? 1 : 2) * bytesB);
         tma_load_2d(&mapA, &bar_full[s], sA_hi(s), kb * bk, row0);
         tma_load_2d(&mapB, &bar_full[s], sB_hi(s), kb * bk, n0);
-        tma_load_2d(&mapB2, &bar_full[s], sB_lo(s), kb * bk, n0);
+        if (!one) tma_load_2d(&mapB2, &bar_full[s], sB_lo(s), kb * bk, n0);
         if (++s == g.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -155,8 +157,10 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         for (int k = 0; k < BK / UK; ++k) {
           const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          umma_tf32(tmem_c, dAl + adv, dBh + adv, idesc, acc);
-          umma_tf32(tmem_c, dAh + adv, dBl + adv, idesc, 1u);
+          if (!one) {
+            umma_tf32(tmem_c, dAl + adv, dBh + adv, idesc, acc);
+            umma_tf32(tmem_c, dAh + adv, dBl + adv, idesc, 1u);
+          }
           umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);
         }
         umma_commit(&bar_empty[s]);
@@ -229,7 +233,7 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       int s = 0, ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&bar_full[s], ph);
-        split_tile(reinterpret_cast<uint4*>(sA_hi(s)), reinterpret_cast<uint4*>(sA_lo(s)), (int)(bytesA / 16), et);
+        if (!one) split_tile(reinterpret_cast<uint4*>(sA_hi(s)), reinterpret_cast<uint4*>(sA_lo(s)), (int)(bytesA / 16), et);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_ready[s]);
@@ -247,8 +251,12 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         uint32_t r[32], q[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
         tmem_ld32(taddr, r);
-        tmem_ld32(taddr + (uint32_t)g.BN, q);
+        if (!one) tmem_ld32(taddr + (uint32_t)g.BN, q);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (one) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q[j] = 0u;                 // +0.0f: no correction accumulator in the single-pass mode
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (c0 + 4 * j < g.BN) {
@@ -391,7 +399,7 @@ static size_t graph_bytes(int nv_max) {
   return (size_t)kEdgeCap * 4 + (size_t)nv_max * (kEdgeCap + EAGCN_ROW_TILE + EAGCN_SIG_STRIDE) * 4 + 16;
 }
 static size_t front_bytes(int BN, int stages) {                    // pipeline stages, re-used by the Z tile + statistics
-  const size_t pipe = (size_t)stages * (2 * BM * BK * 4 + 2 * BN * BK * 4);
+  const size_t pipe = (size_t)stages * (tc_passes() == 1 ? 1 : 2) * (BM * BK * 4 + BN * BK * 4);
   const size_t epi = (size_t)EAGCN_ROW_TILE * (BN + 4) * 4 + (size_t)kRedFloats * 4;
   return ((pipe > epi ? pipe : epi) + 15) & ~(size_t)15;
 }
@@ -417,7 +425,7 @@ int layer_fwd_fused(const eagcn_plan_t* plan, const PlanDev& p, const LayerDev& 
   const int BN = pick_chunk(C, p.t_cap);
   const int num_kb = (K + BK - 1) / BK;
   const int nv_max = max_views_per_chunk(L, BN);
-  int stages = pick_stages(BN, num_kb);
+  int stages = pick_stages(BN, num_kb, BK, tc_passes());
   while (stages > 2 && front_bytes(BN, stages) + graph_bytes(nv_max) + 1024 > (size_t)kSmemBudget) --stages;
   const float* wT = (const float*)w->wallT;
   CUtensorMap mA, mB, mB2;
@@ -431,6 +439,7 @@ int layer_fwd_fused(const eagcn_plan_t* plan, const PlanDev& p, const LayerDev& 
   g.want_stats = (w->training & 1) ? 1 : 0;
   g.save_z = (w->training & 16) ? 0 : 1;
   g.nv_max = nv_max;
+  g.passes = tc_passes();
   g.graph_off = (uint32_t)front_bytes(BN, stages);
   g.ball = (const float*)w->ball; g.sig = (const float*)w->sig;
   g.Z = (float*)w->Z; g.Y = (float*)w->Y; g.invR = (float*)w->invR; g.partial = (float*)w->partial;

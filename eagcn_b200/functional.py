@@ -799,6 +799,13 @@ def set_gemm_engine(name: str):
     check(lib().eagcn_set_gemm_mode({"tcgen05": 0, "ffma": 1, "tcgen05-nt": 2}[name]), "eagcn_set_gemm_mode")
 
 
+def set_tc_precision(name: str):
+    """'fp32x3' (default: hi/lo-compensated 3xTF32, fp32-faithful, the parity mode) or 'tf32' (ONE TF32 tensor-core pass on
+    the raw operands: ~1e-3 relative error, NOT within the 1e-5 parity bar -- the analogue of BASELINE.json's "bf16"
+    configuration, for throughput reporting beside the strict mode)."""
+    check(lib().eagcn_set_tc_passes({"fp32x3": 3, "tf32": 1}[name]), "eagcn_set_tc_passes")
+
+
 def set_agg_engine(name: str):
     """'tile' (default: shared-memory tile aggregation kernels, BatchNorm backward folded into the backward one) or
     'generic' (warp-per-row kernels reading neighbours through L2, dY materialised)."""

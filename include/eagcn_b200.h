@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 16
+#define EAGCN_ABI_VERSION 17
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -266,6 +266,13 @@ int eagcn_get_gemm_mode(void);
 /* k-block of the K-major tcgen05 products: 0 (default) = chosen per shape by the pipeline model, 16 = 64-byte rows
  * (SWIZZLE_64B, up to 6 stages), 32 = 128-byte rows (SWIZZLE_128B).  Process-wide; for measurements.            */
 int eagcn_set_tc_bk(int bk);
+/* tensor-core precision of the projection products (layers.py:40 and its autograd products).  3 (default): fp32-faithful
+ * 3xTF32 -- every fp32 operand split exactly into hi + lo, three TF32 passes, two fp32 accumulators: meets the 1e-5 parity
+ * bar.  1: ONE TF32 pass on the raw operands (the tensor core truncates to a 10-bit mantissa): ~1e-3 relative error, the
+ * analogue of BASELINE.json's "bf16" configuration -- reported beside the strict mode by bench.py, never the default.
+ * Process-wide; for measurements.                                                                                 */
+int eagcn_set_tc_passes(int passes);
+int eagcn_get_tc_passes(void);
 int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock stamps of the GEMM pipeline (see .cu) */
 int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);

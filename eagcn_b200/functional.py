@@ -236,7 +236,7 @@ class RngState:
             Overlap.join_fwd(self.state.device)
             return self._queue.pop(0)
         snap = torch.empty_like(self.state)
-        check(lib().eagcn_rng_fork(ptr(self.state), ptr(snap), 1 << 20, _stream()), "eagcn_rng_fork")
+        check(lib().eagcn_rng_fork(ptr(self.state), ptr(snap), 1 << 20, _stream(self.state.device)), "eagcn_rng_fork")
         return snap
 
     def prefork(self, n, stream=None):
@@ -244,7 +244,7 @@ class RngState:
         (seed, offset) sequence as n separate forks; snapshots left over from an earlier prefork are dropped."""
         snaps = torch.empty(n, 2, dtype=torch.int64, device=self.state.device)
         check(lib().eagcn_rng_fork_n(ptr(self.state), ptr(snaps), n, 1 << 20,
-                                     _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)),
+                                     _stream(self.state.device) if stream is None else ctypes.c_void_p(stream.cuda_stream)),
               "eagcn_rng_fork_n")
         self._queue = [snaps[i] for i in range(n)]
 
@@ -339,7 +339,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.rng_stream = int(cfg.rng_stream)
         w.m_total, w.n_pad = int(plan.m_total), int(plan.n_pad)
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
-        st = _stream()
+        st = _stream(dev)
         check(L.eagcn_layer_forward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_forward_a")
         if cfg.training and cfg.stat_allreduce is not None:
             cfg.stat_allreduce(sums)
@@ -391,7 +391,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
         w.dX, w.dY, w.Q, w.dH, w.dwall, w.dvec, w.datt = ptr(dX), ptr(dY), ptr(Q), ptr(dH), ptr(dwall), ptr(dvec), ptr(datt)
         w.bsums, w.gemm_ws, w.gemm_ws_bytes = ptr(bsums), ptr(gemm_ws), ws_bytes
-        st = _stream()
+        st = _stream(dev)
         check(L.eagcn_layer_backward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_a")
         if cfg.training and cfg.stat_allreduce is not None:
             cfg.stat_allreduce(bsums)
@@ -441,7 +441,10 @@ def _prep_buffers(fin, C, V, dev):
 class LayerPrep:
     """Per-step parameter-derived buffers of one layer (W_all, its transposed / hi-lo split copies, bias / gamma / beta
     rows, sigmoid tables), filled by eagcn_layer_prepare -- on the side stream when ``stream`` is given, so that it runs
-    beside the packing of the batch.  Valid until the parameters change (one optimiser step)."""
+    beside the packing of the batch.  Valid until the parameters change (one optimiser step): ``matches`` compares the
+    parameters' storage and ``_version`` counters, so an in-place update through ``.data`` (the reference's
+    ``weights_init``, utils.py:702-708) between a prefetch and the forward pass it was made for is NOT detected -- prefetch
+    right before the forward call (EAGCNStack.forward does) and after any such initialisation."""
 
     def __init__(self, fin, fo, channels, params, dev, stream=None):
         self.fin, self.fo, self.channels = int(fin), tuple(int(f) for f in fo), tuple(int(c) for c in channels)
@@ -466,7 +469,7 @@ class LayerPrep:
             ls.off[v] = off
         w = WorkStruct()
         w.wall, w.wallT, w.wsplit, w.ball, w.sig = ptr(self.wall), ptr(self.wallT), ptr(self.wsplit), ptr(self.ball), ptr(self.sig)
-        st = _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        st = _stream(dev) if stream is None else ctypes.c_void_p(stream.cuda_stream)
         check(lib().eagcn_layer_prepare(ctypes.byref(ps), ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_prepare")
 
     def matches(self, cfg, params, plan):
@@ -565,7 +568,7 @@ class _ReadoutSumFn(torch.autograd.Function):
         ctx.plan = plan
         F = packed.shape[1]
         out = torch.empty(plan.B, F, dtype=_F32, device=plan.device)
-        check(lib().eagcn_readout_sum(plan.ref, ptr(packed.contiguous()), ptr(out), F, _stream()), "eagcn_readout_sum")
+        check(lib().eagcn_readout_sum(plan.ref, ptr(packed.contiguous()), ptr(out), F, _stream(plan.device)), "eagcn_readout_sum")
         return out
 
     @staticmethod
@@ -573,7 +576,7 @@ class _ReadoutSumFn(torch.autograd.Function):
         plan = ctx.plan
         F = g.shape[1]
         out = torch.empty(plan.t_cap, F, dtype=_F32, device=plan.device)
-        check(lib().eagcn_readout_sum_bwd(plan.ref, ptr(g.contiguous()), ptr(out), F, _stream()),
+        check(lib().eagcn_readout_sum_bwd(plan.ref, ptr(g.contiguous()), ptr(out), F, _stream(plan.device)),
               "eagcn_readout_sum_bwd")
         return None, out
 
@@ -593,7 +596,7 @@ class _AttentionDenseFn(torch.autograd.Function):
         for v in range(plan.V):
             s.att_w[v] = att[v].data_ptr()
         A = torch.empty(plan.V, plan.B, plan.N, plan.N, dtype=_F32, device=plan.device)
-        check(lib().eagcn_attention_dense(plan.ref, ctypes.byref(s), ptr(A), _stream()), "eagcn_attention_dense")
+        check(lib().eagcn_attention_dense(plan.ref, ctypes.byref(s), ptr(A), _stream(plan.device)), "eagcn_attention_dense")
         ctx.plan, ctx.att = plan, att
         return A
 
@@ -605,7 +608,7 @@ class _AttentionDenseFn(torch.autograd.Function):
         for v in range(plan.V):
             s.att_w[v] = att[v].data_ptr()
         datt = torch.empty(plan.V, _lib.SIG_STRIDE, dtype=_F32, device=plan.device)
-        check(lib().eagcn_attention_dense_bwd(plan.ref, ctypes.byref(s), ptr(dA.contiguous()), ptr(datt), _stream()),
+        check(lib().eagcn_attention_dense_bwd(plan.ref, ctypes.byref(s), ptr(dA.contiguous()), ptr(datt), _stream(plan.device)),
               "eagcn_attention_dense_bwd")
         return (None, *[datt[v, :plan.channels[v]].reshape(att[v].shape) for v in range(plan.V)])
 
@@ -621,7 +624,7 @@ def dropout_keep_mask(plan, cfg: LayerConfig, fo_tot, rng_state):
     w.rng = ptr(rng_state)
     w.p_drop, w.rng_stream = float(cfg.p_drop), int(cfg.rng_stream)
     keep = torch.empty(plan.t_cap, fo_tot, dtype=torch.uint8, device=plan.device)
-    check(lib().eagcn_dropout_mask(plan.ref, ctypes.byref(w), fo_tot, ptr(keep), _stream()), "eagcn_dropout_mask")
+    check(lib().eagcn_dropout_mask(plan.ref, ctypes.byref(w), fo_tot, ptr(keep), _stream(plan.device)), "eagcn_dropout_mask")
     return keep
 
 
@@ -646,7 +649,7 @@ class _BnActFn(torch.autograd.Function):
         check(lib().eagcn_bn_act_forward(ptr(x), ptr(y), ptr(g), ptr(b), ptr(rm), ptr(rv),
                                          ptr(nbt) if nbt is not None else None, ptr(mean), ptr(invstd), B, C,
                                          int(training), int(relu), float(p_drop), ptr(snap) if snap is not None else None,
-                                         int(rng_stream), float(momentum), float(eps), _stream()), "eagcn_bn_act_forward")
+                                         int(rng_stream), float(momentum), float(eps), _stream(x.device)), "eagcn_bn_act_forward")
         ctx.cfg = cfg
         ctx.saved = (x, g, b, mean, invstd, snap)
         return y
@@ -661,7 +664,7 @@ class _BnActFn(torch.autograd.Function):
         dg, db = GradArena.empty(C, x.device), GradArena.empty(C, x.device)
         check(lib().eagcn_bn_act_backward(ptr(x), ptr(dy), ptr(g), ptr(b), ptr(mean), ptr(invstd), ptr(dx), ptr(dg),
                                           ptr(db), B, C, int(training), int(relu), float(p_drop),
-                                          ptr(snap) if snap is not None else None, int(rng_stream), _stream()),
+                                          ptr(snap) if snap is not None else None, int(rng_stream), _stream(x.device)),
               "eagcn_bn_act_backward")
         return None, None, dx, dg, db
 
@@ -706,7 +709,7 @@ def _mm_tile(A, transA, B, transB, stream=None, bufs=None):
         raise ValueError("mm: inner dimensions differ")
     L = lib()
     C, ws, tk, nbytes = bufs if bufs is not None else _mm_tile_bufs(A, transA, B, transB, 0 if stream is None else 1)
-    st = _stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+    st = _stream(A.device) if stream is None else ctypes.c_void_p(stream.cuda_stream)
     check(L.eagcn_mm_tile(ptr(A), A.shape[1], int(transA), ptr(B), B.shape[1], int(transB), ptr(C), M, N, K,
                           ptr(ws), nbytes, ptr(tk), st), "eagcn_mm_tile")
     return C, ws
@@ -768,7 +771,7 @@ def bn_act(x, bn, training, relu=False, p_drop=0.0, rng_stream=1000):
 def dropout_keep_mask_flat(rng_state, rng_stream, p_drop, total):
     """Test hook: keep mask of the flat index range [0, total) for (rng_state, rng_stream): u8 [total]."""
     keep = torch.empty(total, dtype=torch.uint8, device=rng_state.device)
-    check(lib().eagcn_dropout_mask_flat(ptr(rng_state), int(rng_stream), float(p_drop), int(total), ptr(keep), _stream()),
+    check(lib().eagcn_dropout_mask_flat(ptr(rng_state), int(rng_stream), float(p_drop), int(total), ptr(keep), _stream(rng_state.device)),
           "eagcn_dropout_mask_flat")
     return keep
 
@@ -778,7 +781,7 @@ def gemm_nt(A, B, m_dev, engine=0):
     A, B = A.contiguous(), B.contiguous()
     C = torch.empty(A.shape[0], B.shape[0], dtype=_F32, device=A.device)
     check(lib().eagcn_gemm_nt(ptr(A), A.shape[1], ptr(B), B.shape[1], ptr(C), B.shape[0], A.shape[0], B.shape[0],
-                              A.shape[1], ptr(m_dev), engine, _stream()), "eagcn_gemm_nt")
+                              A.shape[1], ptr(m_dev), engine, _stream(A.device)), "eagcn_gemm_nt")
     return C
 
 
@@ -789,7 +792,7 @@ def gemm_tn(A, B, k_dev, engine=0):
     C = torch.empty(M, N, dtype=_F32, device=A.device)
     nbytes = int(lib().eagcn_gemm_workspace_bytes(M, N, K))
     ws = torch.empty(max(nbytes // 4, 1), dtype=_F32, device=A.device)
-    check(lib().eagcn_gemm_tn(ptr(A), M, ptr(B), N, ptr(C), M, N, K, ptr(k_dev), ptr(ws), nbytes, engine, _stream()),
+    check(lib().eagcn_gemm_tn(ptr(A), M, ptr(B), N, ptr(C), M, N, K, ptr(k_dev), ptr(ws), nbytes, engine, _stream(A.device)),
           "eagcn_gemm_tn")
     return C
 

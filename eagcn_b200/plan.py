@@ -24,8 +24,9 @@ def _round_up(x, m):
     return (int(x) + m - 1) // m * m
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream ON ``device`` (the plan's / tensor's device, not whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class GraphPlan:
@@ -129,7 +130,7 @@ class GraphPlan:
 
     def _run(self, adj, rels, codes, t_cap, e_cap):
         L = lib()
-        st = _stream()
+        st = _stream(self.device)
         sync_sizes = t_cap is None or e_cap is None
         if sync_sizes:
             # phase 1 with unlimited capacities, read (T, E) once, allocate exactly
@@ -193,13 +194,13 @@ class GraphPlan:
         """dense [B,N,F] -> packed rows [t_cap,F] (no autograd; see functional.gather_rows)."""
         F = dense.shape[-1]
         out = torch.empty(self.t_cap, F, dtype=torch.float32, device=self.device)
-        check(lib().eagcn_rows_gather(self.ref, ptr(dense.contiguous()), ptr(out), F, _stream()), "eagcn_rows_gather")
+        check(lib().eagcn_rows_gather(self.ref, ptr(dense.contiguous()), ptr(out), F, _stream(self.device)), "eagcn_rows_gather")
         return out
 
     def scatter(self, packed):
         F = packed.shape[-1]
         out = torch.empty(self.B, self.N, F, dtype=torch.float32, device=self.device)
-        check(lib().eagcn_rows_scatter(self.ref, ptr(packed.contiguous()), ptr(out), F, _stream()),
+        check(lib().eagcn_rows_scatter(self.ref, ptr(packed.contiguous()), ptr(out), F, _stream(self.device)),
               "eagcn_rows_scatter")
         return out
 
@@ -207,7 +208,7 @@ class GraphPlan:
         """(one-hot relation tensor of view v, adjacency) re-expanded from the plan (bit-exactness check)."""
         rel = torch.empty(self.B, self.channels[v], self.N, self.N, dtype=torch.float32, device=self.device)
         adj = torch.empty(self.B, self.N, self.N, dtype=torch.float32, device=self.device)
-        check(lib().eagcn_unpack_view(self.ref, v, ptr(rel), ptr(adj), _stream()), "eagcn_unpack_view")
+        check(lib().eagcn_unpack_view(self.ref, v, ptr(rel), ptr(adj), _stream(self.device)), "eagcn_unpack_view")
         return rel, adj
 
     def row_mask(self):

@@ -12,7 +12,7 @@ from ctypes import c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeagcn_sm100.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 MAX_VIEWS = 16
 ROW_TILE = 128
 SIG_STRIDE = 257
@@ -53,7 +53,8 @@ class WorkStruct(ctypes.Structure):
                 ("p_drop", c_double), ("eps", c_double), ("momentum", c_double),
                 ("dX", c_void_p), ("dY", c_void_p), ("Q", c_void_p), ("dH", c_void_p), ("dwall", c_void_p),
                 ("dvec", c_void_p), ("datt", c_void_p), ("bsums", c_void_p), ("gemm_ws", c_void_p),
-                ("gemm_ws_bytes", c_int64), ("wallT", c_void_p), ("wsplit", c_void_p), ("phase", c_int64)]
+                ("gemm_ws_bytes", c_int64), ("wallT", c_void_p), ("wsplit", c_void_p), ("phase", c_int64),
+                ("tickets", c_void_p)]
 
 
 _PROTOS = {

@@ -142,15 +142,22 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  float* __restrict__ partial, int C, int training, float p_drop,
                                                                  const unsigned long long* rng, unsigned long long stream,
-                                                                 float* __restrict__ G) {
+                                                                 float* __restrict__ G, int* __restrict__ tickets,
+                                                                 double* __restrict__ bsums, float* __restrict__ dvec) {
   pdl_prologue();
   __shared__ float4 s_red[2][8][32];
+  __shared__ double s_fin[2][8][32][4];
+  __shared__ int s_last;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
-  if (tile * kStatRows >= T) return;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.y * 32 + cx) * 4;
   const bool act = c < C;
+  if (T == 0 && tile == 0 && tickets && ry < 3 && act) {   // empty batch: no tile is live, the sums are zero
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { dvec[ry * C + c + u] = 0.f; if (ry < 2) bsums[ry * C + c + u] = 0.0; }
+  }
+  if (tile * kStatRows >= T) return;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (act) {
     const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
@@ -182,6 +189,53 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
 #pragma unroll
     for (int w = 1; w < 8; ++w) { const float4 b = s_red[ry][w][cx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
     *reinterpret_cast<float4*>(partial + ((size_t)tile * 2 + ry) * C + c) = a;
+  }
+  if (!tickets) return;                       // separate stat_reduce launch (global-batch statistics keep it simple too)
+  // ---- "last CTA reduces": the CTA that completes a 128-channel block's last tile sums that block's tile partials in
+  // FIXED tile order (so the result does not depend on which CTA happens to be last) -> bsums (double) and dbias /
+  // dgamma / dbeta: the stat_reduce launch between this kernel and the aggregation backward disappears
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ntile = (T + kStatRows - 1) / kStatRows;
+    const int prev = atomicAdd(&tickets[blockIdx.y], 1);
+    s_last = prev == ntile - 1;
+    if (s_last) tickets[blockIdx.y] = 0;      // leave the ticket array zero for the next call
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int ntile = (T + kStatRows - 1) / kStatRows;
+    double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+    if (act) {
+#pragma unroll 4
+      for (int t = ry; t < ntile; t += 8) {
+        const float4 x1 = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)t * 2 + 0) * C + c));
+        const float4 x2 = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)t * 2 + 1) * C + c));
+        a1[0] += (double)x1.x; a1[1] += (double)x1.y; a1[2] += (double)x1.z; a1[3] += (double)x1.w;
+        a2[0] += (double)x2.x; a2[1] += (double)x2.y; a2[2] += (double)x2.z; a2[3] += (double)x2.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s_fin[0][ry][cx][u] = a1[u]; s_fin[1][ry][cx][u] = a2[u]; }
+    __syncthreads();
+    if (ry < 2 && act) {                      // warp 0: sum g, warp 1: sum g * xhat
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c + u >= C) break;
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_fin[ry][w][cx][u];
+        bsums[ry * C + c + u] = acc;
+        if (ry == 0) {                        // dvec = [dbias | dgamma | dbeta]
+          dvec[c + u] = training ? 0.0f : (float)((double)ball[C + c + u] * (double)invstd[c + u] * acc);
+          dvec[2 * C + c + u] = (float)acc;
+        } else {
+          dvec[C + c + u] = (float)acc;
+        }
+      }
+    }
   }
 }
 
@@ -653,6 +707,7 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   cudaStream_t st = (cudaStream_t)stream;
   PlanDev p = to_dev(plan);
   const int C = (int)layer->fo_tot;
+  if (!w->dvec) return EAGCN_E_ARG;
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y)) {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 31) / 32);
     EAGCN_PROF("bn_bwd_partial_kernel", st);
@@ -661,8 +716,10 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
                                                     C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,
                                                     (unsigned long long)w->rng_stream,
-                                                    tile_bwd_ok(plan, layer, w) ? (float*)w->dY : nullptr);
+                                                    tile_bwd_ok(plan, layer, w) ? (float*)w->dY : nullptr,
+                                                    (int*)w->tickets, (double*)w->bsums, (float*)w->dvec);
     EAGCN_LAUNCH_CHECK();
+    if (w->tickets) return w->dvec ? 0 : EAGCN_E_ARG;   // the sums were reduced by the kernel's last CTAs
   } else {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
     EAGCN_PROF("bn_bwd_partial_kernel", st);

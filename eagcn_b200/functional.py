@@ -391,6 +391,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
         w.p_drop, w.eps, w.momentum = float(cfg.p_drop), float(cfg.eps), float(cfg.momentum)
         w.dX, w.dY, w.Q, w.dH, w.dwall, w.dvec, w.datt = ptr(dX), ptr(dY), ptr(Q), ptr(dH), ptr(dwall), ptr(dvec), ptr(datt)
         w.bsums, w.gemm_ws, w.gemm_ws_bytes = ptr(bsums), ptr(gemm_ws), ws_bytes
+        if _bwd_tickets_enabled:
+            w.tickets = ptr(_ticket_buf(dev, 2, C // 128 + 2))     # BatchNorm backward sums reduced by the last CTAs
         st = _stream(dev)
         check(L.eagcn_layer_backward_a(plan.ref, ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_backward_a")
         if cfg.training and cfg.stat_allreduce is not None:
@@ -670,6 +672,7 @@ class _BnActFn(torch.autograd.Function):
 
 
 _tickets = {}
+_bwd_tickets_enabled = os.environ.get("EAGCN_BWD_TICKETS", "1") != "0"   # 0: separate stat_reduce launch (A/B measurements)
 
 
 def _ticket_buf(dev, lane, n):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EAGCN_ABI_VERSION 17
+#define EAGCN_ABI_VERSION 18
 #define EAGCN_MAX_VIEWS 16
 #define EAGCN_ROW_TILE 128          /* packed-row capacity granularity (one MMA tile of rows) */
 
@@ -146,6 +146,9 @@ typedef struct eagcn_work {
                    * the host can put independent parts on different streams: 1 = aggregation backward (Q, attention
                    * partials; needs backward_a), 2 = dH = Q W^T (needs 1), 4 = dW = H^T Q + d att / d self_r sums
                    * (needs 1; independent of 2)                                                          */
+  void* tickets;  /* i32 [fo_tot/128 + 1], ZERO when first used (the kernels leave it zero), or NULL.  eagcn_layer_backward_a
+                   * then reduces the BatchNorm backward sums in the LAST CTA of each 128-channel block (fixed tile order:
+                   * deterministic) instead of a separate reduction launch.  One array per stream of calls              */
 } eagcn_work_t;
 
 int eagcn_version(void);

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from eagcn_b200 import _lib
     assert ctypes.sizeof(_lib.PlanStruct) == 8 * (5 + 16 + 13)
     assert ctypes.sizeof(_lib.LayerStruct) == 8 * (3 + 16 + 17 + 9 * 16)
-    assert ctypes.sizeof(_lib.WorkStruct) == 8 * 33
+    assert ctypes.sizeof(_lib.WorkStruct) == 8 * 34
     L = _lib.lib()
     for which, cls in enumerate((_lib.PlanStruct, _lib.LayerStruct, _lib.WorkStruct)):
         assert L.eagcn_sizeof(which) == ctypes.sizeof(cls), cls.__name__

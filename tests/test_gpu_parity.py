@@ -1120,3 +1120,53 @@ def test_fused_forward_equals_two_kernel_form(B, dataset, fin, fo, training, fix
     for k in sd0_:
         if sd0_[k].is_floating_point():
             assert rel_err(sd1[k], sd0_[k]) <= 1e-6, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,dataset,fin,fo,training", [
+    (64, "tox21", 30, (30, 10, 10, 10, 10), True),                  # 70 channels: one 128-channel block
+    (256, "tox21", 60, (60, 20, 20, 20, 20), True),                 # 140 channels: two blocks, ~160 row tiles
+    (5, "hiv", 20, (16, 8, 8, 8, 8), False),                        # eval: d bias = gamma * invstd * sum g
+])
+def test_bn_backward_last_cta_reduction(B, dataset, fin, fo, training):
+    """The BatchNorm-backward sums reduced by the last CTA of each channel block (work.tickets) against the separate
+    stat_reduce launch: same tile partials, both in double precision and fixed order (8 vs 32 tile lanes), so the
+    gradients agree to the rounding of one double sum; one launch less; and two runs are bit-identical (the result does
+    not depend on which CTA arrives last)."""
+    from eagcn_b200 import functional as EF, layers as EL, _lib
+    from eagcn_b200.data import make_batch, DATASETS
+    dev = _cuda()
+    kb = DATASETS[dataset]["kb"]
+    batch = make_batch(B, dataset=dataset, seed=B + 1, kb=kb, n_afeat=fin)
+    torch.manual_seed(B)
+    layer = EL.GraphConv_Layer(fin, kb, *fo, dropout=0.2 if training else 0.0, structure="Concate").to(dev)
+    layer.train(training)
+    ins = _to(dev, [torch.from_numpy(a) for a in batch.dense()])
+    with torch.no_grad():
+        layer(*ins)
+    sd0 = {k: v.clone() for k, v in layer.state_dict().items()}
+    res = []
+    old = EF._bwd_tickets_enabled
+    try:
+        for tickets in (True, True, False):
+            EF._bwd_tickets_enabled = tickets
+            layer.load_state_dict(sd0)
+            EF.manual_seed(3, dev)
+            for prm in layer.parameters():
+                prm.grad = None
+            afm = ins[1].clone().requires_grad_(True)
+            c0 = _lib.launch_count()
+            x, _ = layer(ins[0], afm, *ins[2:])
+            x.square().sum().backward()
+            torch.cuda.synchronize()
+            res.append((afm.grad.clone(), {n: q.grad.clone() for n, q in layer.named_parameters() if q.grad is not None},
+                        _lib.launch_count() - c0))
+    finally:
+        EF._bwd_tickets_enabled = old
+    (ga, pa, na), (gb, pb, nb), (gc, pc, nc) = res
+    assert na == nb == nc - 1
+    assert torch.equal(ga, gb) and all(torch.equal(pa[k], pb[k]) for k in pa)
+    assert rel_err(ga, gc) <= 1e-6
+    scale = max(float(v.abs().max()) for v in pc.values())
+    for k in pc:
+        assert float((pa[k] - pc[k]).abs().max()) <= 1e-6 * max(float(pc[k].abs().max()), 1e-3 * scale), k

@@ -618,6 +618,8 @@ def run_b200(args):
     L.eagcn_set_fuse_mode(0 if args.fuse_bn else 1)
     L.eagcn_set_fwd_fused(1 if args.fwd_fused else 0)
     L.eagcn_set_tc_bk(args.tc_bk)
+    if args.tc_a_tmem is not None:
+        L.eagcn_set_tc_a_tmem(args.tc_a_tmem)
     if args.no_pdl:
         L.eagcn_set_pdl(0)
     _M2.Dense.mm_engine = args.dense_mm
@@ -1225,6 +1227,9 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="1: independent branches of a step on a side stream (parallel graph branches); 0: one stream")
     ap.add_argument("--bn-act", default="vec", choices=["vec", "c32"], help="head BatchNorm kernels: float4 or 32-channel")
+    ap.add_argument("--tc-a-tmem", type=int, default=None, choices=[0, 1, 2, 3],
+                    help="diagnostic: where the split activation operand of the tcgen05 GEMMs lives (bit 0 K-major products, "
+                         "bit 1 split-K dW; set = tensor memory, the default)")
     ap.add_argument("--tc-bk", type=int, default=0, choices=[0, 16, 32],
                     help="k-block of the K-major tcgen05 products (0: pipeline model picks per shape)")
     ap.add_argument("--fuse-bn", type=int, default=1, choices=[0, 1],

@@ -103,6 +103,8 @@ _PROTOS = {
     "eagcn_set_tc_bk": (c_int, [c_int]),
     "eagcn_set_tc_passes": (c_int, [c_int]),
     "eagcn_get_tc_passes": (c_int, []),
+    "eagcn_set_tc_a_tmem": (c_int, [c_int]),
+    "eagcn_get_tc_a_tmem": (c_int, []),
     "eagcn_set_pdl": (c_int, [c_int]),
     "eagcn_get_pdl": (c_int, []),
     "eagcn_set_agg_mode": (c_int, [c_int]),

@@ -48,6 +48,12 @@ extern "C" int eagcn_set_tc_passes(int passes) {
   return 0;
 }
 extern "C" int eagcn_get_tc_passes(void) { return eagcn::tc::tc_passes(); }
+extern "C" int eagcn_set_tc_a_tmem(int mask) {
+  if (mask < 0 || mask > 3) return EAGCN_E_ARG;
+  eagcn::tc::tc_a_tmem() = mask;
+  return 0;
+}
+extern "C" int eagcn_get_tc_a_tmem(void) { return eagcn::tc::tc_a_tmem(); }
 extern "C" int eagcn_set_pdl(int on) { eagcn::pdl_mode() = on ? 1 : 0; return 0; }
 extern "C" int eagcn_get_pdl(void) { return eagcn::pdl_mode(); }
 extern "C" int eagcn_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t m_cap,

@@ -117,6 +117,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(accum)
       : "memory");
 }
+// A operand from TENSOR MEMORY (lane = row of the 128-row tile, one 32-bit column per k element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of the warp's 32 TMEM lanes <- 16 registers per thread (lane = thread)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -151,6 +172,15 @@ __device__ __forceinline__ void split_tile(uint4* hi, uint4* lo, int n, int xt) 
 // error -- outside the 1e-5 parity bar, the analogue of BASELINE.json's "bf16" configuration, reported beside the strict
 // mode, never the default.  No hi/lo split, half the shared memory per stage, a third of the MMAs.  Process-wide.
 inline int& tc_passes() { static int v = 3; return v; }
+// Where the split activation operand (A) lives.  1 (default): the transform warps read the raw fp32 tile from shared
+// memory ONCE and write its hi / lo parts straight into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM
+// (tcgen05.mma [d], [a], b-desc).  Per 128 x BN x 32 k-block that removes 32 KB of shared-memory writes (hi / lo copies)
+// and 48 KB of UMMA operand reads (3 x 16 KB of A) from the pipe that bounds this kernel (shared-memory bandwidth, see
+// DESIGN.md 4): 262 KB -> 182 KB at BN = 240.  TMEM budget: 2 x BN accumulator columns + 64 columns (hi | lo) per
+// stage <= 512, so BN <= 192 with two stages.  0: hi / lo copies in shared memory (the round-1 form).  Process-wide.
+// Bit 0: the K-major products (Z = H W, dH = Q W^T); bit 1: the MN-major split-K product dW = H^T Q.
+inline int& tc_a_tmem() { static int v = 3; return v; }
+constexpr int kATmemCols = 2 * BK;   // TMEM columns of one A stage: 32 (hi) + 32 (lo)
 
 struct TcArgs {
   float* C;
@@ -166,6 +196,7 @@ struct TcArgs {
   long long split_stride;          // TN: elements between split partials
   long long* trace;                // diagnostic: clock64 stamps of CTA (0,0,0)'s pipeline events (nullptr: off)
   int passes;                      // 3: hi/lo-compensated 3xTF32, 1: single TF32 pass on the raw operands
+  int a_tmem;                      // 1: A hi / lo in tensor memory (needs passes == 3, bk == 32, 2*BN + stages*64 <= 512)
 };
 constexpr int kTraceKb = 64, kTracePer = 8, kTraceStride = 8 + kTracePer * kTraceKb;
 
@@ -209,11 +240,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t bytesA = BM * bk * 4, bytesB = (uint32_t)g.BN * bk * 4;
   const bool one = g.passes == 1;                       // single TF32 pass: [A | B] per stage, no lo copies
-  const uint32_t stage_bytes = one ? bytesA + bytesB : 2 * bytesA + 2 * bytesB;
+  const bool atm = g.a_tmem != 0;                       // A hi / lo in tensor memory: [A raw | B hi | B lo] per stage
+  const uint32_t stage_bytes = one ? bytesA + bytesB : (atm ? bytesA + 2 * bytesB : 2 * bytesA + 2 * bytesB);
+  const uint32_t offB = (one || atm) ? bytesA : 2 * bytesA;
   auto sA_hi = [&](int s) { return base + (size_t)s * stage_bytes; };
   auto sA_lo = [&](int s) { return base + (size_t)s * stage_bytes + bytesA; };
-  auto sB_hi = [&](int s) { return base + (size_t)s * stage_bytes + (one ? bytesA : 2 * bytesA); };
-  auto sB_lo = [&](int s) { return base + (size_t)s * stage_bytes + 2 * bytesA + bytesB; };
+  auto sB_hi = [&](int s) { return base + (size_t)s * stage_bytes + offB; };
+  auto sB_lo = [&](int s) { return base + (size_t)s * stage_bytes + offB + bytesB; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
@@ -235,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
   const uint32_t tmem_c = tmem_d + (uint32_t)g.BN;                 // correction accumulator: columns [BN, 2*BN)
+  const uint32_t tmem_a0 = tmem_d + 2u * (uint32_t)g.BN;           // a_tmem: stage s -> columns [+64 s, +64 s + 32) hi, then lo
   // TN: 32-wide MN boxes actually inside the tensors (the others are zero-filled by the transform warps)
   const uint32_t box_bytes = bk * 128;
   const int nboxA = tn ? min(BM / 32, (g.Mcap - m0 + 31) / 32) : 0;
@@ -266,8 +300,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (bit4), a=b=TF32 (2<<7, 2<<10), K-major A/B,
     // N>>3 at [17,23), M>>4 at [24,29)
     // TN: a_major (bit 15) = b_major (bit 16) = 1 (MN-major)
+    // a_tmem: A comes from tensor memory, which is always "K-major" (lane = row): only b_major is set for TN
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
-                           ((uint32_t)(BM >> 4) << 24) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
+                           ((uint32_t)(BM >> 4) << 24) | (tn ? ((atm ? 0u : (1u << 15)) | (1u << 16)) : 0u);
     // a single thread runs the whole issue loop: nothing of it needs the other 31 lanes, and re-converging the warp
     // every k-block (__syncwarp + 32 lanes polling the barrier) sat on the critical path of the tensor pipe
     if (lane == 0) {
@@ -288,6 +323,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           // NT: +32 bytes per UMMA_K inside the swizzled (128 B or 64 B) row;  TN: +1024 bytes (next group of 8 k rows)
           const uint64_t adv = tn ? (uint64_t)((k * 1024) >> 4) : (uint64_t)((k * UK * 4) >> 4);
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          if (atm) {
+            const uint32_t ah = tmem_a0 + (uint32_t)(s * kATmemCols + k * UK), al = ah + (uint32_t)BK;
+            umma_tf32_ts(tmem_c, al, dBh + adv, idesc, acc);
+            umma_tf32_ts(tmem_c, ah, dBl + adv, idesc, 1u);
+            umma_tf32_ts(tmem_d, ah, dBh + adv, idesc, acc);
+            continue;
+          }
           if (!one) {
             umma_tf32(tmem_c, dAl + adv, dBh + adv, idesc, acc);  // correction terms -> second accumulator
             umma_tf32(tmem_c, dAh + adv, dBl + adv, idesc, 1u);
@@ -312,12 +354,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (tr && xt == 0 && kb < kTraceKb) g.trace[8 + kb * kTracePer + 1] = clock64();
       if (tn) {                                                    // boxes outside the tensors were not loaded
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        uint4* ah = reinterpret_cast<uint4*>(sA_hi(s));
-        for (int i = nboxA * (int)(box_bytes / 16) + xt; i < (int)(bytesA / 16); i += kXformThreads) ah[i] = z;
+        if (!atm) {
+          uint4* ah = reinterpret_cast<uint4*>(sA_hi(s));
+          for (int i = nboxA * (int)(box_bytes / 16) + xt; i < (int)(bytesA / 16); i += kXformThreads) ah[i] = z;
+        }
         uint4* bh = reinterpret_cast<uint4*>(sB_hi(s));
         for (int i = nboxB * (int)(box_bytes / 16) + xt; i < (int)(bytesB / 16); i += kXformThreads) bh[i] = z;
       }
-      if (!one) {
+      if (atm) {
+        // A: this thread owns row (TMEM lane) 32*quad + lane of the tile and half of the k-block's 32 k values: 16 fp32
+        // from shared memory -> hi / lo in registers -> two tcgen05.st (16 columns each).  The stage's TMEM columns are
+        // free: bar_full[s] fired only after the MMAs that read them retired (bar_empty -> TMA -> bar_full).
+        const int quad = warp & 3, kh = (warp - 2) >> 2;           // TMEM lane quadrant of this warp, k half
+        uint32_t x[16];
+        if (!tn) {
+          // K-major SWIZZLE_128B: row r at r*128, its 16-byte chunk c at position c ^ (r & 7)
+          const int r = quad * 32 + lane;
+          const uint8_t* rowp = sA_hi(s) + r * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((kh * 4 + c) ^ (r & 7)) << 4));
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          }
+        } else if (quad < nboxA) {
+          // MN-major, 32-byte-atom 128B swizzle: box `quad` holds [32 k][32 m]; element (k, m) at
+          // k*128 + (((m >> 3) ^ (k & 3)) << 5) + (m & 7)*4 -- a warp reads one permuted 128-byte line per k
+          const uint8_t* boxp = sA_hi(s) + quad * box_bytes + (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = kh * 16 + i;
+            x[i] = *reinterpret_cast<const uint32_t*>(boxp + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = 0u;
+        }
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          h[i] = x[i] & 0xFFFFE000u;
+          l[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(h[i]));
+        }
+        const uint32_t ta = tmem_a0 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kATmemCols + kh * 16);
+        tmem_st16(ta, h);
+        tmem_st16(ta + (uint32_t)BK, l);
+        if (!g.b_split)
+          split_tile(reinterpret_cast<uint4*>(sB_hi(s)), reinterpret_cast<uint4*>(sB_lo(s)), (int)(bytesB / 16), xt);
+        tmem_st_wait();
+        tc_fence_before();
+      } else if (!one) {
         split_tile(reinterpret_cast<uint4*>(sA_hi(s)), reinterpret_cast<uint4*>(sA_lo(s)), (int)(bytesA / 16), xt);
         if (!g.b_split)
           split_tile(reinterpret_cast<uint4*>(sB_hi(s)), reinterpret_cast<uint4*>(sB_lo(s)), (int)(bytesB / 16), xt);
@@ -442,19 +527,53 @@ static bool make_map(CUtensorMap* m, const float* ptr, long long rows, long long
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int pick_stages(int BN, int num_kb, int bk = BK, int passes = 3) {
-  const int stage_bytes = (passes == 1 ? 1 : 2) * (BM * bk * 4 + BN * bk * 4);
-  int st = (kSmemBudget - 1024) / stage_bytes;
+static int stage_bytes_of(int BN, int bk, int passes, bool atm) {
+  if (passes == 1) return BM * bk * 4 + BN * bk * 4;
+  return (atm ? 1 : 2) * BM * bk * 4 + 2 * BN * bk * 4;          // a_tmem: no hi / lo copies of A in shared memory
+}
+static int pick_stages(int BN, int num_kb, int bk = BK, int passes = 3, bool atm = false) {
+  int st = (kSmemBudget - 1024) / stage_bytes_of(BN, bk, passes, atm);
+  if (atm && st > (512 - 2 * BN) / kATmemCols) st = (512 - 2 * BN) / kATmemCols;   // TMEM columns left for A stages
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (st > num_kb) st = num_kb;
   return st < 2 ? 2 : st;
 }
+static uint32_t tmem_cols_for(int BN, int stages, bool atm) {      // power of two >= 32
+  const int need = 2 * BN + (atm ? stages * kATmemCols : 0);
+  return need <= 128 ? 128u : (need <= 256 ? 256u : 512u);
+}
+// A-in-TMEM is available for the 3-pass mode with 128-byte k-blocks
+static bool use_a_tmem(int bk, int passes, int mode_bit) { return (tc_a_tmem() & mode_bit) != 0 && passes == 3 && bk == BK; }
 
 // N-tile width of the K-major products (multiple of 16, 64..256) from the same pipeline model as pick_tn_shape: one CTA
 // per SM, so first avoid a nearly empty second wave; then a k-block costs max(MMA, (TMA round trip + transform +
 // MMA) / stages) -- a tile narrow enough for a third shared-memory stage (144 columns for N = 400, with the full
 // 224 KB of dynamic shared memory) hides most of the TMA round trip, which the clock trace shows exposed with two.
 inline int& nt_bk_override() { static int v = 0; return v; }   // 0: model picks; 16 / 32: forced (A/B measurements)
+
+// a_tmem variant of the model below: shared-memory BYTES per k-block bound the main loop (128 B/clk for
+// TMA writes + transform reads/writes + UMMA operand reads together), the MMAs need 12 * max(75, bn/2) cycles.
+static int pick_bn_atm(int N, int mtiles, int K, bool b_presplit) {
+  int best = 128;
+  long long best_cost = 1LL << 60;
+  const int kb = (K + BK - 1) / BK;
+  for (int bn = 192; bn >= 64; bn -= 16) {                     // 2*bn + 2 stages * 64 TMEM columns <= 512
+    const int ntiles = (N + bn - 1) / bn;
+    const long long rounds = ((long long)ntiles * mtiles + 147) / 148;
+    const int stages = pick_stages(bn, kb, BK, 3, true);
+    const long long bytesA = BM * BK * 4, bytesB = (long long)bn * BK * 4;
+    // TMA writes (A, B hi, B lo or raw B) + A read + [B split: read + 2 writes] + 3 UMMA reads of B
+    const long long bytes = 2 * bytesA + (b_presplit ? 2 : 1) * bytesB + (b_presplit ? 0 : 3 * bytesB) + 3 * bytesB;
+    const long long mma = 12 * (bn / 2 > 75 ? bn / 2 : 75);
+    long long per_kb = bytes / 128 + 60;
+    per_kb = per_kb < mma + 60 ? mma + 60 : per_kb;
+    const long long lat = (2500 + mma) / stages;               // TMA round trip + transform + MMA, hidden `stages` deep
+    per_kb = per_kb < lat ? lat : per_kb;
+    const long long cost = rounds * (kb * per_kb + 4000 + 25 * bn) * 100 + (long long)(ntiles * bn - N);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
 
 static int pick_bn(int N, int mtiles, int K, bool b_presplit, int* bk_out) {
   int best = 128, best_bk = BK;
@@ -507,14 +626,16 @@ static long long* next_trace() {
 int gemm_tc_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int Mcap, int N, int K,
                const int* Mdev, cudaStream_t st, const char* tag, const float* B_lo = nullptr) {
   int bk = BK;
-  const int BN = pick_bn(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr, &bk);
+  int BN = pick_bn(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr, &bk);
+  const bool atm = use_a_tmem(bk, tc_passes(), 1);
+  if (atm) BN = pick_bn_atm(N, (Mcap + BM - 1) / BM, K, B_lo != nullptr);
   CUtensorMap mA, mB, mB2;
   if (!make_map(&mA, A, Mcap, K, lda, BM, false, bk) || !make_map(&mB, B, N, K, ldb, BN, false, bk)) return EAGCN_E_UNSUPPORTED;
   if (!make_map(&mB2, B_lo ? B_lo : B, N, K, ldb, BN, false, bk)) return EAGCN_E_UNSUPPORTED;
-  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, bk, 0, next_trace(), tc_passes()};
-  g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // main + correction accumulators
-  g.stages = pick_stages(BN, (K + bk - 1) / bk, bk, g.passes);
-  const size_t smem = (size_t)g.stages * (g.passes == 1 ? 1 : 2) * (BM * bk * 4 + BN * bk * 4) + 1024;
+  TcArgs g{C, ldc, Mcap, N, K, BN, Mdev, 0, 0, 2, B_lo ? 1 : 0, nullptr, 0, bk, 0, next_trace(), tc_passes(), atm ? 1 : 0};
+  g.stages = pick_stages(BN, (K + bk - 1) / bk, bk, g.passes, atm);
+  g.tmem_cols = tmem_cols_for(BN, g.stages, atm);                  // main + correction accumulators (+ A stages)
+  const size_t smem = (size_t)g.stages * stage_bytes_of(BN, bk, g.passes, atm) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -543,10 +664,33 @@ int tn_splits(int M, int N, int Kcap) {
 // ~300 + 30/KB, twelve UMMAs cost 12 * max(75, BN/2) cycles (a narrow UMMA is not cheaper than ~75 cycles), and the
 // three overlap only as far as the stage count allows.  Narrow tiles looked attractive on padding alone (N = 700 ->
 // BN = 64) but run 55 k-blocks at the UMMA floor; wide tiles with more K splits are ~2.4x faster.
-static void pick_tn_shape(int M, int N, int Kcap, long long ws_floats, int* bn_out, int* ns_out) {
+static void pick_tn_shape(int M, int N, int Kcap, long long ws_floats, int* bn_out, int* ns_out, bool atm) {
   const int mt = (M + BM - 1) / BM, kmax = (Kcap + 127) / 128;
   long long best = 1LL << 60;
   *bn_out = 128; *ns_out = 1;
+  if (atm) {                                                    // shared-memory-bytes model, see pick_bn_atm
+    for (int bn = 192; bn >= 32; bn -= 32) {
+      const int tiles = mt * ((N + bn - 1) / bn);
+      int ns = 148 / tiles;
+      if (ns < 1) ns = 1;
+      if (ns > kmax) ns = kmax;
+      if (ns > 32) ns = 32;
+      while (ns > 1 && (long long)ns * M * N > ws_floats) --ns;
+      const int kb = (((Kcap + ns - 1) / ns) + BK - 1) / BK;
+      const int stages = pick_stages(bn, kb, BK, 3, true);
+      const long long bytesA = BM * BK * 4, bytesB = (long long)bn * BK * 4;
+      const long long bytes = 2 * bytesA + 7 * bytesB;          // TMA A, B + A read + B split (1 + 2) + 3 UMMA reads of B
+      const long long mma = 12 * (bn / 2 > 75 ? bn / 2 : 75);
+      long long per_kb = bytes / 128 + 60;
+      per_kb = per_kb < mma + 60 ? mma + 60 : per_kb;
+      const long long lat = (2500 + 30 * (bn / 8) + mma) / stages;
+      per_kb = per_kb < lat ? lat : per_kb;
+      const long long waves = (tiles * (long long)ns + 147) / 148;
+      const long long cost = waves * (kb * per_kb + 4000 + 25 * bn);
+      if (cost < best) { best = cost; *bn_out = bn; *ns_out = ns; }
+    }
+    return;
+  }
   for (int bn = 256; bn >= 32; bn -= 32) {
     const int tiles = mt * ((N + bn - 1) / bn);
     int ns = 148 / tiles;
@@ -576,16 +720,17 @@ static void pick_tn_shape(int M, int N, int Kcap, long long ws_floats, int* bn_o
 int gemm_tc_tn(const float* A, int lda, const float* B, int ldb, float* ws, long long ws_floats, int M, int N, int Kcap,
                const int* Kdev, int* nsplit_out, cudaStream_t st) {
   int BN, ns;
-  pick_tn_shape(M, N, Kcap, ws_floats, &BN, &ns);
+  const bool atm = use_a_tmem(BK, tc_passes(), 2);
+  pick_tn_shape(M, N, Kcap, ws_floats, &BN, &ns, atm);
   if (ws_floats < (long long)ns * M * N) return EAGCN_E_ARG;
   CUtensorMap mA, mB;
   if (!make_map(&mA, A, Kcap, M, lda, BK, true) || !make_map(&mB, B, Kcap, N, ldb, BK, true)) return EAGCN_E_UNSUPPORTED;
   int kchunk = (Kcap + ns - 1) / ns;
   kchunk = ((kchunk + BK - 1) / BK) * BK;
-  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, BK, (long long)M * N, next_trace(), tc_passes()};
-  g.tmem_cols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
-  g.stages = pick_stages(BN, kchunk / BK, BK, g.passes);
-  const size_t smem = (size_t)g.stages * (g.passes == 1 ? 1 : 2) * (BM * BK * 4 + BN * BK * 4) + 1024;
+  TcArgs g{ws, N, M, N, Kcap, BN, nullptr, 0, 1, 2, 0, Kdev, kchunk, BK, (long long)M * N, next_trace(), tc_passes(), atm ? 1 : 0};
+  g.stages = pick_stages(BN, kchunk / BK, BK, g.passes, atm);
+  g.tmem_cols = tmem_cols_for(BN, g.stages, atm);
+  const size_t smem = (size_t)g.stages * stage_bytes_of(BN, BK, g.passes, atm) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ns);

@@ -276,6 +276,13 @@ int eagcn_set_tc_bk(int bk);
  * Process-wide; for measurements.                                                                                 */
 int eagcn_set_tc_passes(int passes);
 int eagcn_get_tc_passes(void);
+/* where the hi / lo split of the ACTIVATION operand of the 3xTF32 products lives.  Bit 0: K-major products (Z = H W,
+ * dH = Q W^T), bit 1: the split-K product dW = H^T Q.  Bit set (default 3): the transform warps write hi / lo straight
+ * into TENSOR MEMORY (tcgen05.st) and the MMAs take A from TMEM -- no hi / lo copies and no A operand reads in shared
+ * memory, whose bandwidth bounds these kernels.  Bit clear: hi / lo copies in shared memory.  Same arithmetic, bit-
+ * identical results.  Process-wide; for measurements.                                                              */
+int eagcn_set_tc_a_tmem(int mask);
+int eagcn_get_tc_a_tmem(void);
 int eagcn_gemm_trace(void* buf, int64_t max_launches);   /* diagnostic: clock stamps of the GEMM pipeline (see .cu) */
 int64_t eagcn_gemm_trace_stride(void);
 int eagcn_set_agg_mode(int mode);

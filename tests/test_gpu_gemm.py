@@ -226,3 +226,40 @@ def test_tf32_single_pass_mode_is_opt_in_and_coarser():
         e = float((a - b).abs().max() / b.abs().max())
         assert 1e-7 < e <= 2e-2, e
     assert L.eagcn_get_tc_passes() == 3
+
+
+@pytest.mark.parametrize("Mcap,T,N,K", [
+    (128, 128, 64, 32), (512, 511, 700, 400), (256, 129, 176, 40), (4864, 4853, 400, 700), (4864, 4853, 700, 400),
+    (384, 300, 24, 400), (128, 1, 16, 8),
+])
+def test_gemm_activation_operand_in_tensor_memory(Mcap, T, N, K):
+    """eagcn_set_tc_a_tmem: the hi / lo split of the activation operand written to TENSOR MEMORY (tcgen05.st, MMA with A
+    from TMEM) against the shared-memory hi / lo copies.  Same split values, same MMA order per accumulator: the K-major
+    product is BIT-IDENTICAL; the split-K product differs only through the number of K splits the tile shape implies."""
+    from eagcn_b200 import functional as EF, _lib
+    dev = _cuda()
+    L = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(Mcap + N + K + 1)
+    A = torch.randn(Mcap, K, generator=g).to(dev)
+    B = torch.randn(N, K, generator=g).to(dev)
+    m_dev = torch.tensor([T], dtype=torch.int32, device=dev)
+    # TN operands: [Kcap = Mcap rows, M = K columns] and [Kcap, N]
+    At = torch.randn(Mcap, K, generator=g); Bt = torch.randn(Mcap, N, generator=g)
+    At[T:] = 0; Bt[T:] = 0
+    At, Bt = At.to(dev), Bt.to(dev)
+    assert L.eagcn_get_tc_a_tmem() == 3                      # the default
+    out = {}
+    try:
+        for mask in (0, 3):
+            assert L.eagcn_set_tc_a_tmem(mask) == 0
+            out[mask] = (EF.gemm_nt(A, B, m_dev, 0).clone(),
+                         EF.gemm_tn(At, Bt, m_dev, 0).clone() if min(K, N) >= 32 else None)
+            torch.cuda.synchronize()
+    finally:
+        L.eagcn_set_tc_a_tmem(3)
+    assert torch.equal(out[0][0], out[3][0])
+    ref = At.double().t() @ Bt.double()
+    for mask in (0, 3):
+        if out[mask][1] is not None:
+            assert float((out[mask][1].double() - ref).abs().max()) / float(ref.abs().max()) <= 6e-6, mask
+    assert L.eagcn_set_tc_a_tmem(4) != 0

@@ -145,8 +145,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
                                                                  float* __restrict__ G, int* __restrict__ tickets,
                                                                  double* __restrict__ bsums, float* __restrict__ dvec) {
   pdl_prologue();
-  __shared__ float4 s_red[2][8][32];
-  __shared__ double s_fin[2][8][32][4];
+  __shared__ __align__(16) float4 s_red[2][8][32];         // 8 KB; the last CTA reuses it as double [8][32][4]
   __shared__ int s_last;
   const int T = min(p.counts[EAGCN_CNT_T], p.t_cap);
   const int tile = blockIdx.x;
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
     const int ntile = (T + kStatRows - 1) / kStatRows;
     double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
     if (act) {
-#pragma unroll 4
+#pragma unroll 8
       for (int t = ry; t < ntile; t += 8) {
         const float4 x1 = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)t * 2 + 0) * C + c));
         const float4 x2 = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)t * 2 + 1) * C + c));
@@ -217,22 +216,27 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, cons
         a2[0] += (double)x2.x; a2[1] += (double)x2.y; a2[2] += (double)x2.z; a2[3] += (double)x2.w;
       }
     }
+    double (*s_fin)[32][4] = reinterpret_cast<double (*)[32][4]>(&s_red[0][0][0]);   // [8][32][4], one sum at a time
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { s_fin[0][ry][cx][u] = a1[u]; s_fin[1][ry][cx][u] = a2[u]; }
-    __syncthreads();
-    if (ry < 2 && act) {                      // warp 0: sum g, warp 1: sum g * xhat
+    for (int k = 0; k < 2; ++k) {             // k = 0: sum g, k = 1: sum g * xhat
+      __syncthreads();                        // s_red (k = 0) / the previous round (k = 1) fully consumed
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c + u >= C) break;
-        double acc = 0.0;
+      for (int u = 0; u < 4; ++u) s_fin[ry][cx][u] = k == 0 ? a1[u] : a2[u];
+      __syncthreads();
+      if (ry == k && act) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) acc += s_fin[ry][w][cx][u];
-        bsums[ry * C + c + u] = acc;
-        if (ry == 0) {                        // dvec = [dbias | dgamma | dbeta]
-          dvec[c + u] = training ? 0.0f : (float)((double)ball[C + c + u] * (double)invstd[c + u] * acc);
-          dvec[2 * C + c + u] = (float)acc;
-        } else {
-          dvec[C + c + u] = (float)acc;
+        for (int u = 0; u < 4; ++u) {
+          if (c + u >= C) break;
+          double acc = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) acc += s_fin[w][cx][u];
+          bsums[k * C + c + u] = acc;
+          if (k == 0) {                       // dvec = [dbias | dgamma | dbeta]
+            dvec[c + u] = training ? 0.0f : (float)((double)ball[C + c + u] * (double)invstd[c + u] * acc);
+            dvec[2 * C + c + u] = (float)acc;
+          } else {
+            dvec[C + c + u] = (float)acc;
+          }
         }
       }
     }

@@ -135,6 +135,7 @@ __device__ __forceinline__ void grad_through_act4(const float4 dx, const float4 
   }
 }
 
+constexpr int kTicketTiles = 192;   // most 32-row tiles for which the in-kernel reduction of the backward sums is used
 // grid (stat tiles, ceil(C/4/32)); block (32 channel-groups x 8 row-groups): a thread sums 1/8 of the tile's rows
 // for its 4 channels, the 8 row-groups are then combined through shared memory in fixed order
 __global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
@@ -714,6 +715,10 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
   if (!w->dvec) return EAGCN_E_ARG;
   if ((C & 3) == 0 && aligned16(w->dX) && aligned16(w->Y)) {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C / 4 + 31) / 32);
+    // "last CTA reduces" pays per CTA (fence + ticket before it retires) and per tile (one CTA sums them all): it beats the
+    // separate reduction launch for a few hundred tiles per SM wave (Tox21 batch: +0.3 %) and loses beyond
+    // (Lipophilicity B = 512, 432 tiles x 8 channel blocks: -2.6 %, profiles/r02_dp2_notes.md r02w)
+    int* tickets = eagcn_stat_tiles(p.t_cap) <= kTicketTiles ? (int*)w->tickets : nullptr;
     EAGCN_PROF("bn_bwd_partial_kernel", st);
     EAGCN_LAUNCH(bn_bwd_partial_vec_kernel, grid, 256, 0, st)(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
@@ -721,9 +726,9 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
                                                     (const unsigned long long*)w->rng,
                                                     (unsigned long long)w->rng_stream,
                                                     tile_bwd_ok(plan, layer, w) ? (float*)w->dY : nullptr,
-                                                    (int*)w->tickets, (double*)w->bsums, (float*)w->dvec);
+                                                    tickets, (double*)w->bsums, (float*)w->dvec);
     EAGCN_LAUNCH_CHECK();
-    if (w->tickets) return w->dvec ? 0 : EAGCN_E_ARG;   // the sums were reduced by the kernel's last CTAs
+    if (tickets) return 0;                              // the sums were reduced by the kernel's last CTAs
   } else {
     dim3 grid((unsigned)eagcn_stat_tiles(p.t_cap), (C + 127) / 128);
     EAGCN_PROF("bn_bwd_partial_kernel", st);

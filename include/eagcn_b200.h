@@ -148,7 +148,8 @@ typedef struct eagcn_work {
                    * (needs 1; independent of 2)                                                          */
   void* tickets;  /* i32 [fo_tot/128 + 1], ZERO when first used (the kernels leave it zero), or NULL.  eagcn_layer_backward_a
                    * then reduces the BatchNorm backward sums in the LAST CTA of each 128-channel block (fixed tile order:
-                   * deterministic) instead of a separate reduction launch.  One array per stream of calls              */
+                   * deterministic) instead of a separate reduction launch -- for t_cap <= 6 144 rows (192 tiles); larger
+                   * batches keep the separate launch, which measured faster there.  One array per stream of calls      */
 } eagcn_work_t;
 
 int eagcn_version(void);

@@ -215,6 +215,7 @@ class RngState:
         self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
         self._inc = torch.tensor([0, 1 << 20], dtype=torch.int64, device=device)
         self._queue = []
+        self._queue_ready = None
 
     @classmethod
     def get(cls, device):
@@ -226,6 +227,7 @@ class RngState:
     def seed(self, seed):
         self.state.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
         self._queue = []
+        self._queue_ready = None
 
     def advance(self):
         self.state.add_(self._inc)
@@ -233,7 +235,11 @@ class RngState:
     def fork(self):
         """Snapshot for one dropout call site + advance of the live state, in one (graph-capturable) launch."""
         if self._queue:
-            Overlap.join_fwd(self.state.device)
+            if self._queue_ready is not None:        # the snapshots were written on a side stream: wait for that launch only
+                torch.cuda.current_stream(self.state.device).wait_event(self._queue_ready)
+                self._queue_ready = None
+            elif not _prep_events_enabled:
+                Overlap.join_fwd(self.state.device)
             return self._queue.pop(0)
         snap = torch.empty_like(self.state)
         check(lib().eagcn_rng_fork(ptr(self.state), ptr(snap), 1 << 20, _stream(self.state.device)), "eagcn_rng_fork")
@@ -247,6 +253,10 @@ class RngState:
                                      _stream(self.state.device) if stream is None else ctypes.c_void_p(stream.cuda_stream)),
               "eagcn_rng_fork_n")
         self._queue = [snaps[i] for i in range(n)]
+        self._queue_ready = None
+        if stream is not None and _prep_events_enabled:
+            self._queue_ready = torch.cuda.Event()
+            self._queue_ready.record(stream)
 
 
 def manual_seed(seed, device=None):
@@ -473,6 +483,12 @@ class LayerPrep:
         w.wall, w.wallT, w.wsplit, w.ball, w.sig = ptr(self.wall), ptr(self.wallT), ptr(self.wsplit), ptr(self.ball), ptr(self.sig)
         st = _stream(dev) if stream is None else ctypes.c_void_p(stream.cuda_stream)
         check(lib().eagcn_layer_prepare(ctypes.byref(ps), ctypes.byref(ls), ctypes.byref(w), st), "eagcn_layer_prepare")
+        # the consumer waits for THIS layer's preparation only (not for the whole side stream): layer 2's preparation then
+        # runs beside layer 1's forward pass instead of ahead of it
+        self.ready = None
+        if stream is not None and _prep_events_enabled:
+            self.ready = torch.cuda.Event()
+            self.ready.record(stream)
 
     def matches(self, cfg, params, plan):
         return (self.fin == cfg.fin and self.fo == tuple(cfg.fo) and self.channels == tuple(plan.channels[:plan.V]) and
@@ -480,7 +496,10 @@ class LayerPrep:
 
     def join(self):
         if self.side:
-            Overlap.join_fwd(self.dev)
+            if self.ready is not None:
+                torch.cuda.current_stream(self.dev).wait_event(self.ready)
+            else:
+                Overlap.join_fwd(self.dev)
             self.side = False
 
 
@@ -672,6 +691,7 @@ class _BnActFn(torch.autograd.Function):
 
 
 _tickets = {}
+_prep_events_enabled = os.environ.get("EAGCN_PREP_EVENTS", "1") != "0"   # 0: a prefetch consumer joins the whole side stream
 _bwd_tickets_enabled = os.environ.get("EAGCN_BWD_TICKETS", "1") != "0"   # 0: separate stat_reduce launch (A/B measurements)
 
 

@@ -139,9 +139,15 @@ class EAGCNStack(nn.Module):
         if dev.type != "cuda":
             return
         side = EF.Overlap.fork_fwd(dev)
+        # side-stream order = order of first use: layer 1's tables (its forward kernel is the first consumer), the dropout
+        # snapshots (first used after that kernel), then the later layers' tables (they run beside layer 1's forward pass);
+        # every consumer waits for its own item only (LayerPrep.ready / RngState._queue_ready)
+        layers = list(self.conv_layers)
+        preps = [layers[0].prepare(side)]
         if self.training and float(self.dropout) > 0.0:
             EF.RngState.get(dev).prefork(self.n_layers + 1, side)       # one site per layer + the head's dropout
-        self._prefetched = [layer.prepare(side) for layer in self.conv_layers]
+        preps += [layer.prepare(side) for layer in layers[1:]]
+        self._prefetched = preps
 
     def forward(self, adjs, afms, TypeAtt=None, OrderAtt=None, AromAtt=None, ConjAtt=None, RingAtt=None, size=None):
         if isinstance(adjs, GraphPlan):

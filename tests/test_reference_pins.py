@@ -123,3 +123,65 @@ def test_ref_stack_is_models_eagcn():
             assert (p0.grad is None) == (p1.grad is None), k
             if p0.grad is not None:
                 assert torch.equal(p0.grad, p1.grad), k
+
+
+@pytest.mark.parametrize("dataset,kb,molfp,training,B,seed", [
+    ("tox21", 30, "sum", True, 9, 0),
+    ("tox21", 30, "ave", False, 5, 1),
+    ("lipo", 18, "pool", True, 6, 2),
+    ("hiv", 30, "sum", False, 4, 3),
+    ("freesolv", 17, "ave", True, 8, 4),
+])
+def test_lookup_oracle_full_model_vs_live_reference(dataset, kb, molfp, training, B, seed):
+    """The oracle the GPU parity tests compare against -- O.stack_forward + O.head_forward, the LOOKUP form on uint8 edge
+    codes -- against the unmodified models.EAGCN (models.py:14-121): outputs, graph representation, atom representations
+    and EVERY parameter gradient, in training and eval mode, for the three read-outs and four data sets' bond vocabularies
+    (batches include ragged sizes, padded rows and molecules whose atoms have a single bond)."""
+    with ref_loader.cpu_only():
+        _, M, _ = ref_loader.load()
+        torch.manual_seed(seed)
+        s1, s2 = 8, 12
+        ref = M.EAGCN(30, 24, *([s1] * 5), *([s2] * 5), 16, 8, 3, dropout=0.0, structure="Concate", molfp_mode=molfp)
+        # models.EAGCN is written for Tox21's bond vocabulary sizes; the data sets differ only in the channel counts
+        batch, dense, sizes = _batch(B, dataset, seed + 10, kb)
+        chans = [int(r.shape[1]) for r in dense[2:]]
+        for l, layer in enumerate((ref.layer1, ref.layer2, ref.layer3, ref.layer4)):
+            for v, blk in enumerate((layer.block1, layer.block2, layer.block3, layer.block4, layer.block5)):
+                if blk.att.weight.shape[1] != chans[v]:
+                    blk.att = torch.nn.Conv2d(chans[v], 1, kernel_size=1, stride=1, padding=0, bias=False)
+        seeded_init(ref, seed=seed + 1)
+        ref.train(training)
+        if not training:                                          # eval mode normalises with the running statistics
+            with torch.no_grad():
+                for k, t in ref.state_dict().items():
+                    if k.endswith("running_mean"):
+                        t.copy_(0.1 * torch.randn(t.shape, generator=torch.Generator().manual_seed(len(k))))
+                    elif k.endswith("running_var"):
+                        t.copy_(0.5 + torch.rand(t.shape, generator=torch.Generator().manual_seed(len(k) + 1)))
+        y_ref, atom_ref, g_ref = ref(*dense, sizes)
+        cot = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(7))
+        (y_ref * cot).sum().backward()
+    sd = O.clone_sd(ref.state_dict())
+    for k, t in sd.items():
+        if t.is_floating_point() and "running" not in k:
+            t.requires_grad_(True)
+    adj, afm = dense[0], dense[1]
+    codes = [O.codes_from_onehot(adj, r) for r in dense[2:]]
+    h, outs = O.stack_forward(sd, adj, afm, codes, 4, training, last_flags=[0, 0, 0, 1])
+    y, g = O.head_forward(sd, h, sizes, training, molfp_mode=molfp, A_last=outs[-1]["A_weight"])
+    (y * cot).sum().backward()
+    assert rel_err(h.detach(), atom_ref.detach()) <= 2e-5
+    assert rel_err(y.detach(), y_ref.detach()) <= 5e-5 and rel_err(g.detach(), g_ref.detach()) <= 5e-5
+    scale = max(float(p.grad.abs().max()) for p in ref.parameters() if p.grad is not None)
+    checked = 0
+    for k, prm in ref.named_parameters():
+        if prm.grad is None:
+            continue
+        got = sd[k].grad
+        assert got is not None, k
+        denom = max(float(prm.grad.abs().max()), 1e-3 * scale)
+        if k.endswith("graph_conv.bias") and training:
+            denom = scale                                         # d bias through a train-mode BatchNorm: analytically zero
+        assert float((got.reshape(prm.grad.shape) - prm.grad).abs().max()) / denom <= 2e-4, k
+        checked += 1
+    assert checked >= 100                                         # 4 layers x 5 views x (att, self_r, W, bias, gamma, beta) + head

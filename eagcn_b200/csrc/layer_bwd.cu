@@ -13,6 +13,7 @@
 //                     d a_v[c] = sum_{edges of type c} dU * s(1-s),   d r_v = sum_i dU[i,i] * s_r(1-s_r)
 //                     Q_v[j]   = sum_i A_v[i,j] dY_v[i]   (transposed aggregation through the reverse-edge codes)
 //   gemm          : dH = Q . W_all^T ,  dW_all = H^T . Q   (split-K, fixed-order reduction)
+#include <cstdlib>
 #include "common.cuh"
 
 namespace eagcn {
@@ -138,7 +139,8 @@ __device__ __forceinline__ void grad_through_act4(const float4 dx, const float4 
 constexpr int kTicketTiles = 192;   // most 32-row tiles for which the in-kernel reduction of the backward sums is used
 // grid (stat tiles, ceil(C/4/32)); block (32 channel-groups x 8 row-groups): a thread sums 1/8 of the tile's rows
 // for its 4 channels, the 8 row-groups are then combined through shared memory in fixed order
-__global__ void __launch_bounds__(256) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) bn_bwd_partial_vec_kernel(PlanDev p, const float* __restrict__ dX,
                                                                  const float* __restrict__ Y, const float* __restrict__ ball,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  float* __restrict__ partial, int C, int training, float p_drop,
@@ -720,7 +722,12 @@ extern "C" int eagcn_layer_backward_a(const eagcn_plan_t* plan, const eagcn_laye
     // (Lipophilicity B = 512, 432 tiles x 8 channel blocks: -2.6 %, profiles/r02_dp2_notes.md r02w)
     int* tickets = eagcn_stat_tiles(p.t_cap) <= kTicketTiles ? (int*)w->tickets : nullptr;
     EAGCN_PROF("bn_bwd_partial_kernel", st);
-    EAGCN_LAUNCH(bn_bwd_partial_vec_kernel, grid, 256, 0, st)(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
+    // compiled for 4 resident CTAs per SM (64 registers, 16 B of spills) by default: a third more loads in flight for this
+    // bandwidth/latency-shaped kernel, 785.7 k -> 793.3 k molecules/s (r02ad); EAGCN_PARTIAL_MINB=0 selects the 80-register build
+    static int minb = -1;
+    if (minb < 0) { const char* e = getenv("EAGCN_PARTIAL_MINB"); minb = (e && e[0] == '0') ? 3 : 4; }
+    auto kern = minb == 4 ? bn_bwd_partial_vec_kernel<4> : bn_bwd_partial_vec_kernel<3>;
+    EAGCN_LAUNCH(kern, grid, 256, 0, st)(p, (const float*)w->dX, (const float*)w->Y, (const float*)w->ball,
                                                     (const float*)w->mean, (const float*)w->invstd, (float*)w->partial,
                                                     C, (w->training & 1) ? 1 : 0, (float)w->p_drop,
                                                     (const unsigned long long*)w->rng,

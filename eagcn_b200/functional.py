@@ -108,15 +108,42 @@ class Overlap:
             cls._cb_armed[key] = True
             torch.autograd.Variable._execution_engine.queue_callback(lambda: cls.join(dev))
 
+    # ---- how many autograd functions of the recorded graph(s) produce a gradient for a parameter -------------------
+    # A parameter with TWO producers (models.py:104-106 / layers.py:318: the attention weights feed the layer AND the
+    # returned dense attention of the 'pool' read-out; user-side weight tying) gets its gradients SUMMED by the autograd
+    # engine's input buffer the moment the second one arrives -- a main-stream kernel reading the first one, which a
+    # deferred join may not have written yet.  Every function of this library that hands out parameter gradients
+    # registers its parameters at forward time; a parameter seen more than once since the last backward pass makes
+    # ``fresh`` false (the join then precedes the function's return).
+    _uses = {}             # parameter storage pointer -> number of gradient producers recorded since the last backward
+    _bwd_seen = False
+
+    @classmethod
+    def note_use(cls, params):
+        """Forward side: these parameters get a gradient producer (call only when the function will be differentiated)."""
+        if cls._bwd_seen:                     # first forward after a backward pass: a new set of graphs starts
+            cls._uses.clear()
+            cls._bwd_seen = False
+        for p in params:
+            if p is not None and p.requires_grad:
+                k = p.data_ptr()
+                cls._uses[k] = cls._uses.get(k, 0) + 1
+
+    @classmethod
+    def note_backward(cls):
+        cls._bwd_seen = True
+
     @staticmethod
     def fresh(params):
         """True when autograd will adopt the returned gradient tensors as-is, i.e. when NOTHING launches a kernel on
         them before the end of the backward pass: every parameter is a leaf without a gradient yet (AccumulateGrad
-        steals the tensor), carries no tensor hooks and no post-accumulate-grad hooks (optimizer-in-backward, FSDP),
-        and the backward pass is not itself being recorded (``create_graph=True`` keeps grad mode on and makes
-        AccumulateGrad clone).  Hooks on the AccumulateGrad NODES (torch DDP's bucket hooks) cannot be seen from here:
-        wrap the model in DDP only with ``Overlap.defer_param_grads = False`` -- the join then precedes the layer's
-        return (eagcn_b200.parallel's own FlatGradBucket reduces after backward() and needs nothing)."""
+        steals the tensor), has exactly ONE gradient producer in the recorded graphs (``note_use``; two producers are
+        summed by the engine on arrival), carries no tensor hooks and no post-accumulate-grad hooks
+        (optimizer-in-backward, FSDP), and the backward pass is not itself being recorded (``create_graph=True`` keeps
+        grad mode on and makes AccumulateGrad clone).  Hooks on the AccumulateGrad NODES (torch DDP's bucket hooks)
+        cannot be seen from here: wrap the model in DDP only with ``Overlap.defer_param_grads = False`` -- the join then
+        precedes the layer's return (eagcn_b200.parallel's own FlatGradBucket reduces after backward() and needs
+        nothing)."""
         if not Overlap.defer_param_grads or torch.is_grad_enabled():
             return False
         for p in params:
@@ -125,6 +152,8 @@ class Overlap:
             if not p.is_leaf or p.grad is not None or p._backward_hooks:
                 return False
             if getattr(p, "_post_accumulate_grad_hooks", None):
+                return False
+            if Overlap._uses.get(p.data_ptr(), 0) != 1:      # unregistered (0) or shared (> 1): do not defer
                 return False
         return True
 
@@ -311,6 +340,8 @@ class _GraphConvLayerFn(torch.autograd.Function):
                              f"got {tuple(H.shape)} {H.dtype} on {H.device}")
         H = H.contiguous()
         ctx.param_refs = params
+        if any(ctx.needs_input_grad[4:]):
+            Overlap.note_use(params)
         params = tuple(p.detach() for p in params)
         _check_params(plan, cfg, params, buffers)
         ls = _layer_struct(plan, cfg, params, buffers)
@@ -365,6 +396,7 @@ class _GraphConvLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dX, gz=None):
         L = lib()
+        Overlap.note_backward()
         plan, cfg, buffers, params = ctx.plan, ctx.cfg, ctx.buffers, ctx.params
         H, Z, Y, invR, wall, wsplit, ball, sig, mean, invstd, rng_snapshot = ctx.saved
         dev = plan.device
@@ -613,6 +645,8 @@ class _AttentionDenseFn(torch.autograd.Function):
     def forward(ctx, plan, *att_ws):
         s = LayerStruct()
         s.V = plan.V
+        if any(ctx.needs_input_grad[1:]):
+            Overlap.note_use(att_ws)                    # the layer's own function produces a gradient for these too
         att = tuple(a.detach().contiguous() for a in att_ws)
         for v in range(plan.V):
             s.att_w[v] = att[v].data_ptr()
@@ -747,6 +781,8 @@ class _DenseMmFn(torch.autograd.Function):
         if not x.is_cuda:
             raise EagcnError("eagcn_b200.dense_mm is CUDA-only (sm_100a, no CPU fallback)")
         ctx.w_ref = W
+        if ctx.needs_input_grad[1]:
+            Overlap.note_use((W,))
         x, W = x.contiguous(), W.detach().contiguous()
         ctx.save_for_backward(x, W)
         if engine != "tile":
@@ -755,6 +791,7 @@ class _DenseMmFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        Overlap.note_backward()
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]

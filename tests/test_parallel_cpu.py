@@ -182,3 +182,33 @@ def test_shard_balanced_same_molecules_even_atoms():
     # one rank: the identity
     one = PAR.shard_balanced(batches[:1], 0, 1)
     assert np.array_equal(one.adj, batches[0].adj) and np.array_equal(one.codes, batches[0].codes)
+
+
+def test_deferred_join_needs_a_single_gradient_producer():
+    """functional.Overlap.fresh: the join of a side-stream weight-gradient branch may be deferred to the end of the backward
+    pass only when autograd adopts the returned tensors untouched.  A parameter with TWO gradient producers (the attention
+    weights of a layer whose dense attention is also returned -- 'pool' read-out, models.py:104-106 -- or tied weights) is
+    summed by the engine when the second gradient arrives, so it must not be deferred.  Pure bookkeeping: CPU tensors."""
+    import torch
+    from eagcn_b200.functional import Overlap
+    a = torch.nn.Parameter(torch.zeros(3))
+    b = torch.nn.Parameter(torch.zeros(3))
+    c = torch.nn.Parameter(torch.zeros(3))
+    frozen = torch.nn.Parameter(torch.zeros(3), requires_grad=False)
+    Overlap._uses.clear(); Overlap._bwd_seen = False
+    with torch.no_grad():
+        assert not Overlap.fresh((a,))                       # never registered: not deferred
+        Overlap.note_use((a, b, frozen, None))
+        Overlap.note_use((b,))                               # b has a second producer (e.g. attention_dense)
+        assert Overlap.fresh((a, frozen, None))
+        assert not Overlap.fresh((a, b)) and not Overlap.fresh((b,))
+        a.grad = torch.zeros(3)                              # a gradient is already there: the engine will accumulate
+        assert not Overlap.fresh((a,))
+        a.grad = None
+        Overlap.note_backward()                              # a backward pass ran ...
+        Overlap.note_use((b, c))                             # ... the next forward starts counting afresh
+        assert Overlap.fresh((b, c)) and not Overlap.fresh((a,))
+        Overlap.note_use((c,))                               # two forward passes before one backward: both count
+        assert not Overlap.fresh((c,)) and Overlap.fresh((b,))
+    assert not Overlap.fresh((b,))                           # grad mode on (create_graph): never deferred
+    Overlap._uses.clear(); Overlap._bwd_seen = False
